@@ -1,0 +1,125 @@
+/* vsearch_b200.h -- C ABI of the B200-native index-scoring engine.
+ *
+ * The upstream project (jzhoubu/vsearch) is pure Python and has no FFI of its
+ * own; the narrowest seam is the `Index` class family in
+ * src/ir/retriever/index.py.  Each entry point below names the reference
+ * interface it replaces (paths relative to the upstream repo).  The Python
+ * mirror of those classes (vsearch_b200/index.py) binds this ABI with ctypes;
+ * INTEGRATION.md shows the stub a maintainer would add upstream.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *  - every function returns a vs_status (0 = OK) and never throws; the message
+ *    of the last failure on the calling thread is vs_last_error();
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the
+ *    functions do not synchronise it unless stated ("SYNC");
+ *  - pointers named d_* must be device pointers on the index's device; pointers
+ *    named hd_* may be host or device (the library checks);
+ *  - a handle may be used from one host thread at a time.
+ */
+#ifndef VSEARCH_B200_H
+#define VSEARCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VS_ABI_VERSION 1
+
+typedef enum {
+    VS_OK = 0,
+    VS_ERR_INVALID = 1,      /* bad argument (also: k > N, the reference's RuntimeError, index.py:92) */
+    VS_ERR_UNSUPPORTED = 2,  /* valid request this build cannot serve (e.g. V too large for shared memory) */
+    VS_ERR_CUDA = 3,         /* a CUDA runtime call failed; see vs_last_error() */
+    VS_ERR_NOMEM = 4
+} vs_status;
+
+typedef enum {
+    VS_F32 = 0, VS_F16 = 1, VS_BF16 = 2, VS_I32 = 3, VS_I64 = 4, VS_U16 = 5, VS_U32 = 6, VS_NONE = 7
+} vs_dtype;
+
+/* which kernel family serves vs_search on a sparse / binary index */
+typedef enum {
+    VS_MODE_AUTO = 0,     /* engine picks scan vs inverted from the query sparsity */
+    VS_MODE_SCAN = 1,     /* K1/K2: passage-major stream, query vector in shared memory */
+    VS_MODE_INVERTED = 2  /* K3: token-major posting lists of the query's non-zero tokens */
+} vs_mode;
+
+typedef struct vs_index vs_index; /* opaque; owns device memory */
+
+const char *vs_last_error(void);
+int vs_abi_version(void);
+
+/* ---- index construction --------------------------------------------------------------
+ * Replaces SparseIndex._scipy_csr_to_torch_csr + `.to(device)` (index.py:144-161,179) and
+ * Index.move_to_device (index.py:54-57): takes the CSR triple of the [N, V] index
+ * (crow: N+1 entries, col/val: nnz entries; hd_* = host or device memory) and builds the
+ * compact device format (uint16 columns in 16-byte chunks, optional values, per-warp
+ * stream partition).  val_dtype == VS_NONE (hd_val == NULL) builds the binary
+ * bag-of-token index (BoTIndex, index.py:205-218; all values 1).  store_dtype picks the
+ * on-device value type: VS_F32 / VS_F16 / VS_BF16 (ignored for binary).  SYNC. */
+int vs_index_create_csr(int device, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                        const void *hd_crow, int crow_dtype,   /* VS_I32 | VS_I64 */
+                        const void *hd_col, int col_dtype,     /* VS_I32 | VS_I64 */
+                        const void *hd_val, int val_dtype,     /* VS_F32 | VS_F16 | VS_BF16 | VS_NONE */
+                        int store_dtype, void *stream, vs_index **out);
+
+/* Dense index: `Index.vector` strided [N, D] (index.py:25-44,88-94).  Stored bf16 or f32. */
+int vs_index_create_dense(int device, int64_t n_rows, int64_t dim, const void *hd_x, int x_dtype,
+                          int64_t ld, int store_dtype, void *stream, vs_index **out);
+
+int vs_index_destroy(vs_index *idx);
+
+/* shape / layout queries (Index.__str__, index.py:117-126) */
+int vs_index_info(const vs_index *idx, int64_t *n_rows, int64_t *n_cols, int64_t *nnz,
+                  int *kind /* 0 dense, 1 sparse, 2 binary */, int *store_dtype, int64_t *device_bytes,
+                  int64_t *stream_bytes /* bytes one scan pass reads */);
+
+/* Export the index back to a CSR triple (for SparseIndex.save, index.py:181-202).
+ * d_crow int64[N+1], d_col int64[nnz], d_val float32[nnz] device buffers. */
+int vs_index_export_csr(const vs_index *idx, int64_t *d_crow, int64_t *d_col, float *d_val, void *stream);
+
+/* ---- search ---------------------------------------------------------------------------
+ * Replaces Index.search (index.py:88-94): scores = q @ vector.t(); scores.topk(k).
+ *   hd_q      [B, ldq] queries (host or device), q_dtype VS_F32 | VS_F16 | VS_BF16
+ *   k         1 <= k <= min(N, VS_MAX_K); k > N -> VS_ERR_INVALID (reference: RuntimeError)
+ *   d_ids     int64 [B, k]  out: passage ids + id_offset, ranked (score desc, id asc)
+ *   d_scores  float [B, k]  out: scores (fp32 accumulate)
+ *   score_round  VS_F32 none | VS_F16 | VS_BF16: round scores to that type BEFORE ranking,
+ *             mirroring `q.type(vector.dtype)` / scores in the index dtype (index.py:89)
+ *   d_workspace  >= vs_search_workspace_bytes(idx, B, k) bytes, 256-byte aligned
+ * The [B, N] score matrix is never written. */
+#define VS_MAX_K 2048
+size_t vs_search_workspace_bytes(const vs_index *idx, int64_t B, int k);
+int vs_search(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int k, int mode,
+              int score_round, int64_t id_offset, int64_t *d_ids, float *d_scores,
+              void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Same search, but returns the packed 64-bit rank keys (ordered score bits << 32 | ~global id),
+ * sorted descending: what each rank contributes to the one all-gather of the row-sharded path
+ * (no reference counterpart: upstream searches one device, index.py:179). */
+int vs_search_keys(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int k, int mode,
+                   int score_round, int64_t id_offset, uint64_t *d_keys,
+                   void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Diagnostic: the dense score matrix itself (upstream index.py:91), d_scores_full float [B, N].
+ * Not used by the search path; lets tests separate scoring errors from selection errors. */
+int vs_scores(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int score_round,
+              float *d_scores_full, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Merge P candidate lists per query (e.g. the all-gathered [P, B, k] keys of P shards) into the
+ * global top-k.  d_keys_in[p * stride_p + b * stride_b + j], j < k_in. */
+int vs_merge_keys(int device, const uint64_t *d_keys_in, int64_t P, int64_t stride_p, int64_t stride_b,
+                  int64_t B, int k_in, int k_out, int64_t *d_ids, float *d_scores, void *stream);
+
+/* timing hook for bench.py: device time (ms) of the scan/score kernel of the last vs_search on this
+ * handle, measured with CUDA events on the launching stream.  SYNC (waits for those events). */
+int vs_last_kernel_ms(const vs_index *idx, float *ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSEARCH_B200_H */

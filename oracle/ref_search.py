@@ -165,3 +165,33 @@ def compare_results(ours: SearchResults, ref_scores_mat: torch.Tensor, k: int,
         if not bool(((a - g).abs() <= 4 * rtol * a.abs().clamp_min(1e-30)).all()):
             return "ids differ outside near-tie runs"
     return None
+
+
+# ---------------------------------------------------------------------------
+# rank-key wire format of the sharded path (include/vsearch_b200.h, vs_search_keys):
+# key = ordered(score bits) << 32 | ~uint32(global id), carried as int64 bit patterns.
+# ---------------------------------------------------------------------------
+def pack_keys(ids: torch.Tensor, scores: torch.Tensor) -> torch.Tensor:
+    s = (scores.to(torch.float32) + 0.0).contiguous().numpy().view(np.uint32).astype(np.uint64)
+    neg = (s & np.uint64(0x80000000)) != 0
+    ordered = np.where(neg, (~s) & np.uint64(0xFFFFFFFF), s | np.uint64(0x80000000))
+    low = (~ids.numpy().astype(np.uint64)) & np.uint64(0xFFFFFFFF)
+    return torch.from_numpy(((ordered << np.uint64(32)) | low).view(np.int64).copy())
+
+
+def unpack_keys(keys: torch.Tensor):
+    u = keys.contiguous().numpy().view(np.uint64)
+    hi = (u >> np.uint64(32)).astype(np.uint32)
+    bits = np.where(hi & np.uint32(0x80000000), hi & np.uint32(0x7FFFFFFF), ~hi)
+    ids = ((~u) & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    return torch.from_numpy(ids), torch.from_numpy(bits.astype(np.uint32).view(np.float32).copy())
+
+
+def merge_keys_oracle(gathered: torch.Tensor, k: int):
+    """[P, B, k_in] keys -> (ids, scores) [B, k]: sort keys descending as unsigned, drop empty (0) keys."""
+    P, B, kin = gathered.shape
+    u = gathered.permute(1, 0, 2).reshape(B, P * kin).contiguous().numpy().view(np.uint64)
+    order = np.argsort(u, axis=1, kind="stable")[:, ::-1][:, :k]
+    top = np.take_along_axis(u, order, axis=1)
+    ids, sc = unpack_keys(torch.from_numpy(top.view(np.int64).copy()))
+    return ids, sc

@@ -1,0 +1,226 @@
+"""Parity of the CUDA path (through the C ABI, via the Python mirror of the reference classes) against
+the oracle: golden vectors from the reference, seeded synthetic indices, and the reference's edge cases.
+Bit-exact ids/scores on dyadic-grid data; 1e-5 relative (fp32) on continuous data."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_search
+from tests.util import V, golden_search_cases, load_golden, sparse_queries, stratified_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(cls_name, crow, col, val, shape, device="cuda:0", dtype=None):
+    import vsearch_b200 as vs
+
+    cls = getattr(vs, cls_name)
+    idx = cls()
+    v = torch.as_tensor(val)
+    if dtype is not None:
+        v = v.to(dtype)
+    idx.vector = ref_search.torch_csr(torch.as_tensor(crow).to(torch.int64), torch.as_tensor(col).to(torch.int64), v, shape)
+    idx.move_to_device(device)
+    return idx
+
+
+@pytest.mark.parametrize("name", golden_search_cases("csr"))
+def test_golden_csr(name, cuda_device):
+    z = load_golden(name)
+    cls = "BoTIndex" if bool(z["binary"]) else "SparseIndex"
+    idx = _mk(cls, z["crow"], z["col"], z["val"], z["shape"])
+    q = torch.from_numpy(z["q"])
+    ref = torch.from_numpy(z["ref_scores"])
+    # scoring alone (index.py:91)
+    sc = idx._require_engine().scores(q.reshape(-1, q.shape[-1])).cpu().reshape(ref.shape)
+    exact = "cont" not in name
+    if exact:
+        assert torch.equal(sc, ref + 0.0)
+    else:
+        torch.testing.assert_close(sc, ref, rtol=1e-5, atol=1e-6)
+    # scoring + selection (index.py:91-93)
+    res = idx.search(q, z["k"])
+    assert res.ids.dtype == torch.int64 and res.ids.is_cuda and tuple(res.ids.shape) == tuple(z["ref_topk_ids"].shape)
+    msg = ref_search.compare_results(res, ref, z["k"], exact=exact)
+    assert msg is None, msg
+    if exact:  # the reference's own top-k VALUES (tie order only affects ids)
+        assert torch.equal(res.scores.cpu(), torch.from_numpy(z["ref_topk_scores"]) + 0.0)
+
+
+@pytest.mark.parametrize("n,m,B,k,binary", [
+    (200_000, 120, 8, 100, True),     # config-2 shape, one shard slice
+    (100_000, 256, 8, 100, False),    # config-1 shape
+    (60_000, 256, 3, 1000, False),    # config-3 k
+    (50_000, 120, 5, 1000, True),
+])
+def test_synthetic_grid_exact(n, m, B, k, binary, cuda_device):
+    crow, col, val = stratified_csr(n, V, m, seed=11, grid=True, binary=binary, jitter=17)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    idx = _mk("BoTIndex" if binary else "SparseIndex", crow, col, val, (n, V))
+    q = sparse_queries(B, V, 64, seed=5)
+    res = idx.search(q, k)
+    msg = ref_search.compare_results(res, ref_search.ref_scores(q, X), k, exact=True)
+    assert msg is None, msg
+
+
+def test_synthetic_continuous_tolerance(cuda_device):
+    n, m = 80_000, 256
+    crow, col, val = stratified_csr(n, V, m, seed=3, grid=False)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    idx = _mk("SparseIndex", crow, col, val, (n, V))
+    q = sparse_queries(6, V, 128, seed=9, grid=False)
+    res = idx.search(q, 100)
+    msg = ref_search.compare_results(res, ref_search.ref_scores(q, X), 100, rtol=1e-5, exact=False)
+    assert msg is None, msg
+
+
+def test_dense_query_768_nnz(cuda_device):
+    """the reference's default a=768 activations (retriever.py:134)"""
+    n, m = 50_000, 120
+    crow, col, val = stratified_csr(n, V, m, seed=21, grid=True, binary=True)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    idx = _mk("BoTIndex", crow, col, val, (n, V))
+    q = sparse_queries(4, V, 768, seed=2)
+    res = idx.search(q, 100)
+    assert ref_search.compare_results(res, ref_search.ref_scores(q, X), 100, exact=True) is None
+
+
+def test_edge_cases(cuda_device):
+    n, v = 300, 1000
+    crow, col, val = stratified_csr(n, v, 20, seed=4, grid=True, jitter=20)  # includes empty rows
+    X = ref_search.torch_csr(crow, col, val, (n, v))
+    idx = _mk("SparseIndex", crow, col, val, (n, v))
+    q = sparse_queries(3, v, 30, seed=6, neg=True)
+    q[1] = 0  # all-zero query -> ids 0..k-1
+    ref = ref_search.ref_scores(q, X)
+    for k in (1, 5, 100, n):
+        res = idx.search(q, k)
+        msg = ref_search.compare_results(res, ref, k, exact=True)
+        assert msg is None, f"k={k}: {msg}"
+    assert idx.search(q, 7).ids[1].tolist() == list(range(7))
+    with pytest.raises(RuntimeError):  # the reference raises RuntimeError for k > N (index.py:92)
+        idx.search(q, n + 1)
+    # 1-D query -> [k]
+    r1 = idx.search(q[0], 9)
+    assert tuple(r1.ids.shape) == (9,) and torch.equal(r1.ids, idx.search(q[:1], 9).ids[0])
+    # numpy / half / bf16 / device queries
+    rh = idx.search(q.to(torch.float16).cuda(), 5)
+    assert ref_search.compare_results(rh, ref_search.ref_scores(q.half().float(), X), 5, exact=True) is None
+
+
+def test_negative_values_untouched_rows_outrank(cuda_device):
+    n, v = 5000, 2000
+    crow, col, val = stratified_csr(n, v, 16, seed=8, grid=True)
+    val = -val
+    X = ref_search.torch_csr(crow, col, val, (n, v))
+    idx = _mk("SparseIndex", crow, col, val, (n, v))
+    q = sparse_queries(4, v, 200, seed=1)
+    res = idx.search(q, 50)
+    assert ref_search.compare_results(res, ref_search.ref_scores(q, X), 50, exact=True) is None
+    assert float(res.scores.max()) <= 0.0
+
+
+def test_heavy_ties_binary(cuda_device):
+    """binary index x constant-valued queries: scores are small integers, thousands of exact ties that
+    cross warp, CTA and staging-buffer boundaries; ids must still be (score desc, id asc)."""
+    n = 120_000
+    crow, col, val = stratified_csr(n, V, 60, seed=13, binary=True, jitter=30)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    idx = _mk("BoTIndex", crow, col, val, (n, V))
+    q = (sparse_queries(6, V, 512, seed=3) != 0).float()
+    for k in (10, 100, 1000):
+        res = idx.search(q, k)
+        msg = ref_search.compare_results(res, ref_search.ref_scores(q, X), k, exact=True)
+        assert msg is None, f"k={k}: {msg}"
+
+
+def test_ascending_scores_worst_case_for_threshold(cuda_device):
+    """scores increase with the row id: every row beats the running threshold -> exercises the in-kernel
+    prune path continuously."""
+    n, v = 40_000, 64
+    crow = torch.arange(n + 1, dtype=torch.int64)
+    col = torch.zeros(n, dtype=torch.int64)
+    val = torch.arange(n, dtype=torch.float32) / 8.0
+    X = ref_search.torch_csr(crow, col, val, (n, v))
+    idx = _mk("SparseIndex", crow, col, val, (n, v))
+    q = torch.zeros(2, v)
+    q[0, 0], q[1, 0] = 1.0, -1.0
+    for k in (100, 1500):
+        res = idx.search(q, k)
+        assert ref_search.compare_results(res, ref_search.ref_scores(q, X), k, exact=True) is None
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_half_precision_values(dtype, cuda_device):
+    """Parity rule 3: quantise values and queries to the storage dtype, feed those numbers to the fp32
+    reference; our scores are then rounded to the index dtype (index.py:89 dtype contract)."""
+    n, m = 30_000, 64
+    crow, col, val = stratified_csr(n, V, m, seed=17, grid=False)
+    idx = _mk("SparseIndex", crow, col, val, (n, V), dtype=dtype)
+    q = sparse_queries(4, V, 64, seed=2, grid=False)
+    vq, qq = ref_search.quantize_like(val, dtype), ref_search.quantize_like(q, dtype)
+    ref = ref_search.ref_scores(qq, ref_search.torch_csr(crow, col, vq, (n, V)))
+    # (a) fp32 accumulate over the quantised numbers: within 1e-5 of the fp32 reference on the same numbers
+    from vsearch_b200 import _native as nat
+    ids, sc = idx._require_engine().search(qq, 20, mode="scan", score_round=nat.VS_F32)
+    msg = ref_search.compare_results(ref_search.SearchResults(ids, sc), ref, 20, rtol=1e-5, exact=False)
+    assert msg is None, msg
+    # (b) the public call returns scores in the index dtype (index.py:89): equal to the reference's fp32
+    # scores rounded to that dtype, up to one unit in the last place (2^-8 bf16 / 2^-11 fp16 relative)
+    res = idx.search(q, 20)
+    assert res.scores.dtype == dtype
+    canon = ref_search.canonical_topk(ref, 20)
+    ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    torch.testing.assert_close(res.scores.float().cpu(), canon.scores.to(dtype).float(), rtol=ulp, atol=1e-6)
+
+
+def test_export_roundtrip_and_save(tmp_path, cuda_device):
+    import scipy.sparse as sp
+
+    import vsearch_b200 as vs
+
+    n, v = 2000, 3000
+    crow, col, val = stratified_csr(n, v, 24, seed=5, grid=True, jitter=24)
+    idx = _mk("SparseIndex", crow, col, val, (n, v))
+    c2, j2, v2 = idx._require_engine().export_csr()
+    assert torch.equal(c2.cpu(), crow) and torch.equal(j2.cpu(), col) and torch.equal(v2.cpu(), val)
+    p = str(tmp_path / "idx.npz")
+    idx.save(p)
+    m = sp.load_npz(p)  # scipy must be able to read what we write
+    assert m.shape == (n, v) and np.array_equal(m.indptr, crow.numpy()) and np.array_equal(m.data, val.numpy())
+    r = vs.Retriever(device="cuda:0")
+    r.load_index(p, index_type="sparse")
+    q = sparse_queries(2, v, 40, seed=1)
+    a, b = idx.search(q, 10), r.retrieve(q, k=10)
+    assert torch.equal(a.ids, b.ids)
+
+
+def test_virtual_shards_merge(cuda_device):
+    """Row-split on one GPU + the same merge kernel = the multi-GPU path without a cluster."""
+    import vsearch_b200 as vs
+
+    n, W, k = 90_001, 4, 100
+    crow, col, val = stratified_csr(n, V, 48, seed=19, binary=True, jitter=10)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    q = (sparse_queries(5, V, 300, seed=4) != 0).float()  # heavy ties across shard boundaries
+    keys = []
+    for r in range(W):
+        lo, hi = vs.row_partition(n, W, r)
+        c = crow[lo:hi + 1] - crow[lo]
+        sl = slice(int(crow[lo]), int(crow[hi]))
+        shard = _mk("BoTIndex", c, col[sl], val[sl], (hi - lo, V))
+        keys.append(shard.search_keys(q, k, id_offset=lo))
+    ids, scores = vs.merge_keys(torch.stack(keys), k)
+    msg = ref_search.compare_results(ref_search.SearchResults(ids, scores), ref_search.ref_scores(q, X), k, exact=True)
+    assert msg is None, msg
+
+
+def test_large_batch_chunks(cuda_device):
+    """B > the internal 1024-query chunk."""
+    n, v = 3000, 512
+    crow, col, val = stratified_csr(n, v, 16, seed=2, grid=True)
+    X = ref_search.torch_csr(crow, col, val, (n, v))
+    idx = _mk("SparseIndex", crow, col, val, (n, v))
+    q = sparse_queries(1100, v, 12, seed=3)
+    res = idx.search(q, 10)
+    assert ref_search.compare_results(res, ref_search.ref_scores(q, X), 10, exact=True) is None

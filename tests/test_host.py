@@ -1,0 +1,140 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol, the
+.npz loader/saver matches what the reference reads/writes, the Python mirror keeps the reference's
+API contracts, and the product path refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+import zipfile
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import vsearch_b200 as vs
+from tests.util import GOLDEN
+from vsearch_b200 import _native, npz_io
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "vsearch_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(vs_[a-z_0-9]+)\s*\(", body))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/vsearch_b200.h but not exported"
+    assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
+    assert lib.vs_abi_version() == 1
+
+
+def test_abi_argument_validation_without_gpu():
+    """No compute: NULL / bad arguments are rejected before any CUDA call."""
+    lib = _native.LIB
+    out = ctypes.c_void_p()
+    rc = lib.vs_index_create_csr(0, 10, 70000, 0, None, _native.VS_I64, None, _native.VS_I64, None, _native.VS_NONE,
+                                 _native.VS_NONE, None, ctypes.byref(out))
+    assert rc == _native.VS_ERR_UNSUPPORTED and "uint16" in _native.last_error()
+    rc = lib.vs_index_create_csr(0, 10, 100, 0, None, _native.VS_F32, None, _native.VS_I64, None, _native.VS_NONE,
+                                 _native.VS_NONE, None, ctypes.byref(out))
+    assert rc == _native.VS_ERR_INVALID
+    assert lib.vs_index_destroy(None) == 0
+    with pytest.raises(ValueError):
+        _native.check(rc)
+
+
+@pytest.mark.parametrize("shift", [0, 100])
+def test_loader_matches_reference_loader(shift):
+    """sorted-glob order (index10 before index2), column shift, row concatenation (index.py:172-175)."""
+    z = np.load(os.path.join(GOLDEN, f"load_shift{shift}.npz"))
+    idx = vs.SparseIndex(os.path.join(GOLDEN, "shards", "index*.npz"), None, fp16=False, device="cpu", shift=shift)
+    v = idx.vector
+    assert tuple(v.shape) == tuple(z["shape"])
+    assert np.array_equal(v.crow_indices().numpy(), z["crow"])
+    assert np.array_equal(v.col_indices().numpy(), z["col"])
+    assert np.array_equal(v.values().numpy(), z["val"])
+    assert v.values().dtype == torch.float32
+    assert len(idx) == 0 and "SparseIndex" in str(idx) and "torch.sparse_csr" in str(idx)
+
+
+def test_loader_fp16_default_like_reference():
+    idx = vs.SparseIndex(os.path.join(GOLDEN, "shards", "index1.npz"))  # fp16=True is the upstream default
+    assert idx.vector.values().dtype == torch.float16
+
+
+def test_reads_file_saved_by_reference_and_writes_same_layout(tmp_path):
+    ref_file = os.path.join(GOLDEN, "saved_by_reference.npz")
+    idx = vs.SparseIndex(ref_file, None, fp16=False)
+    src = sp.load_npz(os.path.join(GOLDEN, "shards", "index1.npz"))
+    assert np.array_equal(idx.vector.values().numpy(), src.data)
+    assert np.array_equal(idx.vector.col_indices().numpy(), src.indices)
+    out = str(tmp_path / "mine.npz")
+    idx.save(out)
+    with zipfile.ZipFile(ref_file) as a, zipfile.ZipFile(out) as b:
+        assert [i.filename for i in a.infolist()] == [i.filename for i in b.infolist()]
+        assert all(i.compress_type == zipfile.ZIP_DEFLATED for i in b.infolist())
+    za, zb = np.load(ref_file), np.load(out)
+    for k in za.files:
+        assert za[k].dtype == zb[k].dtype or k in ("indices", "indptr"), k
+        assert np.array_equal(za[k], zb[k]), k
+    m = sp.load_npz(out)  # scipy (what the reference's loader calls) reads our file
+    assert (m != src).nnz == 0
+
+
+def test_fp16_npz_roundtrip(tmp_path):
+    """fp16 data members (BoT indices built in memory upstream are fp16, retriever.py:232)."""
+    p = str(tmp_path / "h.npz")
+    npz_io.save_csr_npz(p, np.array([0, 2, 3]), np.array([1, 5, 2]), np.array([1, 1, 1], dtype=np.float16), (2, 9))
+    idx = vs.BoTIndex(p, None, fp16=True)
+    assert idx.vector.values().dtype == torch.float16 and tuple(idx.vector.shape) == (2, 9)
+
+
+def test_index_type_contract_and_retriever_dispatch(tmp_path):
+    assert [t.value for t in vs.IndexType] == ["dense", "sparse", "bag_of_token"]
+    r = vs.Retriever(device="cpu")
+    with pytest.raises(ValueError):
+        r.load_index("foo.bin")
+    with pytest.raises(TypeError):
+        r.load_index("foo.npz", index_type=3)
+    with pytest.raises(ValueError):
+        r.load_index("foo.npz", index_type="nope")
+    with pytest.raises(TypeError):
+        r.build_index(vectors=torch.zeros(2, 3), index_type=7)
+    r.load_index(os.path.join(GOLDEN, "shards", "index0.npz"))
+    assert r.index_type == vs.IndexType.SPARSE and isinstance(r.index, vs.SparseIndex)
+    r.load_index(os.path.join(GOLDEN, "shards", "index0.npz"), index_type="BAG_OF_TOKEN")
+    assert isinstance(r.index, vs.BoTIndex)
+    assert torch.equal(r.process_query(np.ones((2, 3), dtype=np.float64)), torch.ones(2, 3))
+    t = torch.rand(2, 3)
+    assert r.process_query(t) is t
+    with pytest.raises(NotImplementedError):
+        r.process_query(3.5)
+
+
+def test_no_cpu_fallback():
+    idx = vs.SparseIndex(os.path.join(GOLDEN, "shards", "index0.npz"), None, fp16=False, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU search path"):
+        idx.search(torch.zeros(1, 700), 3)
+    with pytest.raises(RuntimeError):
+        vs.merge_keys(torch.zeros(2, 1, 3, dtype=torch.int64), 3)
+    assert "oracle" not in open(os.path.join(ROOT, "vsearch_b200", "index.py")).read().replace("oracle merge", "")
+
+
+def test_text_store_and_low_memory(tmp_path):
+    p = tmp_path / "texts.jsonl"
+    texts = ["alpha", "béta ünïcode", "gamma"]
+    p.write_text("\n".join(__import__("json").dumps(t) for t in texts) + "\n", encoding="utf-8")
+    a = vs.Index(None, str(p))
+    b = vs.Index(None, str(p), low_memory=True)
+    assert len(a) == 3 and [a.get_sample(i) for i in range(3)] == texts
+    assert [b.get_sample(i) for i in range(3)] == texts
+
+
+def test_row_partition_covers_rows():
+    for n, w in [(21015324, 8), (10, 4), (3, 8), (100, 1)]:
+        spans = [vs.row_partition(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+    assert vs.row_partition(21015324, 8, 0) == (0, 2626916)

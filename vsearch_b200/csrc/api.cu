@@ -1,0 +1,270 @@
+// api.cu -- the extern "C" boundary declared in include/vsearch_b200.h.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "index.cuh"
+
+namespace vs {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// scan.cu / merge.cu
+size_t scan_smem_bytes(int vpad, int cap);
+int scan_cap_for_k(int k);
+int launch_prep_query(const void *d_q, int q_dtype, int64_t B, int64_t ldq, int64_t n_cols, int vpad, int round_mode,
+                      float *d_out, cudaStream_t st);
+int launch_scan(const vs_index *idx, const float *d_qprep, int vpad, int64_t B, int k, int score_round,
+                uint64_t *d_cand, float *d_scores_out, cudaStream_t st);
+int launch_merge(const uint64_t *d_in, int64_t P, int64_t stride_p, int64_t stride_b, int64_t B, int k_in, int k_out,
+                 int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, cudaStream_t st);
+
+static size_t dtype_size(int dt) {
+    switch (dt) {
+        case VS_F32: case VS_I32: case VS_U32: return 4;
+        case VS_F16: case VS_BF16: case VS_U16: return 2;
+        case VS_I64: return 8;
+        default: return 0;
+    }
+}
+
+static bool is_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// RAII device staging copy of a host buffer
+struct Staged {
+    const void *ptr = nullptr;
+    void *owned = nullptr;
+    ~Staged() { if (owned) cudaFree(owned); }
+    int init(const void *hd, size_t bytes, cudaStream_t st) {
+        if (hd == nullptr || bytes == 0 || is_device_ptr(hd)) { ptr = hd; return VS_OK; }
+        VS_CUDA(cudaMalloc(&owned, bytes));
+        VS_CUDA(cudaMemcpyAsync(owned, hd, bytes, cudaMemcpyHostToDevice, st));
+        ptr = owned;
+        return VS_OK;
+    }
+};
+
+static inline int vpad_for(int64_t n_cols) { return (int)(((n_cols + 1) + 3) / 4 * 4); }
+
+// workspace layout for one query chunk of Bc queries
+struct Workspace {
+    float *qprep;      // [Bc, vpad]
+    uint64_t *cand;    // [Bc, n_ctas, k]
+    size_t bytes;
+};
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+static Workspace carve(const vs_index *idx, void *base, int64_t Bc, int k) {
+    Workspace w;
+    size_t q_bytes = align256((size_t)Bc * vpad_for(idx->n_cols) * 4);
+    size_t c_bytes = align256((size_t)Bc * idx->n_ctas * (size_t)k * 8);
+    w.qprep = (float *)base;
+    w.cand = (uint64_t *)((uint8_t *)base + q_bytes);
+    w.bytes = q_bytes + c_bytes;
+    return w;
+}
+constexpr int64_t kQueryChunk = 1024;
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" {
+
+const char *vs_last_error(void) { return vs::g_err; }
+int vs_abi_version(void) { return VS_ABI_VERSION; }
+
+int vs_index_create_csr(int device, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *hd_crow, int crow_dtype,
+                        const void *hd_col, int col_dtype, const void *hd_val, int val_dtype, int store_dtype,
+                        void *stream, vs_index **out) {
+    VS_REQUIRE(out != nullptr, VS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    VS_REQUIRE(n_rows >= 0 && n_cols >= 1 && nnz >= 0, VS_ERR_INVALID, "bad shape");
+    VS_REQUIRE(n_cols <= 65535, VS_ERR_UNSUPPORTED, "n_cols=%lld does not fit the uint16 column format", (long long)n_cols);
+    VS_REQUIRE(n_rows < 0xffffffffll, VS_ERR_UNSUPPORTED, "n_rows must be < 2^32 - 1 per shard");
+    VS_REQUIRE(crow_dtype == VS_I32 || crow_dtype == VS_I64, VS_ERR_INVALID, "crow dtype must be int32/int64");
+    VS_REQUIRE(col_dtype == VS_I32 || col_dtype == VS_I64, VS_ERR_INVALID, "col dtype must be int32/int64");
+    const bool binary = (hd_val == nullptr || val_dtype == VS_NONE);
+    if (!binary) {
+        VS_REQUIRE(val_dtype == VS_F32 || val_dtype == VS_F16 || val_dtype == VS_BF16, VS_ERR_INVALID, "bad value dtype");
+        VS_REQUIRE(store_dtype == VS_F32 || store_dtype == VS_F16 || store_dtype == VS_BF16, VS_ERR_INVALID, "bad store dtype");
+    }
+    VS_REQUIRE(hd_crow != nullptr && (nnz == 0 || hd_col != nullptr), VS_ERR_INVALID, "NULL CSR arrays");
+    VS_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+
+    vs_index *idx = new (std::nothrow) vs_index();
+    VS_REQUIRE(idx != nullptr, VS_ERR_NOMEM, "out of host memory");
+    idx->device = device;
+    idx->kind = binary ? 2 : 1;
+    idx->store_dtype = binary ? VS_NONE : store_dtype;
+    idx->n_rows = n_rows; idx->n_cols = n_cols; idx->nnz = nnz;
+
+    int rc;
+    {
+        Staged s_crow, s_col, s_val;
+        rc = s_crow.init(hd_crow, (size_t)(n_rows + 1) * dtype_size(crow_dtype), st);
+        if (rc == VS_OK) rc = s_col.init(hd_col, (size_t)nnz * dtype_size(col_dtype), st);
+        if (rc == VS_OK && !binary) rc = s_val.init(hd_val, (size_t)nnz * dtype_size(val_dtype), st);
+        if (rc == VS_OK) rc = build_ws_index(idx, s_crow.ptr, crow_dtype, s_col.ptr, col_dtype, binary ? nullptr : s_val.ptr,
+                                             binary ? VS_NONE : val_dtype, st);
+        cudaStreamSynchronize(st);
+    }
+    if (rc == VS_OK) {
+        if (cudaEventCreate(&idx->ev0) != cudaSuccess || cudaEventCreate(&idx->ev1) != cudaSuccess) {
+            set_error("cudaEventCreate failed");
+            rc = VS_ERR_CUDA;
+        }
+    }
+    if (rc != VS_OK) { vs_index_destroy(idx); return rc; }
+    *out = idx;
+    return VS_OK;
+}
+
+int vs_index_create_dense(int device, int64_t n_rows, int64_t dim, const void *hd_x, int x_dtype, int64_t ld,
+                          int store_dtype, void *stream, vs_index **out) {
+    (void)device; (void)n_rows; (void)dim; (void)hd_x; (void)x_dtype; (void)ld; (void)store_dtype; (void)stream;
+    if (out) *out = nullptr;
+    vs::set_error("dense index (K4 tcgen05 GEMM + fused top-k) is not built yet");
+    return VS_ERR_UNSUPPORTED;
+}
+
+int vs_index_destroy(vs_index *idx) {
+    if (!idx) return VS_OK;
+    cudaSetDevice(idx->device);
+    cudaFree(idx->cols); cudaFree(idx->vals); cudaFree(idx->tails);
+    cudaFree(idx->part_win_begin); cudaFree(idx->part_row_begin); cudaFree(idx->row_chunk);
+    cudaFree(idx->dense);
+    if (idx->ev0) cudaEventDestroy(idx->ev0);
+    if (idx->ev1) cudaEventDestroy(idx->ev1);
+    delete idx;
+    return VS_OK;
+}
+
+int vs_index_info(const vs_index *idx, int64_t *n_rows, int64_t *n_cols, int64_t *nnz, int *kind, int *store_dtype,
+                  int64_t *device_bytes, int64_t *stream_bytes) {
+    VS_REQUIRE(idx != nullptr, VS_ERR_INVALID, "index is NULL");
+    if (n_rows) *n_rows = idx->n_rows;
+    if (n_cols) *n_cols = idx->n_cols;
+    if (nnz) *nnz = idx->nnz;
+    if (kind) *kind = idx->kind;
+    if (store_dtype) *store_dtype = idx->store_dtype;
+    if (device_bytes) *device_bytes = idx->device_bytes;
+    if (stream_bytes) *stream_bytes = idx->stream_bytes;
+    return VS_OK;
+}
+
+int vs_index_export_csr(const vs_index *idx, int64_t *d_crow, int64_t *d_col, float *d_val, void *stream) {
+    VS_REQUIRE(idx != nullptr && idx->kind != 0, VS_ERR_INVALID, "export needs a sparse/binary index");
+    VS_CUDA(cudaSetDevice(idx->device));
+    return export_ws_csr(idx, d_crow, d_col, d_val, (cudaStream_t)stream);
+}
+
+size_t vs_search_workspace_bytes(const vs_index *idx, int64_t B, int k) {
+    if (!idx || B <= 0 || k <= 0) return 256;
+    int64_t Bc = B < kQueryChunk ? B : kQueryChunk;
+    return carve(idx, nullptr, Bc, k).bytes + 256;
+}
+
+static int search_impl(const vs_index *cidx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int k, int mode,
+                       int score_round, int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys,
+                       float *d_scores_full, void *d_workspace, size_t workspace_bytes, void *stream) {
+    vs_index *idx = const_cast<vs_index *>(cidx);
+    VS_REQUIRE(idx != nullptr, VS_ERR_INVALID, "index is NULL");
+    VS_REQUIRE(idx->kind == 1 || idx->kind == 2, VS_ERR_UNSUPPORTED, "dense search is not built yet");
+    VS_REQUIRE(B >= 0 && ldq >= idx->n_cols, VS_ERR_INVALID, "query leading dimension %lld < n_cols %lld", (long long)ldq,
+               (long long)idx->n_cols);
+    VS_REQUIRE(q_dtype == VS_F32 || q_dtype == VS_F16 || q_dtype == VS_BF16, VS_ERR_INVALID, "bad query dtype");
+    VS_REQUIRE(k >= 1, VS_ERR_INVALID, "k must be >= 1");
+    VS_REQUIRE((int64_t)k <= idx->n_rows, VS_ERR_INVALID, "selected index k out of range (k=%d > N=%lld)", k,
+               (long long)idx->n_rows);
+    VS_REQUIRE(k <= VS_MAX_K, VS_ERR_UNSUPPORTED, "k=%d > VS_MAX_K=%d", k, VS_MAX_K);
+    VS_REQUIRE(mode == VS_MODE_AUTO || mode == VS_MODE_SCAN, VS_ERR_UNSUPPORTED, "inverted-list mode is not built yet");
+    VS_REQUIRE(score_round == VS_F32 || score_round == VS_F16 || score_round == VS_BF16, VS_ERR_INVALID, "bad score_round");
+    VS_REQUIRE(workspace_bytes >= vs_search_workspace_bytes(idx, B, k), VS_ERR_INVALID, "workspace too small");
+    VS_REQUIRE(idx->n_rows + id_offset < 0xffffffffll && id_offset >= 0, VS_ERR_UNSUPPORTED, "global ids must fit 32 bits");
+    if (B == 0) return VS_OK;
+    VS_CUDA(cudaSetDevice(idx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vpad = vpad_for(idx->n_cols);
+    void *ws_base = (void *)(((uintptr_t)d_workspace + 255) / 256 * 256);
+
+    const bool q_on_device = is_device_ptr(hd_q);
+    idx->last_launches = 0;
+    idx->timed = false;
+    for (int64_t b0 = 0; b0 < B; b0 += kQueryChunk) {
+        const int64_t Bc = (B - b0) < kQueryChunk ? (B - b0) : kQueryChunk;
+        Workspace w = carve(idx, ws_base, Bc, k);
+        const uint8_t *qsrc = (const uint8_t *)hd_q + (size_t)b0 * ldq * dtype_size(q_dtype);
+        Staged sq;
+        if (!q_on_device) { int rc = sq.init(qsrc, (size_t)Bc * ldq * dtype_size(q_dtype), st); if (rc) return rc; }
+        else sq.ptr = qsrc;
+        int rc = launch_prep_query(sq.ptr, q_dtype, Bc, ldq, idx->n_cols, vpad, score_round, w.qprep, st);
+        if (rc) return rc;
+        if (b0 == 0) VS_CUDA(cudaEventRecord(idx->ev0, st));
+        rc = launch_scan(idx, w.qprep, vpad, Bc, k, score_round, w.cand,
+                         d_scores_full ? d_scores_full + (size_t)b0 * idx->n_rows : nullptr, st);
+        if (rc) return rc;
+        idx->last_launches += 1;
+        if (b0 + kQueryChunk >= B) { VS_CUDA(cudaEventRecord(idx->ev1, st)); idx->timed = (B <= kQueryChunk); }
+        rc = launch_merge(w.cand, idx->n_ctas, k, (int64_t)idx->n_ctas * k, Bc, k, k, id_offset,
+                          d_ids ? d_ids + b0 * k : nullptr, d_scores ? d_scores + b0 * k : nullptr,
+                          d_keys ? d_keys + b0 * k : nullptr, st);
+        if (rc) return rc;
+        if (!q_on_device) VS_CUDA(cudaStreamSynchronize(st));  // staging buffer is freed at scope exit
+    }
+    return VS_OK;
+}
+
+int vs_search(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int k, int mode,
+              int score_round, int64_t id_offset, int64_t *d_ids, float *d_scores, void *d_workspace,
+              size_t workspace_bytes, void *stream) {
+    VS_REQUIRE(d_ids != nullptr && d_scores != nullptr, VS_ERR_INVALID, "output pointers are NULL");
+    return search_impl(idx, hd_q, q_dtype, B, ldq, k, mode, score_round, id_offset, d_ids, d_scores, nullptr, nullptr,
+                       d_workspace, workspace_bytes, stream);
+}
+
+int vs_search_keys(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int k, int mode,
+                   int score_round, int64_t id_offset, uint64_t *d_keys, void *d_workspace, size_t workspace_bytes,
+                   void *stream) {
+    VS_REQUIRE(d_keys != nullptr, VS_ERR_INVALID, "output pointer is NULL");
+    return search_impl(idx, hd_q, q_dtype, B, ldq, k, mode, score_round, id_offset, nullptr, nullptr, d_keys, nullptr,
+                       d_workspace, workspace_bytes, stream);
+}
+
+int vs_scores(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int score_round,
+              float *d_scores_full, void *d_workspace, size_t workspace_bytes, void *stream) {
+    VS_REQUIRE(d_scores_full != nullptr, VS_ERR_INVALID, "output pointer is NULL");
+    return search_impl(idx, hd_q, q_dtype, B, ldq, 1, VS_MODE_SCAN, score_round, 0, nullptr, nullptr, nullptr,
+                       d_scores_full, d_workspace, workspace_bytes, stream);
+}
+
+int vs_merge_keys(int device, const uint64_t *d_keys_in, int64_t P, int64_t stride_p, int64_t stride_b, int64_t B,
+                  int k_in, int k_out, int64_t *d_ids, float *d_scores, void *stream) {
+    VS_REQUIRE(d_keys_in != nullptr && d_ids != nullptr && d_scores != nullptr, VS_ERR_INVALID, "NULL pointer");
+    VS_REQUIRE(P >= 1 && k_in >= 1 && k_out >= 1 && B >= 0, VS_ERR_INVALID, "bad merge shape");
+    VS_CUDA(cudaSetDevice(device));
+    return launch_merge(d_keys_in, P, stride_p, stride_b, B, k_in, k_out, 0, d_ids, d_scores, nullptr,
+                        (cudaStream_t)stream);
+}
+
+int vs_last_kernel_ms(const vs_index *idx, float *ms, int *launches) {
+    VS_REQUIRE(idx != nullptr && ms != nullptr, VS_ERR_INVALID, "NULL pointer");
+    VS_REQUIRE(idx->timed, VS_ERR_INVALID, "no single-launch search has been timed on this handle");
+    VS_CUDA(cudaEventSynchronize(idx->ev1));
+    VS_CUDA(cudaEventElapsedTime(ms, idx->ev0, idx->ev1));
+    if (launches) *launches = idx->last_launches;
+    return VS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,344 @@
+// scan.cu -- K1 (valued CSR) / K2 (binary bag-of-token) passage-major scan with the top-k
+// fused in (K5), for sm_100a.  Replaces `torch.matmul(q, vector.t())` + `scores.topk(k)`
+// (upstream src/ir/retriever/index.py:91-92) for SparseIndex / BoTIndex.
+//
+// One persistent CTA per SM, 32 warps.  Per query ("pass"):
+//   1. the dense fp32 query vector (V+1 slots, slot V = 0 for padding) is pulled into shared
+//      memory with 1-D bulk TMA copies (cp.async.bulk + mbarrier);
+//   2. every warp streams ITS part of the WS index (index.cuh): one 512-byte window per step,
+//      16 bytes per lane, D windows in flight per warp (register ring) -- loads never depend on
+//      row pointers; each lane gathers q[col] for its 8 entries from shared memory;
+//   3. a segmented warp scan over the window's tail mask turns lane partials into row scores;
+//   4. rows whose rank key beats the CTA threshold go to a per-warp staging buffer, which is
+//      flushed under a shared-memory lock into the CTA candidate buffer; when that fills, the
+//      flushing warp alone radix-selects it down to k and raises the threshold while the other
+//      31 warps keep streaming;
+//   5. at the end of the pass the CTA selects its exact top-k and writes k keys to HBM.
+// The [B, N] score matrix is never written.  A second tiny kernel (merge.cu) merges the
+// per-CTA lists.
+#include "index.cuh"
+
+namespace vs {
+
+constexpr int kScanThreads = 1024;
+constexpr int kStage = 64;  // per-warp staging entries
+
+struct ScanParams {
+    const uint4 *cols;
+    const void *vals;
+    const uint32_t *tails;
+    const uint32_t *part_win_begin;
+    const uint32_t *part_row_begin;
+    const float *q;        // [B, vpad] prepared queries
+    uint64_t *cand;        // [B, n_ctas, k]
+    float *scores_out;     // optional [B, N] (diagnostic vs_scores path), else nullptr
+    int64_t n_rows;
+    int B;
+    int k;
+    int cap;               // CTA candidate buffer entries (>= k + kStage)
+    int vpad;              // floats per prepared query (multiple of 4, > V)
+    int score_round;
+    uint32_t sentinel;     // V | V << 16
+};
+
+// ---- per-chunk payload -----------------------------------------------------------------
+template <int VT> struct Chunk;
+template <> struct Chunk<0> { uint4 c; };
+template <> struct Chunk<1> { uint4 c; uint4 v0, v1; };
+template <> struct Chunk<2> { uint4 c; uint4 v; };
+template <> struct Chunk<3> { uint4 c; uint4 v; };
+
+template <int VT>
+__device__ __forceinline__ void load_chunk(Chunk<VT> &ch, const uint4 *cols, const void *vals, uint64_t chunk) {
+    ch.c = ldg_stream(cols + chunk);
+    if constexpr (VT == 1) {
+        const uint4 *v = (const uint4 *)vals + chunk * 2;
+        ch.v0 = ldg_stream(v);
+        ch.v1 = ldg_stream(v + 1);
+    } else if constexpr (VT >= 2) {
+        ch.v = ldg_stream((const uint4 *)vals + chunk);
+    }
+}
+
+template <int VT>
+__device__ __forceinline__ void sentinel_chunk(Chunk<VT> &ch, uint32_t s) {
+    ch.c = make_uint4(s, s, s, s);
+    if constexpr (VT == 1) { ch.v0 = make_uint4(0, 0, 0, 0); ch.v1 = make_uint4(0, 0, 0, 0); }
+    else if constexpr (VT >= 2) { ch.v = make_uint4(0, 0, 0, 0); }
+}
+
+__device__ __forceinline__ float half_lo(uint32_t x, int vt) {
+    if (vt == 2) return __half2float(__ushort_as_half((unsigned short)(x & 0xffffu)));
+    return __uint_as_float(x << 16);
+}
+__device__ __forceinline__ float half_hi(uint32_t x, int vt) {
+    if (vt == 2) return __half2float(__ushort_as_half((unsigned short)(x >> 16)));
+    return __uint_as_float(x & 0xffff0000u);
+}
+
+// sum over the chunk's 8 entries of q[col] (* val)
+template <int VT>
+__device__ __forceinline__ float chunk_dot(const Chunk<VT> &ch, const float *qs) {
+    const uint32_t w[4] = {ch.c.x, ch.c.y, ch.c.z, ch.c.w};
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        g[2 * i] = qs[w[i] & 0xffffu];
+        g[2 * i + 1] = qs[w[i] >> 16];
+    }
+    if constexpr (VT == 0) {
+        return ((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]));
+    } else if constexpr (VT == 1) {
+        const uint32_t v[8] = {ch.v0.x, ch.v0.y, ch.v0.z, ch.v0.w, ch.v1.x, ch.v1.y, ch.v1.z, ch.v1.w};
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a = fmaf(g[2 * i], __uint_as_float(v[2 * i]), a);
+            b = fmaf(g[2 * i + 1], __uint_as_float(v[2 * i + 1]), b);
+        }
+        return a + b;
+    } else {
+        const uint32_t v[4] = {ch.v.x, ch.v.y, ch.v.z, ch.v.w};
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a = fmaf(g[2 * i], half_lo(v[i], VT), a);
+            b = fmaf(g[2 * i + 1], half_hi(v[i], VT), b);
+        }
+        return a + b;
+    }
+}
+
+// ---- candidate buffer management ---------------------------------------------------------
+struct CtaState {
+    uint64_t mbar;
+    uint64_t tau;       // current threshold key (0 = accept everything)
+    uint32_t cnt;       // entries in cbuf
+    uint32_t lock;
+};
+
+// Called by one whole warp holding the lock: shrink cbuf[0..n) to its k largest, publish tau.
+__device__ __forceinline__ int warp_prune(uint64_t *cbuf, int n, int k, uint32_t *hist, CtaState *st) {
+    const int lane = threadIdx.x & 31;
+    uint64_t kth = radix_kth_largest<false>(cbuf, n, k, hist, lane, 32);
+    int kept = warp_compact_ge(cbuf, n, kth);
+    if (lane == 0) *(volatile uint64_t *)&st->tau = kth;
+    return kept;
+}
+
+__device__ __forceinline__ void warp_flush(uint64_t *cbuf, uint64_t *stage, int n_stage, int k, int cap,
+                                           uint32_t *hist, CtaState *st) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    if (lane == 0) {
+        while (atomicCAS(&st->lock, 0u, 1u) != 0u) __nanosleep(32);
+    }
+    __syncwarp();
+    __threadfence_block();
+    int c = (int)*(volatile uint32_t *)&st->cnt;
+    if (c + n_stage > cap) c = warp_prune(cbuf, c, k, hist, st);
+    for (int i = lane; i < n_stage; i += 32) cbuf[c + i] = stage[i];
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) {
+        *(volatile uint32_t *)&st->cnt = (uint32_t)(c + n_stage);
+        __threadfence_block();
+        atomicExch(&st->lock, 0u);
+    }
+    __syncwarp();
+}
+
+template <int VT, int D>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float *qs = reinterpret_cast<float *>(smem);
+    uint64_t *cbuf = reinterpret_cast<uint64_t *>(smem + (size_t)p.vpad * 4);
+    uint64_t *stage_all = cbuf + p.cap;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(stage_all + 32 * kStage);
+    __shared__ CtaState st;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t *stage = stage_all + warp * kStage;
+    const uint32_t lt = lanemask_lt();
+    const int part = blockIdx.x * 32 + warp;
+    const uint32_t w_begin = p.part_win_begin[part];
+    const int nwin = (int)(p.part_win_begin[part + 1] - w_begin);
+    const uint32_t row0 = p.part_row_begin[part];
+    const uint64_t chunk0 = (uint64_t)w_begin * 32ull + lane;
+    const uint32_t *tails = p.tails + w_begin;
+    const uint32_t q_bytes = (uint32_t)p.vpad * 4u;
+
+    if (tid == 0) {
+        mbar_init(&st.mbar, 1);
+        st.lock = 0;
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    uint32_t phase = 0;
+    for (int b = 0; b < p.B; ++b) {
+        // ---- stage the query vector: bulk TMA into shared memory
+        if (tid == 0) {
+            st.cnt = 0;
+            st.tau = 0;
+            fence_proxy_async();  // earlier generic-proxy reads of qs are ordered before the async writes
+            mbar_arrive_expect_tx(&st.mbar, q_bytes);
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.q + (size_t)b * p.vpad);
+            for (uint32_t off = 0; off < q_bytes; off += 16384u) {
+                uint32_t n = min(16384u, q_bytes - off);
+                bulk_g2s(smem + off, src + off, n, &st.mbar);
+            }
+        }
+        __syncthreads();          // cnt/tau reset visible
+        mbar_wait(&st.mbar, phase);
+        phase ^= 1u;
+
+        // ---- stream this warp's part
+        Chunk<VT> ring[D];
+        uint32_t tring[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            if (j < nwin) { load_chunk<VT>(ring[j], p.cols, p.vals, chunk0 + (uint64_t)j * 32ull); tring[j] = ldg_stream_u32(tails + j); }
+            else { sentinel_chunk<VT>(ring[j], p.sentinel); tring[j] = 0; }
+        }
+        float carry = 0.f;
+        uint32_t row = row0;
+        int n_stage = 0;
+        for (int w = 0; w < nwin; w += D) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                if (w + j < nwin) {  // warp-uniform
+                    Chunk<VT> cur = ring[j];
+                    const uint32_t T = tring[j];
+                    const int nx = w + j + D;
+                    if (nx < nwin) { load_chunk<VT>(ring[j], p.cols, p.vals, chunk0 + (uint64_t)nx * 32ull); tring[j] = ldg_stream_u32(tails + nx); }
+                    float v = chunk_dot<VT>(cur, qs);
+                    if (lane == 0) v += carry;
+                    // segmented inclusive scan: segments end at tail bits
+                    const uint32_t before = T & lt;
+                    const int start = 32 - __clz(before);  // first lane of my segment (0 when no tail before me)
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        float o = __shfl_up_sync(0xffffffffu, v, d);
+                        if (lane >= start + d) v += o;
+                    }
+                    const float last = __shfl_sync(0xffffffffu, v, 31);
+                    carry = (T >> 31) ? 0.f : last;
+                    const bool is_tail = (T >> lane) & 1u;
+                    const uint32_t rid = row + __popc(before);
+                    row += __popc(T);
+                    if (T) {  // warp-uniform: at least one row completes in this window
+                        const float s = round_score(v, p.score_round);
+                        if (p.scores_out != nullptr && is_tail) p.scores_out[(size_t)b * p.n_rows + rid] = s + 0.0f;
+                        const uint64_t key = make_key(s, rid);
+                        const uint64_t tau = *(volatile uint64_t *)&st.tau;
+                        const bool ins = is_tail && key > tau;
+                        const uint32_t m = __ballot_sync(0xffffffffu, ins);
+                        if (m) {
+                            if (ins) stage[n_stage + __popc(m & lt)] = key;
+                            n_stage += __popc(m);
+                            if (n_stage > kStage - 32) {
+                                warp_flush(cbuf, stage, n_stage, p.k, p.cap, hist, &st);
+                                n_stage = 0;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (n_stage) warp_flush(cbuf, stage, n_stage, p.k, p.cap, hist, &st);
+        __syncthreads();
+
+        // ---- exact top-k of this CTA's rows, written unsorted (merge.cu sorts)
+        int n = (int)st.cnt;
+        uint64_t kth = 0;
+        if (n > p.k) kth = radix_kth_largest<true>(cbuf, n, p.k, hist, tid, kScanThreads);
+        uint64_t *out = p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k;
+        if (n > p.k) {
+            __shared__ uint32_t out_cnt;
+            if (tid == 0) out_cnt = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += kScanThreads) {
+                uint64_t x = cbuf[i];
+                if (x >= kth) out[atomicAdd(&out_cnt, 1u)] = x;
+            }
+        } else {
+            for (int i = tid; i < p.k; i += kScanThreads) out[i] = (i < n) ? cbuf[i] : 0ull;
+        }
+        __syncthreads();  // everyone is done with qs / cbuf before the next pass overwrites them
+    }
+}
+
+// ---- query preparation: [B, ldq] any float dtype -> fp32 [B, vpad], zero padded, optionally
+// rounded through the index dtype first (upstream index.py:89 `q.type(self.vector.dtype)`).
+__global__ void prep_query_kernel(const void *q, int q_dtype, int64_t ldq, int64_t n_cols, int vpad, int round_mode,
+                                  float *out) {
+    const int64_t b = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < vpad; i += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (i < n_cols) {
+            if (q_dtype == VS_F32) v = ((const float *)q)[b * ldq + i];
+            else if (q_dtype == VS_F16) v = __half2float(((const __half *)q)[b * ldq + i]);
+            else v = __bfloat162float(((const __nv_bfloat16 *)q)[b * ldq + i]);
+            v = round_score(v, round_mode);
+        }
+        out[b * (int64_t)vpad + i] = v;
+    }
+}
+
+size_t scan_smem_bytes(int vpad, int cap) {
+    return (size_t)vpad * 4 + (size_t)cap * 8 + (size_t)32 * kStage * 8 + 256 * 4;
+}
+
+int scan_cap_for_k(int k) { return k <= 960 ? 4096 : 8192; }
+
+int launch_prep_query(const void *d_q, int q_dtype, int64_t B, int64_t ldq, int64_t n_cols, int vpad, int round_mode,
+                      float *d_out, cudaStream_t st) {
+    if (B == 0) return VS_OK;
+    dim3 grid((unsigned)((vpad + 255) / 256), (unsigned)B);
+    VS_REQUIRE(B <= 65535, VS_ERR_INVALID, "query batch chunk too large");
+    prep_query_kernel<<<grid, 256, 0, st>>>(d_q, q_dtype, ldq, n_cols, vpad, round_mode, d_out);
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+template <int VT, int D>
+static int launch_scan_t(const vs_index *idx, const ScanParams &p, size_t smem, cudaStream_t st) {
+    auto kern = scan_topk_kernel<VT, D>;
+    VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<idx->n_ctas, kScanThreads, smem, st>>>(p);
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// d_qprep: [B, vpad] fp32; d_cand: [B, n_ctas, k] keys; d_scores_out optional [B, N]
+int launch_scan(const vs_index *idx, const float *d_qprep, int vpad, int64_t B, int k, int score_round,
+                uint64_t *d_cand, float *d_scores_out, cudaStream_t st) {
+    ScanParams p;
+    p.cols = idx->cols;
+    p.vals = idx->vals;
+    p.tails = idx->tails;
+    p.part_win_begin = idx->part_win_begin;
+    p.part_row_begin = idx->part_row_begin;
+    p.q = d_qprep;
+    p.cand = d_cand;
+    p.scores_out = d_scores_out;
+    p.n_rows = idx->n_rows;
+    p.B = (int)B;
+    p.k = k;
+    p.cap = scan_cap_for_k(k);
+    p.vpad = vpad;
+    p.score_round = score_round;
+    p.sentinel = (uint32_t)idx->n_cols | ((uint32_t)idx->n_cols << 16);
+    size_t smem = scan_smem_bytes(vpad, p.cap);
+    VS_REQUIRE(smem <= 227 * 1024, VS_ERR_UNSUPPORTED,
+               "n_cols=%lld needs %zu bytes of shared memory (> 227 KB): vocabulary too large for the scan kernel",
+               (long long)idx->n_cols, smem);
+    if (idx->kind == 2) return launch_scan_t<0, 4>(idx, p, smem, st);
+    if (idx->store_dtype == VS_F32) return launch_scan_t<1, 2>(idx, p, smem, st);
+    if (idx->store_dtype == VS_F16) return launch_scan_t<2, 3>(idx, p, smem, st);
+    return launch_scan_t<3, 3>(idx, p, smem, st);
+}
+
+}  // namespace vs

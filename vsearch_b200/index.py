@@ -1,0 +1,442 @@
+"""Index containers of the B200 engine: same public surface as upstream
+``src/ir/retriever/index.py`` (``SearchResults``, ``IndexType``, ``Index``, ``SparseIndex``,
+``BoTIndex``), with ``search`` served by hand-written sm_100a kernels behind the C ABI in
+``include/vsearch_b200.h`` instead of ``torch.matmul`` + ``topk`` (upstream index.py:88-94).
+
+Differences that are deliberate:
+  * ties are ranked (score desc, id asc) -- upstream's order inside ties is arbitrary;
+  * the dense ``.pt`` loader and the ``low_memory`` text store work (both are broken upstream);
+  * an index searches only on a CUDA device: there is no CPU fallback, ``search`` on a CPU-resident
+    index raises.
+``.vector`` stays a torch tensor (CSR or strided) for drop-in use (``save``, ``str``); the engine
+keeps its own compact device copy and never reads ``.vector`` during a search.
+"""
+from __future__ import annotations
+
+import ctypes
+import glob
+import json
+import logging
+from enum import Enum
+from typing import NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+logger = logging.getLogger(__name__)
+
+
+class SearchResults(NamedTuple):
+    """(ids, scores): int64 ``[B, k]`` ids and ``[B, k]`` scores in the index dtype, on the index
+    device, ranked score-descending (upstream index.py:16-18, README.md:160-164)."""
+    ids: torch.Tensor
+    scores: torch.Tensor
+
+
+class IndexType(Enum):
+    DENSE = "dense"
+    SPARSE = "sparse"
+    BAG_OF_TOKEN = "bag_of_token"
+
+
+_TORCH2VS = {torch.float32: nat.VS_F32, torch.float16: nat.VS_F16, torch.bfloat16: nat.VS_BF16,
+             torch.int32: nat.VS_I32, torch.int64: nat.VS_I64}
+
+
+def _is_cuda(device) -> bool:
+    return torch.device(device).type == "cuda"
+
+
+def _stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(torch.device(device)).cuda_stream)
+
+
+class _Engine:
+    """Owns one ``vs_index`` handle plus the reusable search workspace."""
+
+    def __init__(self, handle: ctypes.c_void_p, device: torch.device):
+        self.handle = handle
+        self.device = device
+        self._ws = None
+        info = [ctypes.c_int64() for _ in range(3)]
+        kind, sdt = ctypes.c_int(), ctypes.c_int()
+        dbytes, sbytes = ctypes.c_int64(), ctypes.c_int64()
+        nat.check(nat.LIB.vs_index_info(handle, info[0], info[1], info[2], kind, sdt, dbytes, sbytes))
+        self.n_rows, self.n_cols, self.nnz = (int(x.value) for x in info)
+        self.kind, self.store_dtype = kind.value, sdt.value
+        self.device_bytes, self.stream_bytes = int(dbytes.value), int(sbytes.value)
+
+    @classmethod
+    def from_csr(cls, crow, col, val, shape, device, store_dtype=None) -> "_Engine":
+        """crow/col(/val) torch tensors on any device; val None => binary bag-of-token."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("vsearch_b200 searches on CUDA devices only (no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        crow, col = crow.contiguous(), col.contiguous()
+        if crow.dtype not in (torch.int32, torch.int64):
+            crow = crow.to(torch.int64)
+        if col.dtype not in (torch.int32, torch.int64):
+            col = col.to(torch.int64)
+        if val is not None:
+            val = val.contiguous()
+            if val.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+                val = val.to(torch.float32)
+            if store_dtype is None:
+                store_dtype = val.dtype
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            rc = nat.LIB.vs_index_create_csr(
+                device.index, int(shape[0]), int(shape[1]), int(col.numel()),
+                crow.data_ptr(), _TORCH2VS[crow.dtype], col.data_ptr(), _TORCH2VS[col.dtype],
+                None if val is None else val.data_ptr(), nat.VS_NONE if val is None else _TORCH2VS[val.dtype],
+                nat.VS_NONE if val is None else _TORCH2VS[store_dtype], _stream_ptr(device), ctypes.byref(handle))
+        nat.check(rc)
+        return cls(handle, device)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            nat.LIB.vs_index_destroy(h)
+
+    def workspace(self, B: int, k: int) -> torch.Tensor:
+        need = int(nat.LIB.vs_search_workspace_bytes(self.handle, B, k))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _prep_q(self, q: torch.Tensor):
+        q = q.to(self.device, non_blocking=True)
+        if q.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            q = q.to(torch.float32)
+        if q.dim() != 2 or q.shape[1] != self.n_cols:
+            raise RuntimeError(f"query shape {tuple(q.shape)} does not match index width {self.n_cols}")
+        return q.contiguous()
+
+    def search(self, q: torch.Tensor, k: int, mode: str = "auto", score_round: int = nat.VS_F32,
+               id_offset: int = 0, keys_only: bool = False):
+        q = self._prep_q(q)
+        B = q.shape[0]
+        k = int(k)
+        with torch.cuda.device(self.device):
+            ws = self.workspace(B, max(k, 1))
+            st = _stream_ptr(self.device)
+            if keys_only:
+                keys = torch.empty((B, max(k, 0)), dtype=torch.int64, device=self.device)
+                rc = nat.LIB.vs_search_keys(self.handle, q.data_ptr(), _TORCH2VS[q.dtype], B, q.stride(0), k,
+                                            nat.MODES[mode], score_round, id_offset, keys.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), st)
+                nat.check(rc)
+                return keys
+            ids = torch.empty((B, max(k, 0)), dtype=torch.int64, device=self.device)
+            scores = torch.empty((B, max(k, 0)), dtype=torch.float32, device=self.device)
+            rc = nat.LIB.vs_search(self.handle, q.data_ptr(), _TORCH2VS[q.dtype], B, q.stride(0), k,
+                                   nat.MODES[mode], score_round, id_offset, ids.data_ptr(), scores.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), st)
+        nat.check(rc)
+        return ids, scores
+
+    def scores(self, q: torch.Tensor, score_round: int = nat.VS_F32) -> torch.Tensor:
+        """Diagnostic: the full [B, N] score matrix (upstream index.py:91)."""
+        q = self._prep_q(q)
+        B = q.shape[0]
+        out = torch.empty((B, self.n_rows), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            ws = self.workspace(B, 1)
+            rc = nat.LIB.vs_scores(self.handle, q.data_ptr(), _TORCH2VS[q.dtype], B, q.stride(0), score_round,
+                                   out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
+        nat.check(rc)
+        return out
+
+    def export_csr(self):
+        crow = torch.empty(self.n_rows + 1, dtype=torch.int64, device=self.device)
+        col = torch.empty(self.nnz, dtype=torch.int64, device=self.device)
+        val = torch.empty(self.nnz, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(nat.LIB.vs_index_export_csr(self.handle, crow.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                                  _stream_ptr(self.device)))
+        return crow, col, val
+
+    def last_kernel_ms(self):
+        ms, n = ctypes.c_float(), ctypes.c_int()
+        nat.check(nat.LIB.vs_last_kernel_ms(self.handle, ms, n))
+        return float(ms.value), int(n.value)
+
+
+def merge_keys(keys: torch.Tensor, k_out: int):
+    """Merge gathered rank keys ``[P, B, k_in]`` (int64 bit patterns) into ``(ids, scores)`` ``[B, k_out]``."""
+    if not keys.is_cuda:
+        raise RuntimeError("vsearch_b200 merges on CUDA devices only (no CPU fallback)")
+    keys = keys.contiguous()
+    P, B, k_in = keys.shape
+    ids = torch.empty((B, k_out), dtype=torch.int64, device=keys.device)
+    scores = torch.empty((B, k_out), dtype=torch.float32, device=keys.device)
+    with torch.cuda.device(keys.device):
+        nat.check(nat.LIB.vs_merge_keys(keys.device.index, keys.data_ptr(), P, B * k_in, k_in, B, k_in, k_out,
+                                        ids.data_ptr(), scores.data_ptr(), _stream_ptr(keys.device)))
+    return ids, scores
+
+
+class Index:
+    """Dense index (``[N, D]`` strided ``.vector``) and base class (upstream index.py:25-126)."""
+
+    index_type = IndexType.DENSE
+
+    def __init__(self, index_file: Optional[str] = None, data_file: Optional[str] = None, fp16: bool = True,
+                 device: str = "cpu", low_memory: bool = False):
+        self.data = None
+        self._vector = None
+        self._engine = None
+        self.low_memory = low_memory
+        self.device = device
+        self.search_mode = "auto"  # "auto" | "scan" | "inverted"
+        self.init_index(index_file, fp16)
+        self.load_data(data_file)
+
+    # ---- the logical vector ---------------------------------------------------------------
+    @property
+    def vector(self):
+        if self._vector is None and self._engine is not None and self._engine.kind != 0:
+            crow, col, val = self._engine.export_csr()
+            self._vector = torch.sparse_csr_tensor(crow, col, val.to(self._value_dtype()),
+                                                   size=(self._engine.n_rows, self._engine.n_cols))
+        return self._vector
+
+    @vector.setter
+    def vector(self, value):
+        self._vector = value
+        self._engine = None
+
+    def _value_dtype(self):
+        if self._vector is not None:
+            return self._vector.dtype
+        sd = self._engine.store_dtype if self._engine is not None else nat.VS_F32
+        return {nat.VS_F16: torch.float16, nat.VS_BF16: torch.bfloat16}.get(sd, torch.float32)
+
+    # ---- loading ----------------------------------------------------------------------------
+    def init_index(self, index_path: Optional[str], fp16: bool = True):
+        """Dense shards: glob ``*.pt`` in sorted order, concatenate rows (intent of upstream index.py:36-44)."""
+        if not index_path:
+            return
+        files = sorted(glob.glob(index_path))
+        if not files:
+            raise FileNotFoundError(f"no index files match {index_path!r}")
+        logger.info("***** Loading %s Index from %d files *****", self.index_type.value, len(files))
+        shards = [torch.load(f, map_location="cpu") for f in files]
+        vec = torch.cat(shards, dim=0) if len(shards) > 1 else shards[0]
+        self.vector = vec.to(torch.float16) if fp16 else vec
+        self.move_to_device(self.device)
+
+    def load_data(self, data_file: Optional[str]):
+        if not data_file:
+            return
+        if not self.low_memory:
+            with open(data_file, "r") as f:
+                self.data = [json.loads(line) for line in f]
+        else:
+            self.offsets = self._calculate_offsets(data_file)
+            self.data_file = data_file
+
+    @staticmethod
+    def _calculate_offsets(data_file: str):
+        offsets, pos = [], 0
+        with open(data_file, "rb") as f:
+            for line in f:
+                offsets.append(pos)
+                pos += len(line)
+        return offsets
+
+    def get_sample(self, index: int):
+        if not self.low_memory:
+            return self.data[index]
+        with open(self.data_file, "rb") as f:
+            f.seek(self.offsets[index])
+            return json.loads(f.readline().decode("utf-8"))
+
+    # ---- device placement ----------------------------------------------------------------------
+    def move_to_device(self, device: str):
+        logger.info("Moving index to %s.", device)
+        self.device = device
+        if self._vector is None and self._engine is None:
+            return
+        if _is_cuda(device):
+            if self._engine is None or self._engine.device != self._resolve(device):
+                self._build_engine(device)
+        else:
+            if self._vector is None:
+                self._vector = self.vector  # export before dropping the engine
+            self._vector = self._vector.to(device)
+            self._engine = None
+
+    @staticmethod
+    def _resolve(device) -> torch.device:
+        d = torch.device(device)
+        if d.type == "cuda" and d.index is None:
+            d = torch.device("cuda", torch.cuda.current_device())
+        return d
+
+    def _build_engine(self, device):
+        raise NotImplementedError("dense index (K4) is not built yet")
+
+    def _require_engine(self) -> _Engine:
+        if self._engine is None:
+            if self._vector is None:
+                raise RuntimeError("index is empty: nothing to search")
+            if not _is_cuda(self.device):
+                raise RuntimeError(
+                    "vsearch_b200 has no CPU search path: call index.move_to_device('cuda') first")
+            self._build_engine(self.device)
+        return self._engine
+
+    # ---- search -------------------------------------------------------------------------------------
+    def _score_round(self) -> int:
+        return {torch.float16: nat.VS_F16, torch.bfloat16: nat.VS_BF16}.get(self._value_dtype(), nat.VS_F32)
+
+    def search(self, q_embs: torch.Tensor, k: int) -> SearchResults:
+        """``scores = q @ vector.t(); scores.topk(k)`` (upstream index.py:88-94) without the [B, N] matrix."""
+        eng = self._require_engine()
+        one_d = q_embs.dim() == 1
+        q = q_embs.unsqueeze(0) if one_d else q_embs
+        ids, scores = eng.search(q, k, mode=self.search_mode, score_round=self._score_round())
+        scores = scores.to(self._value_dtype())
+        if one_d:
+            ids, scores = ids[0], scores[0]
+        return SearchResults(ids, scores)
+
+    def search_keys(self, q_embs: torch.Tensor, k: int, id_offset: int = 0) -> torch.Tensor:
+        """Packed rank keys ``[B, k]`` of this shard with global ids (row-sharded path, sharded.py)."""
+        eng = self._require_engine()
+        return eng.search(q_embs, k, mode=self.search_mode, score_round=self._score_round(),
+                          id_offset=id_offset, keys_only=True)
+
+    # ---- persistence / introspection ------------------------------------------------------------------
+    def save(self, path):
+        """Dense: one ``.pt`` tensor (upstream index.py:96-109)."""
+        try:
+            torch.save(self.vector.cpu(), path)
+            logger.info("Index successfully saved to %s", path)
+        except Exception as e:  # noqa: BLE001 - upstream logs then re-raises
+            logger.error("Failed to save index to %s: %s", path, e)
+            raise
+
+    def __len__(self):
+        return len(self.data) if self.data else 0
+
+    def __repr__(self):
+        return repr(self.vector)
+
+    def _shape(self):
+        if self._vector is not None:
+            return self._vector.shape
+        return torch.Size((self._engine.n_rows, self._engine.n_cols))
+
+    def __str__(self):
+        layout = self._vector.layout if self._vector is not None else torch.sparse_csr
+        return (
+            f"Index Type        : {type(self).__name__}\n"
+            f"Vector Shape      : {self._shape()}\n"
+            f"Vector Dtype      : {self._value_dtype()}\n"
+            f"Vector Layout     : {layout}\n"
+            f"Number of Texts   : {len(self.data) if self.data else 0}\n"
+            f"Device            : {self.device}\n"
+        )
+
+
+class SparseIndex(Index):
+    """``[N, V]`` sparse CSR index (upstream index.py:128-202)."""
+
+    index_type = IndexType.SPARSE
+
+    def __init__(self, index_file: Optional[str] = None, data_file: Optional[str] = None, fp16: bool = True,
+                 device: str = "cpu", low_memory: bool = False, shift: int = 0):
+        self.shift = shift
+        super().__init__(index_file, data_file, fp16, device, low_memory)
+
+    def _scipy_csr_to_torch_csr(self, mat) -> torch.Tensor:
+        """scipy CSR -> torch CSR on ``self.device`` (upstream index.py:144-161).  With a CUDA device the
+        torch tensor stays on the host and the engine gets the compact device copy."""
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t = torch.sparse_csr_tensor(torch.from_numpy(np.ascontiguousarray(mat.indptr)),
+                                        torch.from_numpy(np.ascontiguousarray(mat.indices)),
+                                        torch.from_numpy(np.ascontiguousarray(mat.data)), size=mat.shape)
+        return t
+
+    def init_index(self, index_file: Optional[str], fp16: bool = True):
+        """glob -> sorted -> load_npz -> ``[:, shift:]`` -> vstack -> optional fp16 (upstream index.py:163-179)."""
+        if not index_file:
+            return
+        from .npz_io import load_csr_shards
+
+        files = sorted(glob.glob(index_file))
+        if not files:
+            raise FileNotFoundError(f"no index files match {index_file!r}")
+        logger.info("***** Loading %s Index from %d files *****", self.index_type.value, len(files))
+        indptr, indices, data, shape = load_csr_shards(files, self.shift)
+        if fp16:
+            data = data.astype(np.float16)
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.vector = torch.sparse_csr_tensor(torch.from_numpy(indptr), torch.from_numpy(indices),
+                                                  torch.from_numpy(data), size=shape)
+        self.move_to_device(self.device)
+
+    def _csr_parts(self):
+        v = self._vector
+        if v.layout != torch.sparse_csr:
+            v = v.to_sparse_csr()
+        return v.crow_indices(), v.col_indices(), v.values(), v.shape
+
+    def _build_engine(self, device):
+        crow, col, val, shape = self._csr_parts()
+        dev = self._resolve(device)
+        self._engine = _Engine.from_csr(crow.to(dev), col.to(dev), val.to(dev), shape, dev)
+
+    def save(self, path):
+        """scipy-loadable ``.npz`` (upstream index.py:181-202)."""
+        try:
+            from .npz_io import save_csr_npz
+
+            crow, col, val, shape = self._csr_parts() if self._vector is not None else (*self._engine.export_csr(), self._shape())
+            if val.dtype == torch.bfloat16:
+                val = val.to(torch.float32)  # numpy has no bfloat16
+            save_csr_npz(path, crow.cpu().numpy(), col.cpu().numpy(), val.cpu().numpy(), tuple(shape))
+            logger.info("Index successfully saved to %s", path)
+        except Exception as e:  # noqa: BLE001
+            logger.error("Failed to save index to %s: %s", path, e)
+            raise
+
+
+class BoTIndex(SparseIndex):
+    """Binary bag-of-token index (upstream index.py:205-218): all stored values are 1, so the device
+    copy keeps column ids only (2 bytes per entry)."""
+
+    index_type = IndexType.BAG_OF_TOKEN
+
+    def _build_engine(self, device):
+        crow, col, val, shape = self._csr_parts()
+        dev = self._resolve(device)
+        binary = bool((val == 1).all().item()) if val.numel() else True
+        self._engine = _Engine.from_csr(crow.to(dev), col.to(dev), None if binary else val.to(dev), shape, dev)
+
+    @classmethod
+    def from_token_csr(cls, crow: torch.Tensor, col: torch.Tensor, shape, device="cuda", dtype=torch.float32):
+        """Build straight from (crow, col) device arrays -- no values, no torch CSR copy (large synthetic /
+        pre-tokenised corpora).  ``dtype`` is the logical value dtype reported by ``.vector`` / scores."""
+        self = cls(device=device)
+        self._engine = _Engine.from_csr(crow, col, None, shape, self._resolve(device))
+        self._logical_dtype = dtype
+        return self
+
+    def _value_dtype(self):
+        if self._vector is None and getattr(self, "_logical_dtype", None) is not None:
+            return self._logical_dtype
+        return super()._value_dtype()

@@ -1,0 +1,63 @@
+"""Row-sharded search over the GPUs of one box.  No upstream counterpart: upstream
+vstacks all shard files onto ONE device (index.py:172-179).
+
+Partition: contiguous row ranges, rank r owns ``[r*ceil(N/W), min(N, (r+1)*ceil(N/W)))`` -- the same split
+as upstream's build-time ``--num_shard/--shard_id`` files, so shard files map 1:1 to ranks and
+global id = local id + row offset.  Queries are replicated.  Each rank runs the fused scan + top-k on its
+rows and contributes ``k`` packed rank keys per query; ONE all-gather (NCCL over NVLink) moves
+``W x B x k x 8`` bytes, then every rank merges with the K6 kernel.  Contiguous ranges keep "lower id wins"
+consistent across ranks because the key carries the global id.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .index import Index, SearchResults, merge_keys
+
+
+def row_partition(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
+    per = -(-n_rows // world)
+    lo = min(n_rows, rank * per)
+    return lo, min(n_rows, lo + per)
+
+
+def gather_keys(local_keys: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather ``[B, k]`` int64 key tensors into ``[W, B, k]`` (the path's only collective)."""
+    world = dist.get_world_size(group)
+    flat = local_keys.contiguous().view(-1)
+    out = torch.empty(world * flat.numel(), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(out, flat, group=group)
+    return out.view((world,) + tuple(local_keys.shape))
+
+
+class ShardedIndex:
+    """One rank's view of a row-sharded index."""
+
+    def __init__(self, local_index: Index, row_offset: int, n_rows_total: int, group=None,
+                 merge_fn: Optional[Callable] = None):
+        self.local = local_index
+        self.row_offset = int(row_offset)
+        self.n_rows_total = int(n_rows_total)
+        self.group = group
+        self._merge = merge_fn or merge_keys  # tests on CPU/gloo inject the oracle merge here
+
+    def search(self, q_embs: torch.Tensor, k: int) -> SearchResults:
+        if k > self.n_rows_total:
+            raise RuntimeError(f"selected index k out of range (k={k} > N={self.n_rows_total})")
+        one_d = q_embs.dim() == 1
+        q = q_embs.unsqueeze(0) if one_d else q_embs
+        n_local = self.local._require_engine().n_rows
+        k_local = min(k, n_local)
+        keys = self.local.search_keys(q, k_local, id_offset=self.row_offset)
+        if k_local < k:  # short shard: pad with empty keys so every rank gathers the same shape
+            pad = torch.zeros((keys.shape[0], k - k_local), dtype=keys.dtype, device=keys.device)
+            keys = torch.cat([keys, pad], dim=1)
+        gathered = gather_keys(keys, self.group) if dist.is_initialized() else keys.unsqueeze(0)
+        ids, scores = self._merge(gathered, k)
+        scores = scores.to(self.local._value_dtype())
+        if one_d:
+            ids, scores = ids[0], scores[0]
+        return SearchResults(ids, scores)
