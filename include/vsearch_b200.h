@@ -115,9 +115,12 @@ int vs_scores(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int
 int vs_merge_keys(int device, const uint64_t *d_keys_in, int64_t P, int64_t stride_p, int64_t stride_b,
                   int64_t B, int k_in, int k_out, int64_t *d_ids, float *d_scores, void *stream);
 
-/* timing hook for bench.py: device time (ms) of the scan/score kernel of the last vs_search on this
- * handle, measured with CUDA events on the launching stream.  SYNC (waits for those events). */
-int vs_last_kernel_ms(const vs_index *idx, float *ms, int *launches);
+/* timing hook for bench.py: every scan/score kernel launch made through this handle is bracketed by a
+ * CUDA event pair on the launching stream (a ring of VS_TIMER_SLOTS pairs).  Returns the summed device
+ * time (ms) and the number of launches recorded since the last reset; reset != 0 clears the ring
+ * afterwards.  SYNC (waits for the recorded events). */
+#define VS_TIMER_SLOTS 256
+int vs_kernel_timer(vs_index *idx, int reset, float *total_ms, int *launches);
 
 #ifdef __cplusplus
 }

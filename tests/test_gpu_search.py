@@ -224,3 +224,108 @@ def test_large_batch_chunks(cuda_device):
     q = sparse_queries(1100, v, 12, seed=3)
     res = idx.search(q, 10)
     assert ref_search.compare_results(res, ref_search.ref_scores(q, X), 10, exact=True) is None
+
+
+# ---------------------------------------------------------------------------------------------------
+# K3: token-major inverted lists (mode="inverted") and the auto crossover -- same oracle, same bars
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_search_cases("csr"))
+def test_golden_csr_inverted(name, cuda_device):
+    z = load_golden(name)
+    idx = _mk("BoTIndex" if bool(z["binary"]) else "SparseIndex", z["crow"], z["col"], z["val"], z["shape"])
+    idx.search_mode = "inverted"
+    res = idx.search(torch.from_numpy(z["q"]), z["k"])
+    msg = ref_search.compare_results(res, torch.from_numpy(z["ref_scores"]), z["k"], exact="cont" not in name)
+    assert msg is None, msg
+
+
+@pytest.mark.parametrize("n,m,B,k,binary,qnnz", [
+    (200_000, 120, 19, 100, True, 64),
+    (100_000, 256, 9, 100, False, 64),
+    (60_000, 256, 3, 1000, False, 768),
+    (50_000, 120, 5, 1000, True, 768),
+])
+def test_inverted_synthetic_grid_exact(n, m, B, k, binary, qnnz, cuda_device):
+    crow, col, val = stratified_csr(n, V, m, seed=11, grid=True, binary=binary, jitter=17)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    idx = _mk("BoTIndex" if binary else "SparseIndex", crow, col, val, (n, V))
+    idx.search_mode = "inverted"
+    q = sparse_queries(B, V, qnnz, seed=5, neg=not binary)
+    res = idx.search(q, k)
+    msg = ref_search.compare_results(res, ref_search.ref_scores(q, X), k, exact=True)
+    assert msg is None, msg
+    # and both kernel families agree bit for bit
+    idx.search_mode = "scan"
+    res2 = idx.search(q, k)
+    assert torch.equal(res.ids, res2.ids) and torch.equal(res.scores, res2.scores)
+
+
+def test_inverted_edge_cases(cuda_device):
+    n, v = 300, 1000
+    crow, col, val = stratified_csr(n, v, 20, seed=4, grid=True, jitter=20)
+    X = ref_search.torch_csr(crow, col, val, (n, v))
+    idx = _mk("SparseIndex", crow, col, val, (n, v))
+    idx.search_mode = "inverted"
+    q = sparse_queries(3, v, 30, seed=6, neg=True)
+    q[1] = 0  # all-zero query: no postings at all, every score 0 -> ids 0..k-1
+    ref = ref_search.ref_scores(q, X)
+    for k in (1, 5, 100, n):
+        msg = ref_search.compare_results(idx.search(q, k), ref, k, exact=True)
+        assert msg is None, f"k={k}: {msg}"
+    with pytest.raises(RuntimeError):
+        idx.search(q, n + 1)
+    r1 = idx.search(q[2], 9)
+    assert tuple(r1.ids.shape) == (9,)
+    # fewer than k matching rows: zeros fill the tail, lowest ids first (rows never touched still compete)
+    q2 = torch.zeros(1, v)
+    q2[0, int(col[0])] = 1.0
+    res = idx.search(q2, 50)
+    assert ref_search.compare_results(res, ref_search.ref_scores(q2, X), 50, exact=True) is None
+
+
+def test_inverted_heavy_ties_and_continuous(cuda_device):
+    n = 120_000
+    crow, col, val = stratified_csr(n, V, 60, seed=13, binary=True, jitter=30)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    idx = _mk("BoTIndex", crow, col, val, (n, V))
+    idx.search_mode = "inverted"
+    q = (sparse_queries(6, V, 512, seed=3) != 0).float()
+    for k in (10, 1000):
+        msg = ref_search.compare_results(idx.search(q, k), ref_search.ref_scores(q, X), k, exact=True)
+        assert msg is None, f"k={k}: {msg}"
+    crow, col, val = stratified_csr(50_000, V, 128, seed=3, grid=False)
+    X = ref_search.torch_csr(crow, col, val, (50_000, V))
+    idx = _mk("SparseIndex", crow, col, val, (50_000, V))
+    idx.search_mode = "inverted"
+    q = sparse_queries(5, V, 128, seed=9, grid=False)
+    msg = ref_search.compare_results(idx.search(q, 100), ref_search.ref_scores(q, X), 100, rtol=1e-5, exact=False)
+    assert msg is None, msg
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_inverted_half_precision_values(dtype, cuda_device):
+    n, m = 30_000, 64
+    crow, col, val = stratified_csr(n, V, m, seed=17, grid=True)
+    idx = _mk("SparseIndex", crow, col, val, (n, V), dtype=dtype)  # grid values are exact in fp16 and bf16
+    q = sparse_queries(4, V, 64, seed=2, grid=True)
+    idx.search_mode = "inverted"
+    a = idx.search(q, 20)
+    idx.search_mode = "scan"
+    b = idx.search(q, 20)
+    assert torch.equal(a.ids, b.ids) and torch.equal(a.scores, b.scores)
+
+
+def test_auto_mode_crossover(cuda_device):
+    """auto picks inverted lists for sparse queries and the scan for dense ones; results do not depend on it."""
+    n, m = 60_000, 120
+    crow, col, val = stratified_csr(n, V, m, seed=23, grid=True, binary=True)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    idx = _mk("BoTIndex", crow, col, val, (n, V))
+    idx.search_mode = "auto"
+    for qnnz in (8, 64, 768, 6000):
+        q = sparse_queries(3, V, qnnz, seed=qnnz)
+        msg = ref_search.compare_results(idx.search(q, 50), ref_search.ref_scores(q, X), 50, exact=True)
+        assert msg is None, f"qnnz={qnnz}: {msg}"
+    idx.search_mode = "inverted"
+    with pytest.raises(NotImplementedError):  # > 4096 non-zeros per query: inverted lists refuse, auto falls back
+        idx.search(sparse_queries(1, V, 6000, seed=1), 5)

@@ -23,6 +23,12 @@ int launch_prep_query(const void *d_q, int q_dtype, int64_t B, int64_t ldq, int6
                       float *d_out, cudaStream_t st);
 int launch_scan(const vs_index *idx, const float *d_qprep, int vpad, int64_t B, int k, int score_round,
                 uint64_t *d_cand, float *d_scores_out, cudaStream_t st);
+size_t inverted_workspace_bytes(const vs_index *idx, int64_t Bc, int group);
+int inverted_extract(vs_index *idx, const float *d_qprep, int vpad, int64_t Bc, void *d_ws, uint32_t *max_nnz,
+                     double *mean_postings, uint64_t *max_postings, cudaStream_t st);
+bool inverted_usable(uint32_t max_nnz, uint64_t max_postings);
+int launch_inverted(vs_index *idx, int64_t Bc, int k, int score_round, int group, uint32_t max_nnz, void *d_ws,
+                    uint64_t *d_cand, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t st);
 int launch_merge(const uint64_t *d_in, int64_t P, int64_t stride_p, int64_t stride_b, int64_t B, int k_in, int k_out,
                  int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, cudaStream_t st);
 
@@ -61,8 +67,10 @@ static inline int vpad_for(int64_t n_cols) { return (int)(((n_cols + 1) + 3) / 4
 struct Workspace {
     float *qprep;      // [Bc, vpad]
     uint64_t *cand;    // [Bc, n_ctas, k]
+    void *inv;         // K3: query lists + accumulators
     size_t bytes;
 };
+constexpr int kInvGroup = 8;   // queries scored concurrently by the inverted-list path (accumulator rows)
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 static Workspace carve(const vs_index *idx, void *base, int64_t Bc, int k) {
     Workspace w;
@@ -70,10 +78,15 @@ static Workspace carve(const vs_index *idx, void *base, int64_t Bc, int k) {
     size_t c_bytes = align256((size_t)Bc * idx->n_ctas * (size_t)k * 8);
     w.qprep = (float *)base;
     w.cand = (uint64_t *)((uint8_t *)base + q_bytes);
-    w.bytes = q_bytes + c_bytes;
+    w.inv = (uint8_t *)base + q_bytes + c_bytes;
+    w.bytes = q_bytes + c_bytes + align256(inverted_workspace_bytes(idx, Bc, kInvGroup));
     return w;
 }
 constexpr int64_t kQueryChunk = 1024;
+// auto-mode cost model; refined from measurements (profiles/)
+constexpr double kScanBytesPerSec = 4.0e12;
+constexpr double kInvPostingsPerSec = 1.5e11;
+constexpr double kInvSelectBytesPerSec = 5.0e12;
 
 }  // namespace vs
 
@@ -121,10 +134,11 @@ int vs_index_create_csr(int device, int64_t n_rows, int64_t n_cols, int64_t nnz,
         cudaStreamSynchronize(st);
     }
     if (rc == VS_OK) {
-        if (cudaEventCreate(&idx->ev0) != cudaSuccess || cudaEventCreate(&idx->ev1) != cudaSuccess) {
-            set_error("cudaEventCreate failed");
-            rc = VS_ERR_CUDA;
-        }
+        for (int i = 0; i < VS_TIMER_SLOTS && rc == VS_OK; ++i)
+            if (cudaEventCreate(&idx->ev0[i]) != cudaSuccess || cudaEventCreate(&idx->ev1[i]) != cudaSuccess) {
+                set_error("cudaEventCreate failed");
+                rc = VS_ERR_CUDA;
+            }
     }
     if (rc != VS_OK) { vs_index_destroy(idx); return rc; }
     *out = idx;
@@ -145,8 +159,10 @@ int vs_index_destroy(vs_index *idx) {
     cudaFree(idx->cols); cudaFree(idx->vals); cudaFree(idx->tails);
     cudaFree(idx->part_win_begin); cudaFree(idx->part_row_begin); cudaFree(idx->row_chunk);
     cudaFree(idx->dense);
-    if (idx->ev0) cudaEventDestroy(idx->ev0);
-    if (idx->ev1) cudaEventDestroy(idx->ev1);
+    for (int i = 0; i < VS_TIMER_SLOTS; ++i) {
+        if (idx->ev0[i]) cudaEventDestroy(idx->ev0[i]);
+        if (idx->ev1[i]) cudaEventDestroy(idx->ev1[i]);
+    }
     delete idx;
     return VS_OK;
 }
@@ -189,7 +205,8 @@ static int search_impl(const vs_index *cidx, const void *hd_q, int q_dtype, int6
     VS_REQUIRE((int64_t)k <= idx->n_rows, VS_ERR_INVALID, "selected index k out of range (k=%d > N=%lld)", k,
                (long long)idx->n_rows);
     VS_REQUIRE(k <= VS_MAX_K, VS_ERR_UNSUPPORTED, "k=%d > VS_MAX_K=%d", k, VS_MAX_K);
-    VS_REQUIRE(mode == VS_MODE_AUTO || mode == VS_MODE_SCAN, VS_ERR_UNSUPPORTED, "inverted-list mode is not built yet");
+    VS_REQUIRE(mode == VS_MODE_AUTO || mode == VS_MODE_SCAN || mode == VS_MODE_INVERTED, VS_ERR_INVALID, "bad mode");
+    VS_REQUIRE(!(d_scores_full && mode == VS_MODE_INVERTED), VS_ERR_INVALID, "vs_scores uses the scan kernels");
     VS_REQUIRE(score_round == VS_F32 || score_round == VS_F16 || score_round == VS_BF16, VS_ERR_INVALID, "bad score_round");
     VS_REQUIRE(workspace_bytes >= vs_search_workspace_bytes(idx, B, k), VS_ERR_INVALID, "workspace too small");
     VS_REQUIRE(idx->n_rows + id_offset < 0xffffffffll && id_offset >= 0, VS_ERR_UNSUPPORTED, "global ids must fit 32 bits");
@@ -200,8 +217,6 @@ static int search_impl(const vs_index *cidx, const void *hd_q, int q_dtype, int6
     void *ws_base = (void *)(((uintptr_t)d_workspace + 255) / 256 * 256);
 
     const bool q_on_device = is_device_ptr(hd_q);
-    idx->last_launches = 0;
-    idx->timed = false;
     for (int64_t b0 = 0; b0 < B; b0 += kQueryChunk) {
         const int64_t Bc = (B - b0) < kQueryChunk ? (B - b0) : kQueryChunk;
         Workspace w = carve(idx, ws_base, Bc, k);
@@ -211,12 +226,41 @@ static int search_impl(const vs_index *cidx, const void *hd_q, int q_dtype, int6
         else sq.ptr = qsrc;
         int rc = launch_prep_query(sq.ptr, q_dtype, Bc, ldq, idx->n_cols, vpad, score_round, w.qprep, st);
         if (rc) return rc;
-        if (b0 == 0) VS_CUDA(cudaEventRecord(idx->ev0, st));
-        rc = launch_scan(idx, w.qprep, vpad, Bc, k, score_round, w.cand,
-                         d_scores_full ? d_scores_full + (size_t)b0 * idx->n_rows : nullptr, st);
-        if (rc) return rc;
-        idx->last_launches += 1;
-        if (b0 + kQueryChunk >= B) { VS_CUDA(cudaEventRecord(idx->ev1, st)); idx->timed = (B <= kQueryChunk); }
+        // ---- scan (K1/K2) or inverted lists (K3)?
+        bool use_inv = false;
+        uint32_t max_nnz = 0;
+        if (mode != VS_MODE_SCAN && !d_scores_full) {
+            double mean_post = 0;
+            uint64_t max_post = 0;
+            rc = inverted_extract(idx, w.qprep, vpad, Bc, w.inv, &max_nnz, &mean_post, &max_post, st);  // SYNC
+            if (rc) return rc;
+            const bool usable = inverted_usable(max_nnz, max_post);
+            if (mode == VS_MODE_INVERTED) {
+                VS_REQUIRE(usable, VS_ERR_UNSUPPORTED,
+                           "inverted mode needs <= 4096 non-zeros and < 2^32 postings per query (got %u / %llu)", max_nnz,
+                           (unsigned long long)max_post);
+                use_inv = true;
+            } else {
+                // cost model (seconds per query), constants measured on B200
+                const double t_scan = (double)idx->stream_bytes / kScanBytesPerSec;
+                const double t_inv = mean_post / kInvPostingsPerSec + 8.0 * (double)idx->n_rows / kInvSelectBytesPerSec;
+                use_inv = usable && t_inv < t_scan;
+            }
+        }
+        idx->last_mode = use_inv ? VS_MODE_INVERTED : VS_MODE_SCAN;
+        const int slot = idx->timer_n < VS_TIMER_SLOTS ? idx->timer_n : -1;
+        if (use_inv) {
+            rc = launch_inverted(idx, Bc, k, score_round, kInvGroup, max_nnz, w.inv, w.cand,
+                                 slot >= 0 ? idx->ev0[slot] : nullptr, slot >= 0 ? idx->ev1[slot] : nullptr, st);
+            if (rc) return rc;
+        } else {
+            if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev0[slot], st));
+            rc = launch_scan(idx, w.qprep, vpad, Bc, k, score_round, w.cand,
+                             d_scores_full ? d_scores_full + (size_t)b0 * idx->n_rows : nullptr, st);
+            if (rc) return rc;
+            if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
+        }
+        idx->timer_n += 1;
         rc = launch_merge(w.cand, idx->n_ctas, k, (int64_t)idx->n_ctas * k, Bc, k, k, id_offset,
                           d_ids ? d_ids + b0 * k : nullptr, d_scores ? d_scores + b0 * k : nullptr,
                           d_keys ? d_keys + b0 * k : nullptr, st);
@@ -258,12 +302,20 @@ int vs_merge_keys(int device, const uint64_t *d_keys_in, int64_t P, int64_t stri
                         (cudaStream_t)stream);
 }
 
-int vs_last_kernel_ms(const vs_index *idx, float *ms, int *launches) {
-    VS_REQUIRE(idx != nullptr && ms != nullptr, VS_ERR_INVALID, "NULL pointer");
-    VS_REQUIRE(idx->timed, VS_ERR_INVALID, "no single-launch search has been timed on this handle");
-    VS_CUDA(cudaEventSynchronize(idx->ev1));
-    VS_CUDA(cudaEventElapsedTime(ms, idx->ev0, idx->ev1));
-    if (launches) *launches = idx->last_launches;
+int vs_kernel_timer(vs_index *idx, int reset, float *total_ms, int *launches) {
+    VS_REQUIRE(idx != nullptr, VS_ERR_INVALID, "NULL pointer");
+    VS_CUDA(cudaSetDevice(idx->device));
+    const int n = idx->timer_n < VS_TIMER_SLOTS ? idx->timer_n : VS_TIMER_SLOTS;
+    float total = 0.f;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        VS_CUDA(cudaEventSynchronize(idx->ev1[i]));
+        VS_CUDA(cudaEventElapsedTime(&ms, idx->ev0[i], idx->ev1[i]));
+        total += ms;
+    }
+    if (total_ms) *total_ms = total;
+    if (launches) *launches = n;
+    if (reset) idx->timer_n = 0;
     return VS_OK;
 }
 

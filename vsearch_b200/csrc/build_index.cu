@@ -186,7 +186,7 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
 }
 
 // ---- export: WS -> CSR (int64 crow/col, fp32 val), for SparseIndex.save (upstream index.py:181-202)
-__global__ void export_len_kernel(const vs_index idx, const uint32_t *row_chunk, uint64_t *len) {
+__global__ void export_len_kernel(const WsView idx, const uint32_t *row_chunk, uint64_t *len) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > idx.n_rows) return;
     if (r == idx.n_rows) { len[r] = 0; return; }
@@ -201,7 +201,7 @@ __global__ void export_len_kernel(const vs_index idx, const uint32_t *row_chunk,
     len[r] = n;
 }
 
-__global__ void export_fill_kernel(const vs_index idx, const uint32_t *row_chunk, const uint64_t *crow,
+__global__ void export_fill_kernel(const WsView idx, const uint32_t *row_chunk, const uint64_t *crow,
                                    int64_t *out_crow, int64_t *out_col, float *out_val) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > idx.n_rows) return;
@@ -232,12 +232,12 @@ int export_ws_csr(const vs_index *idx, int64_t *d_crow, int64_t *d_col, float *d
     size_t tmp_bytes = 0;
     VS_CUDA(cudaMalloc(&d_len, sizeof(uint64_t) * (size_t)(N + 1)));
     unsigned blocks = (unsigned)((N + 1 + 255) / 256);
-    export_len_kernel<<<blocks, 256, 0, st>>>(*idx, idx->row_chunk, d_len);
+    export_len_kernel<<<blocks, 256, 0, st>>>(ws_view(idx), idx->row_chunk, d_len);
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_len, (int64_t)(N + 1), st);
     cudaError_t e = cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16);
     if (e != cudaSuccess) { cudaFree(d_len); VS_CUDA(e); }
     cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_len, d_len, (int64_t)(N + 1), st);
-    export_fill_kernel<<<blocks, 256, 0, st>>>(*idx, idx->row_chunk, d_len, d_crow, d_col, d_val);
+    export_fill_kernel<<<blocks, 256, 0, st>>>(ws_view(idx), idx->row_chunk, d_len, d_crow, d_col, d_val);
     e = cudaStreamSynchronize(st);
     cudaFree(d_len);
     cudaFree(d_tmp);

@@ -36,6 +36,13 @@ struct vs_index {
     uint32_t *part_row_begin = nullptr;  // n_parts + 1
     uint32_t *row_chunk = nullptr;       // N + 1: first chunk of each row in the stream (export, rerank)
 
+    // ---- K3 token-major inverted lists (built lazily from the WS stream on first use)
+    bool inv_built = false;
+    uint64_t *post_ptr = nullptr;   // n_cols + 1
+    uint32_t *post_doc = nullptr;   // nnz: passage ids, grouped by token (CTA-range order inside a token)
+    void *post_val = nullptr;       // nnz values in store_dtype (valued index only)
+    int64_t inv_bytes = 0;
+
     // ---- dense
     int64_t dim = 0;
     void *dense = nullptr;
@@ -44,13 +51,31 @@ struct vs_index {
     int64_t stream_bytes = 0;
 
     // ---- timing hook
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int last_launches = 0;
-    bool timed = false;
+    cudaEvent_t ev0[VS_TIMER_SLOTS] = {}, ev1[VS_TIMER_SLOTS] = {};
+    int last_mode = VS_MODE_SCAN;  // kernel family the last search used
+    int timer_n = 0;         // launches recorded since the last reset (may exceed the ring)
 };
+
+// Plain-pointer view of an index passed BY VALUE to kernels (vs_index itself carries host-only state).
+struct WsView {
+    const uint4 *cols; const void *vals; const uint32_t *tails;
+    const uint32_t *part_win_begin; const uint32_t *part_row_begin; const uint32_t *row_chunk;
+    uint64_t *post_ptr; uint32_t *post_doc; void *post_val;
+    int64_t n_rows, n_cols;
+    int kind, store_dtype;
+};
+inline WsView ws_view(const vs_index *i) {
+    WsView v;
+    v.cols = i->cols; v.vals = i->vals; v.tails = i->tails;
+    v.part_win_begin = i->part_win_begin; v.part_row_begin = i->part_row_begin; v.row_chunk = i->row_chunk;
+    v.post_ptr = i->post_ptr; v.post_doc = i->post_doc; v.post_val = i->post_val;
+    v.n_rows = i->n_rows; v.n_cols = i->n_cols; v.kind = i->kind; v.store_dtype = i->store_dtype;
+    return v;
+}
 
 namespace vs {
 int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void *d_col, int col_dtype,
                    const void *d_val, int val_dtype, cudaStream_t st);
 int export_ws_csr(const vs_index *idx, int64_t *d_crow, int64_t *d_col, float *d_val, cudaStream_t st);
+int build_inverted(vs_index *idx, cudaStream_t st);
 }  // namespace vs

@@ -17,11 +17,11 @@
 // The [B, N] score matrix is never written.  A second tiny kernel (merge.cu) merges the
 // per-CTA lists.
 #include "index.cuh"
+#include "topk.cuh"
 
 namespace vs {
 
 constexpr int kScanThreads = 1024;
-constexpr int kStage = 64;  // per-warp staging entries
 
 struct ScanParams {
     const uint4 *cols;
@@ -107,45 +107,6 @@ __device__ __forceinline__ float chunk_dot(const Chunk<VT> &ch, const float *qs)
         }
         return a + b;
     }
-}
-
-// ---- candidate buffer management ---------------------------------------------------------
-struct CtaState {
-    uint64_t mbar;
-    uint64_t tau;       // current threshold key (0 = accept everything)
-    uint32_t cnt;       // entries in cbuf
-    uint32_t lock;
-};
-
-// Called by one whole warp holding the lock: shrink cbuf[0..n) to its k largest, publish tau.
-__device__ __forceinline__ int warp_prune(uint64_t *cbuf, int n, int k, uint32_t *hist, CtaState *st) {
-    const int lane = threadIdx.x & 31;
-    uint64_t kth = radix_kth_largest<false>(cbuf, n, k, hist, lane, 32);
-    int kept = warp_compact_ge(cbuf, n, kth);
-    if (lane == 0) *(volatile uint64_t *)&st->tau = kth;
-    return kept;
-}
-
-__device__ __forceinline__ void warp_flush(uint64_t *cbuf, uint64_t *stage, int n_stage, int k, int cap,
-                                           uint32_t *hist, CtaState *st) {
-    const int lane = threadIdx.x & 31;
-    __syncwarp();
-    if (lane == 0) {
-        while (atomicCAS(&st->lock, 0u, 1u) != 0u) __nanosleep(32);
-    }
-    __syncwarp();
-    __threadfence_block();
-    int c = (int)*(volatile uint32_t *)&st->cnt;
-    if (c + n_stage > cap) c = warp_prune(cbuf, c, k, hist, st);
-    for (int i = lane; i < n_stage; i += 32) cbuf[c + i] = stage[i];
-    __syncwarp();
-    __threadfence_block();
-    if (lane == 0) {
-        *(volatile uint32_t *)&st->cnt = (uint32_t)(c + n_stage);
-        __threadfence_block();
-        atomicExch(&st->lock, 0u);
-    }
-    __syncwarp();
 }
 
 template <int VT, int D>
@@ -234,15 +195,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
                         const uint64_t key = make_key(s, rid);
                         const uint64_t tau = *(volatile uint64_t *)&st.tau;
                         const bool ins = is_tail && key > tau;
-                        const uint32_t m = __ballot_sync(0xffffffffu, ins);
-                        if (m) {
-                            if (ins) stage[n_stage + __popc(m & lt)] = key;
-                            n_stage += __popc(m);
-                            if (n_stage > kStage - 32) {
-                                warp_flush(cbuf, stage, n_stage, p.k, p.cap, hist, &st);
-                                n_stage = 0;
-                            }
-                        }
+                        stage_insert(ins, key, stage, n_stage, cbuf, p.k, p.cap, hist, &st, lt);
                     }
                 }
             }
@@ -251,21 +204,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         __syncthreads();
 
         // ---- exact top-k of this CTA's rows, written unsorted (merge.cu sorts)
-        int n = (int)st.cnt;
-        uint64_t kth = 0;
-        if (n > p.k) kth = radix_kth_largest<true>(cbuf, n, p.k, hist, tid, kScanThreads);
-        uint64_t *out = p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k;
-        if (n > p.k) {
-            __shared__ uint32_t out_cnt;
-            if (tid == 0) out_cnt = 0;
-            __syncthreads();
-            for (int i = tid; i < n; i += kScanThreads) {
-                uint64_t x = cbuf[i];
-                if (x >= kth) out[atomicAdd(&out_cnt, 1u)] = x;
-            }
-        } else {
-            for (int i = tid; i < p.k; i += kScanThreads) out[i] = (i < n) ? cbuf[i] : 0ull;
-        }
+        cta_write_topk<kScanThreads>(cbuf, p.k, hist, &st, p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k);
         __syncthreads();  // everyone is done with qs / cbuf before the next pass overwrites them
     }
 }

@@ -161,9 +161,10 @@ class _Engine:
                                                   _stream_ptr(self.device)))
         return crow, col, val
 
-    def last_kernel_ms(self):
+    def kernel_timer(self, reset: bool = True):
+        """(summed device ms, launches) of the scan kernels launched since the last reset."""
         ms, n = ctypes.c_float(), ctypes.c_int()
-        nat.check(nat.LIB.vs_last_kernel_ms(self.handle, ms, n))
+        nat.check(nat.LIB.vs_kernel_timer(self.handle, int(reset), ms, n))
         return float(ms.value), int(n.value)
 
 
