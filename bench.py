@@ -59,10 +59,11 @@ def gen_rows(lo, hi, device, tokens=TOKENS, v=V):
     return torch.cat(parts, dim=0) if len(parts) > 1 else parts[0]
 
 
-def gen_queries(b=B, v=V, nnz=QNNZ, seed=4321):
+def gen_queries(b=None, v=V, nnz=QNNZ, seed=4321):
     """[b, v] fp32 dense-stored queries with `nnz` non-zeros each, U(0.01, 3) (host tensor)."""
     import torch
 
+    b = B if b is None else b
     g = torch.Generator().manual_seed(seed)
     cols = torch.rand(b, v, generator=g).topk(nnz, dim=1).indices
     vals = torch.rand(b, nnz, generator=g) * 2.99 + 0.01
@@ -256,15 +257,20 @@ def run_gpu(args):
     ms_e2e = timed(step_e2e, args.steps, min(args.warmup, 2)) / args.steps
     qps_e2e = B / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (scan + fused top-k) on algorithmic bytes
+    # ---- roofline of the dominant kernel on algorithmic bytes
     n_loc = hi - lo
-    bytes_pass = n_loc * TOKENS * 2 + (n_loc + 1) * 4        # nnz * b_col + (N+1) * b_ptr, binary: b_val = 0
-    passes_per_launch = B                                     # Q_tile = 1: one pass over the shard per query
+    used_mode = index.last_mode()
+    if used_mode == "scan":
+        bytes_pass = n_loc * TOKENS * 2 + (n_loc + 1) * 4    # nnz * b_col + (N+1) * b_ptr, binary: b_val = 0
+    else:  # K3: postings of the query's tokens (uint32 ids) + accumulator clear and read-back
+        bytes_pass = int(args.qnnz * (n_loc * TOKENS / V)) * 4 + 2 * n_loc * 4
+    passes_per_launch = B                                     # Q_tile = 1: one pass per query
     peak, peak_src = measured_peak()
     achieved = passes_per_launch * bytes_pass / (kern_ms / max(kern_n, 1) * 1e-3) / 1e9 if kern_ms > 0 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": profiled_traffic() if world == 1 else None,
-                "kernel": "vs::scan_topk_kernel<0,4>", "peak_source": peak_src,
+                "kernel": "vs::scan_topk_kernel<0,4>" if index.last_mode() == "scan" else "vs::inv_accum_kernel+inv_select_kernel",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": passes_per_launch * bytes_pass,
                 "streamed_bytes_per_launch": passes_per_launch * eng.stream_bytes,
                 "kernel_ms_per_launch": kern_ms / max(kern_n, 1), "launches_timed": kern_n,
@@ -280,10 +286,10 @@ def run_gpu(args):
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cfg2: binary bag-of-token index 21,015,324 x 29,523, 120 tokens/row, B=1024, "
+            "config": {"workload": f"cfg2: binary bag-of-token index {N_TOTAL:,} x 29,523, 120 tokens/row, B={B}, "
                                    f"{args.qnnz} nnz/query, k=100",
                        "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
-                       "mode": args.mode, "l2": "inputs larger than L2 (shard streams "
+                       "mode": args.mode, "mode_used": used_mode, "l2": "inputs larger than L2 (shard streams "
                                                 f"{eng.stream_bytes / 1e9:.2f} GB per query pass; L2 is 126 MB)",
                        "index_build_s": round(build_s, 2)},
             "clocks": clocks,
@@ -301,6 +307,7 @@ def run_gpu(args):
 
 
 def main():
+    global B, N_TOTAL
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -309,7 +316,10 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "scan", "inverted"])
     ap.add_argument("--qnnz", type=int, default=QNNZ)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=B, help="queries per step (default: the config's 1024; smaller only for profiling)")
+    ap.add_argument("--rows", type=int, default=N_TOTAL, help="index rows (default: the config's 21,015,324; smaller only for profiling)")
     args = ap.parse_args()
+    B, N_TOTAL = args.batch, args.rows
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -115,6 +115,9 @@ int vs_scores(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int
 int vs_merge_keys(int device, const uint64_t *d_keys_in, int64_t P, int64_t stride_p, int64_t stride_b,
                   int64_t B, int k_in, int k_out, int64_t *d_ids, float *d_scores, void *stream);
 
+/* which kernel family (VS_MODE_SCAN | VS_MODE_INVERTED) served the last search on this handle */
+int vs_index_last_mode(const vs_index *idx, int *mode);
+
 /* timing hook for bench.py: every scan/score kernel launch made through this handle is bracketed by a
  * CUDA event pair on the launching stream (a ring of VS_TIMER_SLOTS pairs).  Returns the summed device
  * time (ms) and the number of launches recorded since the last reset; reset != 0 clears the ring

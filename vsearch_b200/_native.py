@@ -23,7 +23,7 @@ MODES = {"auto": VS_MODE_AUTO, "scan": VS_MODE_SCAN, "inverted": VS_MODE_INVERTE
 SYMBOLS = [
     "vs_last_error", "vs_abi_version", "vs_index_create_csr", "vs_index_create_dense", "vs_index_destroy",
     "vs_index_info", "vs_index_export_csr", "vs_search_workspace_bytes", "vs_search", "vs_search_keys",
-    "vs_scores", "vs_merge_keys", "vs_kernel_timer",
+    "vs_scores", "vs_merge_keys", "vs_kernel_timer", "vs_index_last_mode",
 ]
 
 
@@ -58,6 +58,7 @@ def _load() -> ctypes.CDLL:
                               c_void_p]
     lib.vs_merge_keys.argtypes = [c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p]
+    lib.vs_index_last_mode.argtypes = [c_void_p, POINTER(c_int)]
     lib.vs_kernel_timer.argtypes = [c_void_p, c_int, POINTER(c_float), POINTER(c_int)]
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError here = header / library mismatch

@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" boundary declared in include/vsearch_b200.h.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -70,7 +71,7 @@ struct Workspace {
     void *inv;         // K3: query lists + accumulators
     size_t bytes;
 };
-constexpr int kInvGroup = 8;   // queries scored concurrently by the inverted-list path (accumulator rows)
+constexpr int kInvGroup = 1;   // queries scored concurrently by the inverted-list path (accumulator rows)
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 static Workspace carve(const vs_index *idx, void *base, int64_t Bc, int k) {
     Workspace w;
@@ -122,6 +123,7 @@ int vs_index_create_csr(int device, int64_t n_rows, int64_t n_cols, int64_t nnz,
     idx->kind = binary ? 2 : 1;
     idx->store_dtype = binary ? VS_NONE : store_dtype;
     idx->n_rows = n_rows; idx->n_cols = n_cols; idx->nnz = nnz;
+    if (const char *e = getenv("VSEARCH_B200_BANK_AWARE")) idx->bank_aware = (e[0] != '0');
 
     int rc;
     {
@@ -300,6 +302,12 @@ int vs_merge_keys(int device, const uint64_t *d_keys_in, int64_t P, int64_t stri
     VS_CUDA(cudaSetDevice(device));
     return launch_merge(d_keys_in, P, stride_p, stride_b, B, k_in, k_out, 0, d_ids, d_scores, nullptr,
                         (cudaStream_t)stream);
+}
+
+int vs_index_last_mode(const vs_index *idx, int *mode) {
+    VS_REQUIRE(idx != nullptr && mode != nullptr, VS_ERR_INVALID, "NULL pointer");
+    *mode = idx->last_mode;
+    return VS_OK;
 }
 
 int vs_kernel_timer(vs_index *idx, int reset, float *total_ms, int *launches) {

@@ -105,6 +105,17 @@ __device__ __forceinline__ void group_sync() {
     if constexpr (BLOCK) __syncthreads(); else __syncwarp();
 }
 
+// Histogram increment with warp aggregation: lanes holding the same digit elect one leader that adds their
+// count.  Candidate sets are full of ties (binary index, untouched rows of the inverted path): without this the
+// same-address shared atomics serialise 32-way.  Must be called by all 32 lanes.
+__device__ __forceinline__ void hist_add_aggregated(uint32_t *hist, uint32_t digit, bool active) {
+    const uint32_t amask = __ballot_sync(0xffffffffu, active);
+    if (active) {
+        const uint32_t peers = __match_any_sync(amask, digit);
+        if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+    }
+}
+
 // k-th largest of n UNIQUE 64-bit keys held in shared memory (1 <= k <= n).
 // 8 passes of 8-bit MSD radix select; `hist` is 256 words of shared memory owned by the group.
 // Called by all `nt` threads of the group (a warp when !BLOCK, the whole CTA when BLOCK).
@@ -116,9 +127,10 @@ __device__ uint64_t radix_kth_largest(const uint64_t *buf, int n, int k, uint32_
     for (int shift = 56; shift >= 0; shift -= 8) {
         for (int i = t; i < 256; i += nt) hist[i] = 0;
         group_sync<BLOCK>();
-        for (int i = t; i < n; i += nt) {
-            uint64_t x = buf[i];
-            if ((x & mask) == prefix) atomicAdd(&hist[(uint32_t)(x >> shift) & 255u], 1u);
+        for (int base = 0; base < n; base += nt) {  // warp-uniform trip count: hist_add_aggregated is convergent
+            const int i = base + t;
+            const uint64_t x = (i < n) ? buf[i] : 0ull;
+            hist_add_aggregated(hist, (uint32_t)(x >> shift) & 255u, (i < n) && ((x & mask) == prefix));
         }
         group_sync<BLOCK>();
         // every warp redundantly locates the digit: lane owns bins [8*lane, 8*lane+8)

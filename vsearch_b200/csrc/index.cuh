@@ -18,6 +18,12 @@
 #pragma once
 #include "common.cuh"
 
+// windows of readable slack allocated past the end of the cols/vals/tails streams (prefetch never checks bounds)
+constexpr int kStreamSlack = 8;
+// warps per persistent scan CTA (= stream parts per SM).  24 warps x 80 registers fills the register file;
+// 32 x 64 spills the prefetch ring.
+constexpr int kScanWarps = 24;
+
 struct vs_index {
     int device = 0;
     int kind = 0;         // 0 dense, 1 sparse (valued), 2 binary
@@ -25,8 +31,9 @@ struct vs_index {
     int64_t n_rows = 0, n_cols = 0, nnz = 0;
 
     // ---- WS format
+    bool bank_aware = true;   // bank-aware entry placement at build (VSEARCH_B200_BANK_AWARE=0 disables: A/B runs)
     int n_ctas = 0;           // persistent scan grid (= #SMs at build time)
-    int warps_per_cta = 32;
+    int warps_per_cta = kScanWarps;
     int n_parts = 0;          // n_ctas * warps_per_cta
     uint64_t n_windows = 0;
     uint4 *cols = nullptr;            // n_windows * 32 chunks

@@ -18,20 +18,21 @@
 namespace vs {
 
 constexpr int kInvThreads = 1024;
+constexpr int kBuildThreads = kScanWarps * 32;   // the builders walk the stream with the scan kernel's partition
 constexpr int kMaxQueryNnz = 4096;   // queries denser than this are served by the scan kernels
 
 // ------------------------------------------------------------------------------------------- build
 // Both build kernels walk the WS stream exactly like the scan kernel: warp = part, window by window.
 template <bool FILL>
-__global__ void __launch_bounds__(kInvThreads, 1)
+__global__ void __launch_bounds__(kBuildThreads, 1)
 inv_build_kernel(const WsView idx, uint32_t *cta_hist /* [n_ctas, V] counts (count pass) / offsets (fill pass) */) {
     extern __shared__ uint32_t s_cnt[];  // V counters
     const int V = (int)idx.n_cols;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *mine = cta_hist + (size_t)blockIdx.x * V;
-    for (int i = tid; i < V; i += kInvThreads) s_cnt[i] = FILL ? mine[i] : 0u;
+    for (int i = tid; i < V; i += kBuildThreads) s_cnt[i] = FILL ? mine[i] : 0u;
     __syncthreads();
-    const int part = blockIdx.x * 32 + warp;
+    const int part = blockIdx.x * kScanWarps + warp;
     const uint32_t w_begin = idx.part_win_begin[part];
     const int nwin = (int)(idx.part_win_begin[part + 1] - w_begin);
     uint32_t row = idx.part_row_begin[part];
@@ -61,7 +62,7 @@ inv_build_kernel(const WsView idx, uint32_t *cta_hist /* [n_ctas, V] counts (cou
     }
     if constexpr (!FILL) {
         __syncthreads();
-        for (int i = tid; i < V; i += kInvThreads) mine[i] = s_cnt[i];
+        for (int i = tid; i < V; i += kBuildThreads) mine[i] = s_cnt[i];
     }
 }
 
@@ -100,12 +101,12 @@ int build_inverted(vs_index *idx, cudaStream_t st) {
 
     VS_CUDA(cudaFuncSetAttribute(inv_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VS_CUDA(cudaFuncSetAttribute(inv_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    inv_build_kernel<false><<<idx->n_ctas, kInvThreads, smem, st>>>(ws_view(idx), d_hist);
+    inv_build_kernel<false><<<idx->n_ctas, kBuildThreads, smem, st>>>(ws_view(idx), d_hist);
     inv_offsets_kernel<<<(V + 1 + 255) / 256, 256, 0, st>>>(d_hist, idx->n_ctas, V, idx->post_ptr, d_err);
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, idx->post_ptr, idx->post_ptr, V + 1, st);
     VS_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16));
     cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, idx->post_ptr, idx->post_ptr, V + 1, st);
-    inv_build_kernel<true><<<idx->n_ctas, kInvThreads, smem, st>>>(ws_view(idx), d_hist);
+    inv_build_kernel<true><<<idx->n_ctas, kBuildThreads, smem, st>>>(ws_view(idx), d_hist);
     int h_err = 0;
     cudaError_t e = cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -219,20 +220,33 @@ __global__ void __launch_bounds__(256) inv_accum_kernel(const AccumParams p) {
     const uint32_t total = s_pref[cnt];
     float *acc = p.acc + (size_t)g * p.n_pad;
     const uint32_t stride = gridDim.x * 256u;
-    for (uint64_t idx64 = (uint64_t)blockIdx.x * 256u + tid; idx64 < total; idx64 += stride) {
-        const uint32_t idx = (uint32_t)idx64;
-        uint32_t lo = 0, hi = cnt;  // largest lo with s_pref[lo] <= idx
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (s_pref[mid] <= idx) lo = mid; else hi = mid;
+    // 4 independent postings per thread per trip: the id loads overlap, then the reductions are issued back to back
+    for (uint64_t idx64 = (uint64_t)blockIdx.x * 256u + tid; idx64 < total; idx64 += 4ull * stride) {
+        uint32_t doc[4];
+        float v[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t i64 = idx64 + (uint64_t)u * stride;
+            ok[u] = i64 < total;
+            const uint32_t idx = ok[u] ? (uint32_t)i64 : 0u;
+            uint32_t lo = 0, hi = cnt;  // largest lo with s_pref[lo] <= idx
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (s_pref[mid] <= idx) lo = mid; else hi = mid;
+            }
+            const uint64_t pos = s_base[lo] + (idx - s_pref[lo]);
+            doc[u] = ok[u] ? p.post_doc[pos] : 0u;
+            v[u] = s_w[lo];
+            if (ok[u]) {
+                if (p.val_kind == 1) v[u] *= ((const float *)p.post_val)[pos];
+                else if (p.val_kind == 2) v[u] *= __half2float(((const __half *)p.post_val)[pos]);
+                else if (p.val_kind == 3) v[u] *= __bfloat162float(((const __nv_bfloat16 *)p.post_val)[pos]);
+            }
         }
-        const uint64_t pos = s_base[lo] + (idx - s_pref[lo]);
-        const uint32_t doc = p.post_doc[pos];
-        float v = s_w[lo];
-        if (p.val_kind == 1) v *= ((const float *)p.post_val)[pos];
-        else if (p.val_kind == 2) v *= __half2float(((const __half *)p.post_val)[pos]);
-        else if (p.val_kind == 3) v *= __bfloat162float(((const __nv_bfloat16 *)p.post_val)[pos]);
-        atomicAdd(acc + doc, v);  // result unused -> RED.E.ADD.F32
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (ok[u]) atomicAdd(acc + doc[u], v[u]);  // result unused -> RED.E.ADD.F32
     }
 }
 
@@ -255,26 +269,45 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_select_kernel(const Select
     const int g = blockIdx.y, b = p.b0 + g;
     uint64_t *stage = stage_all + warp * kStage;
     const uint32_t lt = lanemask_lt();
-    if (tid == 0) { st.cnt = 0; st.tau = 0; st.lock = 0; }
+    if (tid == 0) { st.cnt = 0; st.tau = 0; st.tau_score = -INFINITY; st.lock = 0; }
     __syncthreads();
     float4 *acc4 = reinterpret_cast<float4 *>(p.acc + (size_t)g * p.n_pad);
     const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
     const int64_t r_end = min(p.n_rows, r_begin + p.rows_per_cta);
+    // ---- sampling phase: the first `cap` rows go straight into cbuf, then one CTA-wide select sets the threshold
+    for (int i = tid; i < (p.cap >> 2); i += kInvThreads) {
+        const int64_t r = r_begin + (int64_t)i * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < r_end) {
+            v = acc4[r >> 2];
+            acc4[r >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float s[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            cbuf[i * 4 + e] = (r + e < r_end) ? make_key(round_score(s[e], p.score_round), (uint32_t)(r + e)) : 0ull;
+    }
+    __syncthreads();
+    cta_sample_select<kInvThreads, 8192>(cbuf, p.cap, p.k, hist, &st);
     int n_stage = 0;
-    // warp-uniform trip count: every warp of the CTA iterates the same number of times
-    for (int64_t r = r_begin + (int64_t)tid * 4; r - (int64_t)lane * 4 < r_end; r += (int64_t)kInvThreads * 4) {
+    // ---- the rest: warp-uniform trip count (every lane of a warp iterates the same number of times)
+    for (int64_t r = r_begin + p.cap + (int64_t)tid * 4; r - (int64_t)lane * 4 < r_end; r += (int64_t)kInvThreads * 4) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool in = r < r_end;
         if (in) {
             v = acc4[r >> 2];
             acc4[r >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const float s[4] = {v.x, v.y, v.z, v.w};
+        const float s[4] = {round_score(v.x, p.score_round), round_score(v.y, p.score_round),
+                            round_score(v.z, p.score_round), round_score(v.w, p.score_round)};
+        const float tau_s = *(volatile float *)&st.tau_score;
+        const float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+        if (!__any_sync(0xffffffffu, in && mx >= tau_s)) continue;  // nothing in these 128 rows can qualify
         const uint64_t tau = *(volatile uint64_t *)&st.tau;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int64_t rid = r + e;
-            const uint64_t key = make_key(round_score(s[e], p.score_round), (uint32_t)rid);
+            const uint64_t key = make_key(s[e], (uint32_t)rid);
             const bool ins = in && rid < r_end && key > tau;
             stage_insert(ins, key, stage, n_stage, cbuf, p.k, p.cap, hist, &st, lt);
         }

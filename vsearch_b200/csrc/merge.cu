@@ -41,9 +41,10 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
         for (int shift = 56; shift >= 0; shift -= 8) {
             for (int i = tid; i < 256; i += kMergeThreads) hist[i] = 0;
             __syncthreads();
-            for (int64_t i = tid; i < n; i += kMergeThreads) {
-                uint64_t x = merge_load(p, b, i);
-                if ((x & mask) == prefix) atomicAdd(&hist[(uint32_t)(x >> shift) & 255u], 1u);
+            for (int64_t base = 0; base < n; base += kMergeThreads) {
+                const int64_t i = base + tid;
+                const uint64_t x = (i < n) ? merge_load(p, b, i) : 0ull;
+                hist_add_aggregated(hist, (uint32_t)(x >> shift) & 255u, (i < n) && ((x & mask) == prefix));
             }
             __syncthreads();
             uint32_t h[8], s = 0;

@@ -2,7 +2,7 @@
 // fused in (K5), for sm_100a.  Replaces `torch.matmul(q, vector.t())` + `scores.topk(k)`
 // (upstream src/ir/retriever/index.py:91-92) for SparseIndex / BoTIndex.
 //
-// One persistent CTA per SM, 32 warps.  Per query ("pass"):
+// One persistent CTA per SM, kScanWarps (24) warps.  Per query ("pass"):
 //   1. the dense fp32 query vector (V+1 slots, slot V = 0 for padding) is pulled into shared
 //      memory with 1-D bulk TMA copies (cp.async.bulk + mbarrier);
 //   2. every warp streams ITS part of the WS index (index.cuh): one 512-byte window per step,
@@ -21,7 +21,10 @@
 
 namespace vs {
 
-constexpr int kScanThreads = 1024;
+constexpr int kScanThreads = kScanWarps * 32;
+constexpr int kSampleRegion = 320;                      // sampling-phase keys per warp
+constexpr int kSampleKeys = kScanWarps * kSampleRegion;  // <= kCapMax
+constexpr int kCapMax = 8192;  static_assert(kScanWarps * 320 <= 8192, "sample must fit the candidate buffer");   // CTA candidate buffer entries (sampling phase fills it once per pass)
 
 struct ScanParams {
     const uint4 *cols;
@@ -49,22 +52,14 @@ template <> struct Chunk<2> { uint4 c; uint4 v; };
 template <> struct Chunk<3> { uint4 c; uint4 v; };
 
 template <int VT>
-__device__ __forceinline__ void load_chunk(Chunk<VT> &ch, const uint4 *cols, const void *vals, uint64_t chunk) {
-    ch.c = ldg_stream(cols + chunk);
+__device__ __forceinline__ void load_chunk(Chunk<VT> &ch, const uint4 *c, const uint4 *v) {
+    ch.c = ldg_stream(c);
     if constexpr (VT == 1) {
-        const uint4 *v = (const uint4 *)vals + chunk * 2;
         ch.v0 = ldg_stream(v);
         ch.v1 = ldg_stream(v + 1);
     } else if constexpr (VT >= 2) {
-        ch.v = ldg_stream((const uint4 *)vals + chunk);
+        ch.v = ldg_stream(v);
     }
-}
-
-template <int VT>
-__device__ __forceinline__ void sentinel_chunk(Chunk<VT> &ch, uint32_t s) {
-    ch.c = make_uint4(s, s, s, s);
-    if constexpr (VT == 1) { ch.v0 = make_uint4(0, 0, 0, 0); ch.v1 = make_uint4(0, 0, 0, 0); }
-    else if constexpr (VT >= 2) { ch.v = make_uint4(0, 0, 0, 0); }
 }
 
 __device__ __forceinline__ float half_lo(uint32_t x, int vt) {
@@ -76,15 +71,22 @@ __device__ __forceinline__ float half_hi(uint32_t x, int vt) {
     return __uint_as_float(x & 0xffff0000u);
 }
 
-// sum over the chunk's 8 entries of q[col] (* val)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// sum over the chunk's 8 entries of q[col] (* val).  qs = shared-space byte address of the query vector;
+// address = qs + col * 4 is one LEA per entry after the 16-bit extract.
 template <int VT>
-__device__ __forceinline__ float chunk_dot(const Chunk<VT> &ch, const float *qs) {
+__device__ __forceinline__ float chunk_dot(const Chunk<VT> &ch, const uint32_t qs) {
     const uint32_t w[4] = {ch.c.x, ch.c.y, ch.c.z, ch.c.w};
     float g[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        g[2 * i] = qs[w[i] & 0xffffu];
-        g[2 * i + 1] = qs[w[i] >> 16];
+        g[2 * i] = lds_f32(qs + (__byte_perm(w[i], 0, 0x4410) << 2));
+        g[2 * i + 1] = lds_f32(qs + (__byte_perm(w[i], 0, 0x4432) << 2));
     }
     if constexpr (VT == 0) {
         return ((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]));
@@ -109,24 +111,78 @@ __device__ __forceinline__ float chunk_dot(const Chunk<VT> &ch, const float *qs)
     }
 }
 
-template <int VT, int D>
+// Rare paths of a window, kept out of line so the streaming loop stays small.  They recompute their
+// shared-memory pointers from the launch parameters instead of holding them in registers.
+struct SmemLayout {
+    uint64_t *cbuf, *stage;
+    uint32_t *hist;
+};
+__device__ __forceinline__ SmemLayout smem_layout(uint8_t *smem, const ScanParams &p) {
+    SmemLayout L;
+    L.cbuf = reinterpret_cast<uint64_t *>(smem + (size_t)p.vpad * 4);
+    L.stage = L.cbuf + p.cap + (threadIdx.x >> 5) * kStage;
+    L.hist = reinterpret_cast<uint32_t *>(L.cbuf + p.cap + kScanWarps * kStage);
+    return L;
+}
+
+// One window of one warp: lane partial -> segmented scan -> row scores -> (SAMPLE) key into this warp's
+// sampling region, or (!SAMPLE) threshold test + staging.
+// PRE: every lane holds its chunk `cur`; T = tail mask of the window (warp-uniform).
+template <int VT, bool ROUND, bool DIAG, bool SAMPLE>
+__device__ __forceinline__ void process_window(const Chunk<VT> &cur, const uint32_t T, const uint32_t qs, const int lane,
+                                               const uint32_t lt, float &carry, uint32_t &row, int &n_stage,
+                                               int &n_sample, uint8_t *smem, CtaState *st, const ScanParams &p,
+                                               const int b) {
+    float v = chunk_dot<VT>(cur, qs);
+    if (lane == 0) v += carry;
+    // segmented inclusive scan: segments end at tail bits; `reach` = how many lanes back my segment extends
+    const uint32_t before = T & lt;
+    const int reach = lane - (32 - __clz(before));
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float o = __shfl_up_sync(0xffffffffu, v, d);
+        if (reach >= d) v += o;
+    }
+    carry = __shfl_sync(0xffffffffu, v, 31);
+    if (T >> 31) carry = 0.f;
+    const int rank = __popc(before);
+    const uint32_t rid = row + rank;
+    row += __popc(T);
+    const bool is_tail = (T >> lane) & 1u;
+    float s = v;
+    if constexpr (ROUND) s = round_score(v, p.score_round);
+    if constexpr (DIAG) {
+        if (is_tail) p.scores_out[(size_t)b * p.n_rows + rid] = s + 0.0f;
+    }
+    if constexpr (SAMPLE) {
+        uint64_t *region = reinterpret_cast<uint64_t *>(smem + (size_t)p.vpad * 4) + (threadIdx.x >> 5) * kSampleRegion;
+        if (is_tail) region[n_sample + rank] = make_key(s, rid);
+        n_sample += __popc(T);
+    } else {
+        // cheap float pre-filter against the score part of the threshold; exact test only for survivors
+        const float tau_s = *(volatile float *)&st->tau_score;
+        const bool maybe = is_tail && (s >= tau_s);
+        if (__any_sync(0xffffffffu, maybe)) {
+            const SmemLayout L = smem_layout(smem, p);
+            const uint64_t key = make_key(s, rid);
+            const uint64_t tau = *(volatile uint64_t *)&st->tau;
+            stage_insert(maybe && key > tau, key, L.stage, n_stage, L.cbuf, p.k, p.cap, L.hist, st, lt);
+        }
+    }
+}
+
+template <int VT, int D, bool ROUND, bool DIAG>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    float *qs = reinterpret_cast<float *>(smem);
-    uint64_t *cbuf = reinterpret_cast<uint64_t *>(smem + (size_t)p.vpad * 4);
-    uint64_t *stage_all = cbuf + p.cap;
-    uint32_t *hist = reinterpret_cast<uint32_t *>(stage_all + 32 * kStage);
     __shared__ CtaState st;
-
+    const uint32_t qs = smem_u32(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint64_t *stage = stage_all + warp * kStage;
     const uint32_t lt = lanemask_lt();
-    const int part = blockIdx.x * 32 + warp;
+    const int part = blockIdx.x * kScanWarps + warp;
     const uint32_t w_begin = p.part_win_begin[part];
     const int nwin = (int)(p.part_win_begin[part + 1] - w_begin);
     const uint32_t row0 = p.part_row_begin[part];
     const uint64_t chunk0 = (uint64_t)w_begin * 32ull + lane;
-    const uint32_t *tails = p.tails + w_begin;
     const uint32_t q_bytes = (uint32_t)p.vpad * 4u;
 
     if (tid == 0) {
@@ -143,6 +199,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         if (tid == 0) {
             st.cnt = 0;
             st.tau = 0;
+            st.tau_score = -INFINITY;
             fence_proxy_async();  // earlier generic-proxy reads of qs are ordered before the async writes
             mbar_arrive_expect_tx(&st.mbar, q_bytes);
             const uint8_t *src = reinterpret_cast<const uint8_t *>(p.q + (size_t)b * p.vpad);
@@ -155,56 +212,69 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         mbar_wait(&st.mbar, phase);
         phase ^= 1u;
 
-        // ---- stream this warp's part
+        // ---- stream this warp's part.  The stream carries kStreamSlack windows of slack past its end, so the
+        // prefetch ring never needs a bounds check: loads are unconditional, addresses are base + immediate.
+        const uint4 *cp = p.cols + chunk0;
+        const uint4 *vp = (VT == 1) ? (const uint4 *)p.vals + chunk0 * 2 : (const uint4 *)p.vals + chunk0;
+        const uint32_t *tp = p.tails + w_begin;
         Chunk<VT> ring[D];
         uint32_t tring[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            if (j < nwin) { load_chunk<VT>(ring[j], p.cols, p.vals, chunk0 + (uint64_t)j * 32ull); tring[j] = ldg_stream_u32(tails + j); }
-            else { sentinel_chunk<VT>(ring[j], p.sentinel); tring[j] = 0; }
+            load_chunk<VT>(ring[j], cp + j * 32, vp + j * (VT == 1 ? 64 : 32));
+            tring[j] = ldg_stream_u32(tp + j);
         }
         float carry = 0.f;
         uint32_t row = row0;
-        int n_stage = 0;
-        for (int w = 0; w < nwin; w += D) {
+        int n_stage = 0, n_sample = 0;
+        int w = 0;
+#define VS_STEP(SAMPLE, J)                                                                                         \
+    {                                                                                                              \
+        process_window<VT, ROUND, DIAG, SAMPLE>(ring[J], tring[J], qs, lane, lt, carry, row, n_stage, n_sample,    \
+                                                smem, &st, p, b);                                                  \
+        load_chunk<VT>(ring[J], cp + (D + J) * 32, vp + (D + J) * (VT == 1 ? 64 : 32));                            \
+        tring[J] = ldg_stream_u32(tp + D + J);                                                                     \
+    }
+#define VS_ADVANCE()                                                                                               \
+    {                                                                                                              \
+        cp += D * 32;                                                                                              \
+        vp += D * (VT == 1 ? 64 : 32);                                                                             \
+        tp += D;                                                                                                   \
+        w += D;                                                                                                    \
+    }
+        // ---- phase A: sampling.  Every row's key goes straight into this warp's region of cbuf (no threshold,
+        // no lock) until the region cannot take D more windows; then ONE CTA-wide select sets the threshold.
+        while (w + D <= nwin && n_sample + D * 32 <= kSampleRegion) {
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-                if (w + j < nwin) {  // warp-uniform
-                    Chunk<VT> cur = ring[j];
-                    const uint32_t T = tring[j];
-                    const int nx = w + j + D;
-                    if (nx < nwin) { load_chunk<VT>(ring[j], p.cols, p.vals, chunk0 + (uint64_t)nx * 32ull); tring[j] = ldg_stream_u32(tails + nx); }
-                    float v = chunk_dot<VT>(cur, qs);
-                    if (lane == 0) v += carry;
-                    // segmented inclusive scan: segments end at tail bits
-                    const uint32_t before = T & lt;
-                    const int start = 32 - __clz(before);  // first lane of my segment (0 when no tail before me)
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        float o = __shfl_up_sync(0xffffffffu, v, d);
-                        if (lane >= start + d) v += o;
-                    }
-                    const float last = __shfl_sync(0xffffffffu, v, 31);
-                    carry = (T >> 31) ? 0.f : last;
-                    const bool is_tail = (T >> lane) & 1u;
-                    const uint32_t rid = row + __popc(before);
-                    row += __popc(T);
-                    if (T) {  // warp-uniform: at least one row completes in this window
-                        const float s = round_score(v, p.score_round);
-                        if (p.scores_out != nullptr && is_tail) p.scores_out[(size_t)b * p.n_rows + rid] = s + 0.0f;
-                        const uint64_t key = make_key(s, rid);
-                        const uint64_t tau = *(volatile uint64_t *)&st.tau;
-                        const bool ins = is_tail && key > tau;
-                        stage_insert(ins, key, stage, n_stage, cbuf, p.k, p.cap, hist, &st, lt);
-                    }
-                }
-            }
+            for (int j = 0; j < D; ++j) VS_STEP(true, j)
+            VS_ADVANCE()
         }
-        if (n_stage) warp_flush(cbuf, stage, n_stage, p.k, p.cap, hist, &st);
-        __syncthreads();
-
-        // ---- exact top-k of this CTA's rows, written unsorted (merge.cu sorts)
-        cta_write_topk<kScanThreads>(cbuf, p.k, hist, &st, p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k);
+        {
+            const SmemLayout L = smem_layout(smem, p);
+            for (int i = n_sample + lane; i < kSampleRegion; i += 32) L.cbuf[warp * kSampleRegion + i] = 0ull;
+            __syncthreads();
+            cta_sample_select<kScanThreads, kCapMax>(L.cbuf, kSampleKeys, p.k, L.hist, &st);
+        }
+        // ---- phase B: steady state
+        while (w + D <= nwin) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) VS_STEP(false, j)
+            VS_ADVANCE()
+        }
+#pragma unroll
+        for (int j = 0; j < D - 1; ++j)
+            if (w + j < nwin) process_window<VT, ROUND, DIAG, false>(ring[j], tring[j], qs, lane, lt, carry, row, n_stage,
+                                                                     n_sample, smem, &st, p, b);
+#undef VS_STEP
+#undef VS_ADVANCE
+        {
+            const SmemLayout L = smem_layout(smem, p);
+            if (n_stage) warp_flush(L.cbuf, L.stage, n_stage, p.k, p.cap, L.hist, &st);
+            __syncthreads();
+            // ---- exact top-k of this CTA's rows, written unsorted (merge.cu sorts)
+            cta_write_topk<kScanThreads>(L.cbuf, p.k, L.hist, &st,
+                                         p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k);
+        }
         __syncthreads();  // everyone is done with qs / cbuf before the next pass overwrites them
     }
 }
@@ -227,10 +297,10 @@ __global__ void prep_query_kernel(const void *q, int q_dtype, int64_t ldq, int64
 }
 
 size_t scan_smem_bytes(int vpad, int cap) {
-    return (size_t)vpad * 4 + (size_t)cap * 8 + (size_t)32 * kStage * 8 + 256 * 4;
+    return (size_t)vpad * 4 + (size_t)cap * 8 + (size_t)kScanWarps * kStage * 8 + 256 * 4;
 }
 
-int scan_cap_for_k(int k) { return k <= 960 ? 4096 : 8192; }
+int scan_cap_for_k(int k) { (void)k; return kCapMax; }
 
 int launch_prep_query(const void *d_q, int q_dtype, int64_t B, int64_t ldq, int64_t n_cols, int vpad, int round_mode,
                       float *d_out, cudaStream_t st) {
@@ -242,13 +312,20 @@ int launch_prep_query(const void *d_q, int q_dtype, int64_t B, int64_t ldq, int6
     return VS_OK;
 }
 
-template <int VT, int D>
+template <int VT, int D, bool ROUND, bool DIAG>
 static int launch_scan_t(const vs_index *idx, const ScanParams &p, size_t smem, cudaStream_t st) {
-    auto kern = scan_topk_kernel<VT, D>;
+    auto kern = scan_topk_kernel<VT, D, ROUND, DIAG>;
     VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<idx->n_ctas, kScanThreads, smem, st>>>(p);
     VS_CUDA(cudaGetLastError());
     return VS_OK;
+}
+
+template <int VT, int D>
+static int launch_scan_v(const vs_index *idx, const ScanParams &p, size_t smem, cudaStream_t st) {
+    if (p.scores_out) return launch_scan_t<VT, D, true, true>(idx, p, smem, st);  // diagnostic path
+    if (p.score_round != VS_F32) return launch_scan_t<VT, D, true, false>(idx, p, smem, st);
+    return launch_scan_t<VT, D, false, false>(idx, p, smem, st);
 }
 
 // d_qprep: [B, vpad] fp32; d_cand: [B, n_ctas, k] keys; d_scores_out optional [B, N]
@@ -274,10 +351,11 @@ int launch_scan(const vs_index *idx, const float *d_qprep, int vpad, int64_t B, 
     VS_REQUIRE(smem <= 227 * 1024, VS_ERR_UNSUPPORTED,
                "n_cols=%lld needs %zu bytes of shared memory (> 227 KB): vocabulary too large for the scan kernel",
                (long long)idx->n_cols, smem);
-    if (idx->kind == 2) return launch_scan_t<0, 4>(idx, p, smem, st);
-    if (idx->store_dtype == VS_F32) return launch_scan_t<1, 2>(idx, p, smem, st);
-    if (idx->store_dtype == VS_F16) return launch_scan_t<2, 3>(idx, p, smem, st);
-    return launch_scan_t<3, 3>(idx, p, smem, st);
+    static_assert(kStreamSlack >= 8, "prefetch ring deeper than the stream slack");
+    if (idx->kind == 2) return launch_scan_v<0, 4>(idx, p, smem, st);
+    if (idx->store_dtype == VS_F32) return launch_scan_v<1, 2>(idx, p, smem, st);
+    if (idx->store_dtype == VS_F16) return launch_scan_v<2, 3>(idx, p, smem, st);
+    return launch_scan_v<3, 3>(idx, p, smem, st);
 }
 
 }  // namespace vs

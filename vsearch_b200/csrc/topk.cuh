@@ -13,6 +13,7 @@ constexpr int kStage = 64;  // per-warp staging entries
 struct CtaState {
     uint64_t mbar;
     uint64_t tau;       // current threshold key (0 = accept everything)
+    float tau_score;    // score part of tau (-inf while tau == 0): cheap pre-filter
     uint32_t cnt;       // entries in cbuf
     uint32_t lock;
 };
@@ -22,7 +23,10 @@ __device__ __forceinline__ int warp_prune(uint64_t *cbuf, int n, int k, uint32_t
     const int lane = threadIdx.x & 31;
     uint64_t kth = radix_kth_largest<false>(cbuf, n, k, hist, lane, 32);
     int kept = warp_compact_ge(cbuf, n, kth);
-    if (lane == 0) *(volatile uint64_t *)&st->tau = kth;
+    if (lane == 0) {
+        *(volatile float *)&st->tau_score = key_score(kth);
+        *(volatile uint64_t *)&st->tau = kth;
+    }
     return kept;
 }
 
@@ -61,6 +65,31 @@ __device__ __forceinline__ void stage_insert(bool ins, uint64_t key, uint64_t *s
             n_stage = 0;
         }
     }
+}
+
+// Sampling phase.  The first `cap` keys of a pass are written straight into cbuf (no threshold, no lock;
+// unused slots = 0).  Then the whole CTA calls this once (after a __syncthreads()): keep the k largest,
+// publish the threshold.  From here on only ~k/cap of the remaining rows pass the threshold, so the locked
+// flush / single-warp prune path below becomes the rare case instead of the start-up cost of every pass.
+template <int NT, int CAP_MAX>
+__device__ __forceinline__ void cta_sample_select(uint64_t *cbuf, int cap, int k, uint32_t *hist, CtaState *st) {
+    const int tid = threadIdx.x;
+    constexpr int PER = (CAP_MAX + NT - 1) / NT;
+    uint64_t mine[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { const int i = tid + j * NT; mine[j] = (i < cap) ? cbuf[i] : 0ull; }
+    // zeros are the only duplicates; they rank last, so the k-th largest is exact whenever >= k real keys exist
+    const uint64_t kth = radix_kth_largest<true>(cbuf, cap, k, hist, tid, NT);
+    if (tid == 0) st->cnt = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        if (mine[j] != 0ull && mine[j] >= kth) cbuf[atomicAdd(&st->cnt, 1u)] = mine[j];
+    if (tid == 0) {
+        st->tau = kth;  // 0 when the sample held fewer than k real keys: keep accepting everything
+        st->tau_score = kth ? key_score(kth) : -INFINITY;
+    }
+    __syncthreads();
 }
 
 // End of pass, called by the whole CTA after a __syncthreads(): exact top-k of cbuf -> out[0..k) (unsorted,

@@ -308,6 +308,12 @@ class Index:
             ids, scores = ids[0], scores[0]
         return SearchResults(ids, scores)
 
+    def last_mode(self) -> str:
+        """Kernel family the last search on this index used ("scan" | "inverted")."""
+        m = ctypes.c_int()
+        nat.check(nat.LIB.vs_index_last_mode(self._require_engine().handle, m))
+        return "inverted" if m.value == nat.VS_MODE_INVERTED else "scan"
+
     def search_keys(self, q_embs: torch.Tensor, k: int, id_offset: int = 0) -> torch.Tensor:
         """Packed rank keys ``[B, k]`` of this shard with global ids (row-sharded path, sharded.py)."""
         eng = self._require_engine()
