@@ -1,0 +1,91 @@
+"""K4: dense index (tcgen05 GEMM + fused top-k) against the oracle (torch fp32 matmul + canonical top-k)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_search
+from tests.util import golden_search_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _grid(shape, seed, scale=16.0, lim=32):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(-lim, lim + 1, shape, generator=g).float() / scale
+
+
+def _dense_index(x, dtype=torch.bfloat16):
+    import vsearch_b200 as vs
+
+    idx = vs.Index()
+    idx.vector = x.to(dtype)
+    idx.move_to_device("cuda:0")
+    return idx
+
+
+@pytest.mark.parametrize("name", golden_search_cases("dense"))
+def test_golden_dense(name, cuda_device):
+    z = load_golden(name)
+    x, q, k = torch.from_numpy(z["x"]), torch.from_numpy(z["q"]), z["k"]
+    exact = "grid" in name  # grid values are exact in bf16: every accumulation order gives the same fp32 bits
+    idx = _dense_index(x)
+    res = idx.search(q, k)
+    assert res.ids.dtype == torch.int64 and tuple(res.ids.shape) == (q.shape[0], k)
+    if exact:  # scores come back in the index dtype (index.py:89): round the reference the same way, then rank
+        canon = ref_search.canonical_topk(ref_search.quantize_like(torch.from_numpy(z["ref_scores"]), torch.bfloat16), k)
+        assert torch.equal(res.ids.cpu(), canon.ids)
+        assert torch.equal(res.scores.float().cpu(), canon.scores)
+    else:  # bf16 storage: quantise like the index, compare against the fp32 reference on those numbers (2e-3)
+        ref = ref_search.ref_scores(ref_search.quantize_like(q, torch.bfloat16), ref_search.quantize_like(x, torch.bfloat16))
+        canon = ref_search.canonical_topk(ref, k)
+        torch.testing.assert_close(res.scores.float().cpu(), canon.scores.to(torch.bfloat16).float(), rtol=2 ** -7, atol=1e-2)
+
+
+@pytest.mark.parametrize("n,d,B,k,dtype", [
+    (5000, 768, 7, 10, torch.bfloat16),       # one sample sweep only (N < sample)
+    (70_000, 768, 130, 100, torch.bfloat16),  # sample + filtered sweep, 2 query tiles, ragged N
+    (40_000, 128, 33, 1000, torch.float16),   # k = 1000, fp16 storage, D = 128
+    (300, 96, 3, 300, torch.bfloat16),        # k == N, D not a multiple of 64
+])
+def test_dense_grid_exact(n, d, B, k, dtype, cuda_device):
+    x, q = _grid((n, d), 1), _grid((B, d), 2)
+    idx = _dense_index(x, dtype)
+    res = idx.search(q, k)
+    assert res.scores.dtype == dtype
+    ref = ref_search.ref_scores(q, x)
+    # scores come back in the index dtype (index.py:89): compare ids exactly and scores after the same rounding
+    canon = ref_search.canonical_topk(ref_search.quantize_like(ref, dtype), k)
+    assert torch.equal(res.ids.cpu(), canon.ids), (res.ids.cpu() != canon.ids).nonzero()[:5]
+    assert torch.equal(res.scores.float().cpu(), canon.scores)
+
+
+def test_dense_heavy_ties_and_edges(cuda_device):
+    n, d = 30_000, 64
+    x = (_grid((n, d), 3, scale=1.0, lim=1)).float()   # entries in {-1, 0, 1}: integer scores, massive ties
+    q = (_grid((5, d), 4, scale=1.0, lim=1)).float()
+    q[1] = 0
+    idx = _dense_index(x)
+    ref = ref_search.ref_scores(q, x)
+    for k in (1, 100):
+        res = idx.search(q, k)
+        msg = ref_search.compare_results(ref_search.SearchResults(res.ids, res.scores.float()), ref, k, exact=True)
+        assert msg is None, f"k={k}: {msg}"
+    assert idx.search(q, 5).ids[1].tolist() == [0, 1, 2, 3, 4]
+    with pytest.raises(RuntimeError):
+        idx.search(q, n + 1)
+    assert tuple(idx.search(q[0], 4).ids.shape) == (4,)
+
+
+def test_dense_sorted_index_overflow_retry(cuda_device):
+    """Passages sorted by increasing score: the sample prefix gives a useless threshold, every row of the sweep
+    survives it, the candidate lists overflow and the kernel must tighten and repeat."""
+    n, d = 200_000, 64
+    x = torch.zeros(n, d)
+    x[:, 0] = torch.arange(n).float() / 4.0
+    q = torch.zeros(2, d)
+    q[0, 0], q[1, 0] = 1.0, -1.0
+    idx = _dense_index(x, torch.float16 if False else torch.bfloat16)
+    xq = ref_search.quantize_like(x, torch.bfloat16)
+    res = idx.search(q, 10)
+    canon = ref_search.canonical_topk(ref_search.quantize_like(ref_search.ref_scores(q, xq), torch.bfloat16), 10)
+    assert torch.equal(res.ids.cpu(), canon.ids)

@@ -30,6 +30,9 @@ int inverted_extract(vs_index *idx, const float *d_qprep, int vpad, int64_t Bc, 
 bool inverted_usable(uint32_t max_nnz, uint64_t max_postings);
 int launch_inverted(vs_index *idx, int64_t Bc, int k, int score_round, int group, uint32_t max_nnz, void *d_ws,
                     uint64_t *d_cand, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t st);
+size_t dense_workspace_bytes(const vs_index *idx, int64_t B, int k);
+int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t ldq, int k, int score_round,
+                 int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, void *d_ws, cudaStream_t st);
 int launch_merge(const uint64_t *d_in, int64_t P, int64_t stride_p, int64_t stride_b, int64_t B, int k_in, int k_out,
                  int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, cudaStream_t st);
 
@@ -149,10 +152,34 @@ int vs_index_create_csr(int device, int64_t n_rows, int64_t n_cols, int64_t nnz,
 
 int vs_index_create_dense(int device, int64_t n_rows, int64_t dim, const void *hd_x, int x_dtype, int64_t ld,
                           int store_dtype, void *stream, vs_index **out) {
-    (void)device; (void)n_rows; (void)dim; (void)hd_x; (void)x_dtype; (void)ld; (void)store_dtype; (void)stream;
-    if (out) *out = nullptr;
-    vs::set_error("dense index (K4 tcgen05 GEMM + fused top-k) is not built yet");
-    return VS_ERR_UNSUPPORTED;
+    VS_REQUIRE(out != nullptr, VS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    VS_REQUIRE(n_rows >= 0 && dim >= 1 && ld >= dim && hd_x != nullptr, VS_ERR_INVALID, "bad dense shape");
+    VS_REQUIRE(x_dtype == VS_F32 || x_dtype == VS_F16 || x_dtype == VS_BF16, VS_ERR_INVALID, "bad dense dtype");
+    VS_REQUIRE(store_dtype == VS_F16 || store_dtype == VS_BF16, VS_ERR_UNSUPPORTED,
+               "the dense index is stored as bf16 or fp16 (tcgen05 kind::f16); fp32 storage is not built");
+    VS_REQUIRE(n_rows < 0x7fffff00ll, VS_ERR_UNSUPPORTED, "n_rows must be < 2^31 per shard");
+    VS_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    vs_index *idx = new (std::nothrow) vs_index();
+    VS_REQUIRE(idx != nullptr, VS_ERR_NOMEM, "out of host memory");
+    idx->device = device; idx->kind = 0; idx->store_dtype = store_dtype;
+    idx->n_rows = n_rows; idx->n_cols = dim; idx->dim = dim; idx->nnz = n_rows * dim;
+    int rc;
+    {
+        Staged sx;
+        rc = sx.init(hd_x, (size_t)n_rows * ld * dtype_size(x_dtype), st);
+        if (rc == VS_OK) rc = build_dense_index(idx, sx.ptr, x_dtype, ld, st);
+        cudaStreamSynchronize(st);
+    }
+    for (int i = 0; i < VS_TIMER_SLOTS && rc == VS_OK; ++i)
+        if (cudaEventCreate(&idx->ev0[i]) != cudaSuccess || cudaEventCreate(&idx->ev1[i]) != cudaSuccess) {
+            set_error("cudaEventCreate failed");
+            rc = VS_ERR_CUDA;
+        }
+    if (rc != VS_OK) { vs_index_destroy(idx); return rc; }
+    *out = idx;
+    return VS_OK;
 }
 
 int vs_index_destroy(vs_index *idx) {
@@ -190,6 +217,7 @@ int vs_index_export_csr(const vs_index *idx, int64_t *d_crow, int64_t *d_col, fl
 
 size_t vs_search_workspace_bytes(const vs_index *idx, int64_t B, int k) {
     if (!idx || B <= 0 || k <= 0) return 256;
+    if (idx->kind == 0) return dense_workspace_bytes(idx, B, k) + 256;
     int64_t Bc = B < kQueryChunk ? B : kQueryChunk;
     return carve(idx, nullptr, Bc, k).bytes + 256;
 }
@@ -199,7 +227,6 @@ static int search_impl(const vs_index *cidx, const void *hd_q, int q_dtype, int6
                        float *d_scores_full, void *d_workspace, size_t workspace_bytes, void *stream) {
     vs_index *idx = const_cast<vs_index *>(cidx);
     VS_REQUIRE(idx != nullptr, VS_ERR_INVALID, "index is NULL");
-    VS_REQUIRE(idx->kind == 1 || idx->kind == 2, VS_ERR_UNSUPPORTED, "dense search is not built yet");
     VS_REQUIRE(B >= 0 && ldq >= idx->n_cols, VS_ERR_INVALID, "query leading dimension %lld < n_cols %lld", (long long)ldq,
                (long long)idx->n_cols);
     VS_REQUIRE(q_dtype == VS_F32 || q_dtype == VS_F16 || q_dtype == VS_BF16, VS_ERR_INVALID, "bad query dtype");
@@ -219,6 +246,15 @@ static int search_impl(const vs_index *cidx, const void *hd_q, int q_dtype, int6
     void *ws_base = (void *)(((uintptr_t)d_workspace + 255) / 256 * 256);
 
     const bool q_on_device = is_device_ptr(hd_q);
+    if (idx->kind == 0) {  // dense index: K4 (tcgen05 GEMM + fused top-k)
+        VS_REQUIRE(d_scores_full == nullptr, VS_ERR_UNSUPPORTED, "vs_scores is a sparse-path diagnostic");
+        Staged sq;
+        int rc = sq.init(hd_q, (size_t)B * ldq * dtype_size(q_dtype), st);
+        if (rc) return rc;
+        rc = search_dense(idx, sq.ptr, q_dtype, B, ldq, k, score_round, id_offset, d_ids, d_scores, d_keys, ws_base, st);
+        if (rc == VS_OK && sq.owned) VS_CUDA(cudaStreamSynchronize(st));
+        return rc;
+    }
     for (int64_t b0 = 0; b0 < B; b0 += kQueryChunk) {
         const int64_t Bc = (B - b0) < kQueryChunk ? (B - b0) : kQueryChunk;
         Workspace w = carve(idx, ws_base, Bc, k);

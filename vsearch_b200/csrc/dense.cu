@@ -1,0 +1,434 @@
+// dense.cu -- K4: dense index scoring on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), top-k fused into the
+// epilogue.  Replaces `torch.matmul(q, vector.t())` + `scores.topk(k)` (upstream src/ir/retriever/index.py:91-92)
+// for the strided `Index.vector` [N, D] (bf16 or fp16 storage, fp32 accumulate).
+//
+//   S[b, n] = sum_d Q[b, d] * X[n, d]      A = Q tile [128 queries, 64] , B = X tile [256 passages, 64], both K-major
+//
+// One persistent CTA per SM, warp-specialised (192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the A / B k-blocks (128-byte swizzle) into a
+//               4-stage shared-memory ring, completion on mbarriers
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) x4
+//               per k-block into one of two 256-column TMEM accumulators; tcgen05.commit frees the smem stage /
+//               signals the epilogue
+//   warps 2-5   epilogue: tcgen05.ld the accumulator (thread = query row, 32 columns at a time), never write S:
+//               mode 0 (sample)    emit every score of the tile as a rank key (small sample prefix of the index)
+//               mode 1 (filter)    compare against the per-query threshold; survivors are appended to the
+//                                  query's candidate list with one global atomic
+// Each CTA owns passage tiles nt = blockIdx.x, +gridDim.x, ... and sweeps all query tiles for a passage tile, so X
+// is read from HBM once and re-read from L2.
+//
+// Host side (search_dense): threshold from an exact top-k of a sample prefix -> one filtered sweep over the whole
+// index -> exact top-k of the survivors with the K6 merge kernel.  If a candidate list overflows (adversarial
+// ordering) the threshold is tightened from the stored candidates and the sweep repeated.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <vector>
+
+#include "index.cuh"
+
+namespace vs {
+
+constexpr int kBM = 128, kBN = 256, kBK = 64, kStages = 4;
+constexpr int kDenseThreads = 192;
+constexpr uint32_t kStageBytesA = kBM * kBK * 2, kStageBytesB = kBN * kBK * 2;
+constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;  // 48 KB
+constexpr int kTmemCols = 512;
+
+struct DenseArgs {
+    int n_tiles_m, n_tiles_n, k_blocks;
+    int64_t n_rows;        // real passages (rows >= n_rows of the padded matrix are ignored)
+    int64_t n_queries;     // real queries
+    int64_t row_offset;    // first passage row of this sweep (sample sweeps start at 0)
+    int mode;              // 0 sample: write keys [n_queries, sample_ld]; 1 filter
+    int score_round;
+    uint32_t idesc;
+    uint64_t *sample_keys; int64_t sample_ld;
+    const uint64_t *tau;   // [n_queries] threshold keys (mode 1)
+    uint64_t *cand; uint32_t *cand_cnt; int64_t cand_cap;  // [n_queries, cand_cap], [n_queries]
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(kDenseThreads, 1)
+dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, const DenseArgs a) {
+    extern __shared__ __align__(1024) uint8_t dsmem[];
+    // dynamic smem: [stages x (A 16 KB | B 32 KB)] [barriers] ; 1024-byte alignment is required by SWIZZLE_128B
+    uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)dsmem + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(base);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + kStages * kStageBytes);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + kStages * 8;
+    const uint32_t bar_tfull = bar_empty + kStages * 8, bar_tempty = bar_tfull + 2 * 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_x) : "memory");
+        for (int s = 0; s < kStages; ++s) { mbar_init(bars + s, 1); mbar_init(bars + kStages + s, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bars + 2 * kStages + i, 1); mbar_init(bars + 2 * kStages + 2 + i, 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int nt = blockIdx.x; nt < a.n_tiles_n; nt += gridDim.x)
+                for (int mt = 0; mt < a.n_tiles_m; ++mt)
+                    for (int kb = 0; kb < a.k_blocks; ++kb) {
+                        mbar_wait_u32(bar_empty + stage * 8, phase ^ 1u);
+                        mbar_expect_tx(bar_full + stage * 8, kStageBytes);
+                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        tma_load_2d(sa, &tmap_q, kb * kBK, mt * kBM, bar_full + stage * 8);
+                        tma_load_2d(sa + kStageBytesA, &tmap_x, kb * kBK, (int)(a.row_offset) + nt * kBN, bar_full + stage * 8);
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int nt = blockIdx.x; nt < a.n_tiles_n; nt += gridDim.x)
+                for (int mt = 0; mt < a.n_tiles_m; ++mt) {
+                    mbar_wait_u32(bar_tempty + acc * 8, acc_phase ^ 1u);  // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)acc * kBN;
+                    for (int kb = 0; kb < a.k_blocks; ++kb) {
+                        mbar_wait_u32(bar_full + stage * 8, phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        const uint64_t da = umma_desc(sa), db = umma_desc(sa + kStageBytesA);
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k)   // +32 bytes (2 x 16 B) per UMMA_K inside the swizzle atom
+                            tc_mma_f16(d, da + 2 * k, db + 2 * k, a.idesc, (kb | k) != 0);
+                        tc_commit(bar_empty + stage * 8);      // smem stage free once these MMAs have read it
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit(bar_tfull + acc * 8);            // accumulator complete
+                    acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+                }
+        }
+    } else {
+        // ================= epilogue (warps 2..5 <-> TMEM lane quarters 2,3,0,1) =================
+        const int quarter = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int nt = blockIdx.x; nt < a.n_tiles_n; nt += gridDim.x)
+            for (int mt = 0; mt < a.n_tiles_m; ++mt) {
+                mbar_wait_u32(bar_tfull + acc * 8, acc_phase);
+                tc_fence_after();
+                const int64_t q = (int64_t)mt * kBM + quarter * 32 + lane;   // this thread's query row
+                const bool q_ok = q < a.n_queries;
+                const int64_t n0 = a.row_offset + (int64_t)nt * kBN;         // first passage of the tile
+                uint64_t tau = 0; float tau_s = -INFINITY;
+                if (a.mode == 1 && q_ok) { tau = a.tau[q]; tau_s = tau ? key_score(tau) : -INFINITY; }
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kBN;
+#pragma unroll 1
+                for (int c = 0; c < kBN / 32; ++c) {
+                    uint32_t r[32];
+                    tc_ld32(taddr + c * 32, r);
+                    const int64_t nb = n0 + c * 32;
+                    if (!q_ok) {
+                        // padded query row: nothing to emit
+                    } else if (a.mode == 0) {
+                        uint64_t *dst = a.sample_keys + q * a.sample_ld + (nb - a.row_offset);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int64_t n = nb + j;
+                            const float s = round_score(__uint_as_float(r[j]), a.score_round);
+                            dst[j] = (n < a.n_rows) ? make_key(s, (uint32_t)n) : 0ull;
+                        }
+                    } else {
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                        if (a.score_round != VS_F32) mx = round_score(mx, a.score_round);
+                        if (mx >= tau_s) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int64_t n = nb + j;
+                                const float s = round_score(__uint_as_float(r[j]), a.score_round);
+                                if (s >= tau_s && n < a.n_rows) {
+                                    const uint64_t key = make_key(s, (uint32_t)n);
+                                    if (key >= tau) {
+                                        const uint32_t pos = atomicAdd(a.cand_cnt + q, 1u);
+                                        if (pos < (uint32_t)a.cand_cap) a.cand[q * a.cand_cap + pos] = key;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
+                acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- operand preparation ---------------------------------------------------------------------------------
+// rows of `in` ([rows, ld] f32 / f16 / bf16) -> 16-bit storage [rows_pad, d_pad] (zero padded)
+__global__ void dense_convert_kernel(const void *in, int in_dtype, int64_t rows, int64_t dim, int64_t ld,
+                                     uint16_t *out, int out_dtype, int64_t rows_pad, int64_t d_pad) {
+    const int64_t total = rows_pad * d_pad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / d_pad, c = i - r * d_pad;
+        float v = 0.f;
+        if (r < rows && c < dim) {
+            if (in_dtype == VS_F32) v = ((const float *)in)[r * ld + c];
+            else if (in_dtype == VS_F16) v = __half2float(((const __half *)in)[r * ld + c]);
+            else v = __bfloat162float(((const __nv_bfloat16 *)in)[r * ld + c]);
+        }
+        out[i] = (out_dtype == VS_F16) ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    }
+}
+
+// tau[q] = keys[q * ld + k - 1] (k-th best of the sample), or 0 when the sample has fewer than k rows
+__global__ void dense_tau_kernel(const uint64_t *sorted_keys, int64_t ld, int k, int64_t n_queries, uint64_t *tau) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n_queries) tau[q] = sorted_keys[q * ld + (k - 1)];
+}
+
+static PFN_cuTensorMapEncodeTiled get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled)p;
+    }
+    return fn;
+}
+
+// 2-D K-major tensor map: [rows, d_pad] 16-bit, box = 64 columns x box_rows rows, 128-byte swizzle
+static int make_tmap(CUtensorMap *map, const void *ptr, int dtype, int64_t rows, int64_t d_pad, int box_rows) {
+    PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
+    VS_REQUIRE(enc != nullptr, VS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dtype == VS_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VS_REQUIRE(r == CUDA_SUCCESS, VS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return VS_OK;
+}
+
+int build_dense_index(vs_index *idx, const void *d_x, int x_dtype, int64_t ld, cudaStream_t st) {
+    idx->d_pad = (idx->dim + kBK - 1) / kBK * kBK;
+    idx->n_pad = (idx->n_rows + kBN - 1) / kBN * kBN;
+    if (idx->n_pad == 0) idx->n_pad = kBN;
+    VS_CUDA(cudaMalloc(&idx->dense, (size_t)idx->n_pad * idx->d_pad * 2));
+    dense_convert_kernel<<<2048, 256, 0, st>>>(d_x, x_dtype, idx->n_rows, idx->dim, ld, (uint16_t *)idx->dense,
+                                               idx->store_dtype, idx->n_pad, idx->d_pad);
+    VS_CUDA(cudaGetLastError());
+    VS_CUDA(cudaStreamSynchronize(st));
+    cudaDeviceProp prop;
+    VS_CUDA(cudaGetDeviceProperties(&prop, idx->device));
+    idx->n_ctas = prop.multiProcessorCount;
+    idx->device_bytes = idx->n_pad * idx->d_pad * 2;
+    idx->stream_bytes = idx->device_bytes;
+    return VS_OK;
+}
+
+int launch_merge(const uint64_t *d_in, int64_t P, int64_t stride_p, int64_t stride_b, int64_t B, int k_in, int k_out,
+                 int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, cudaStream_t st);
+int launch_merge_counted(const uint64_t *d_in, const uint32_t *d_counts, int64_t P, int64_t stride_p, int64_t stride_b,
+                         int64_t B, int k_in, int k_out, int64_t id_offset, int64_t *d_ids, float *d_scores,
+                         uint64_t *d_keys, cudaStream_t st);
+
+// workspace carve for one query chunk
+struct DenseWs {
+    uint16_t *q16;        // [b_pad, d_pad]
+    uint64_t *sample;     // [Bc, sample_rows]
+    uint64_t *tau;        // [Bc]
+    uint64_t *tau_sorted; // [Bc, k]
+    uint32_t *cnt;        // [Bc]
+    uint64_t *cand;       // [Bc, cap]
+    size_t bytes;
+};
+constexpr int64_t kDenseQueryChunk = 4096;
+constexpr int64_t kDenseCandCap = 1 << 16;   // per-query survivor list (keys)
+
+static int64_t dense_sample_rows(const vs_index *idx, int k) {
+    // sample prefix: ~256*k rows (>= 16 K), a whole number of tiles, at most the index
+    int64_t s = (int64_t)k * 256;
+    if (s < 16384) s = 16384;
+    s = (s + kBN - 1) / kBN * kBN;
+    return s < idx->n_pad ? s : idx->n_pad;
+}
+
+static DenseWs carve_dense(const vs_index *idx, void *base, int64_t Bc, int k) {
+    DenseWs w;
+    auto al = [](size_t x) { return (x + 1023) / 1024 * 1024; };
+    const int64_t b_pad = (Bc + kBM - 1) / kBM * kBM;
+    size_t o = 0;
+    uint8_t *p = (uint8_t *)base;
+    w.q16 = (uint16_t *)(p + o); o += al((size_t)b_pad * idx->d_pad * 2);
+    w.sample = (uint64_t *)(p + o); o += al((size_t)Bc * dense_sample_rows(idx, k) * 8);
+    w.tau = (uint64_t *)(p + o); o += al((size_t)Bc * 8);
+    w.tau_sorted = (uint64_t *)(p + o); o += al((size_t)Bc * k * 8);
+    w.cnt = (uint32_t *)(p + o); o += al((size_t)Bc * 4);
+    w.cand = (uint64_t *)(p + o); o += al((size_t)Bc * kDenseCandCap * 8);
+    w.bytes = o;
+    return w;
+}
+
+size_t dense_workspace_bytes(const vs_index *idx, int64_t B, int k) {
+    int64_t Bc = B < kDenseQueryChunk ? B : kDenseQueryChunk;
+    return carve_dense(idx, nullptr, Bc, k).bytes + 1024;
+}
+
+static int launch_dense(const vs_index *idx, const CUtensorMap &tq, const CUtensorMap &tx, DenseArgs a, cudaStream_t st) {
+    const size_t smem = (size_t)kStages * kStageBytes + 256 + 1024;
+    VS_CUDA(cudaFuncSetAttribute(dense_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = idx->n_ctas < a.n_tiles_n ? idx->n_ctas : a.n_tiles_n;
+    dense_topk_kernel<<<grid, kDenseThreads, smem, st>>>(tq, tx, a);
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// d_q: device queries [B, ldq]; outputs like the sparse path (ids/scores or keys).  SYNC (reads survivor counts).
+int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t ldq, int k, int score_round,
+                 int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, void *d_ws, cudaStream_t st) {
+    VS_REQUIRE(idx->n_rows + id_offset < 0xffffffffll, VS_ERR_UNSUPPORTED, "global ids must fit 32 bits");
+    CUtensorMap tx;
+    int rc = make_tmap(&tx, idx->dense, idx->store_dtype, idx->n_pad, idx->d_pad, kBN);
+    if (rc) return rc;
+    const uint32_t fmt = idx->store_dtype == VS_F16 ? 0u : 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    void *ws_base = (void *)(((uintptr_t)d_ws + 1023) / 1024 * 1024);
+    for (int64_t b0 = 0; b0 < B; b0 += kDenseQueryChunk) {
+        const int64_t Bc = (B - b0) < kDenseQueryChunk ? (B - b0) : kDenseQueryChunk;
+        const int64_t b_pad = (Bc + kBM - 1) / kBM * kBM;
+        DenseWs w = carve_dense(idx, ws_base, Bc, k);
+        const uint8_t *qsrc = (const uint8_t *)d_q + (size_t)b0 * ldq * (q_dtype == VS_F32 ? 4 : 2);
+        dense_convert_kernel<<<1024, 256, 0, st>>>(qsrc, q_dtype, Bc, idx->dim, ldq, w.q16, idx->store_dtype, b_pad, idx->d_pad);
+        CUtensorMap tq;
+        rc = make_tmap(&tq, w.q16, idx->store_dtype, b_pad, idx->d_pad, kBM);
+        if (rc) return rc;
+        DenseArgs a;
+        a.n_tiles_m = (int)(b_pad / kBM);
+        a.k_blocks = (int)(idx->d_pad / kBK);
+        a.n_rows = idx->n_rows; a.n_queries = Bc; a.row_offset = 0;
+        a.score_round = score_round; a.idesc = idesc;
+        a.sample_keys = w.sample; a.tau = w.tau; a.cand = w.cand; a.cand_cnt = w.cnt; a.cand_cap = kDenseCandCap;
+
+        // ---- phase 1: exact top-k of a sample prefix -> per-query threshold
+        const int64_t srows = dense_sample_rows(idx, k);
+        a.mode = 0; a.n_tiles_n = (int)(srows / kBN); a.sample_ld = srows;
+        const int slot = idx->timer_n < VS_TIMER_SLOTS ? idx->timer_n : -1;
+        if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev0[slot], st));
+        rc = launch_dense(idx, tq, tx, a, st);
+        if (rc) return rc;
+        const int64_t s_real = srows < idx->n_rows ? srows : idx->n_rows;
+        if (s_real >= idx->n_rows) {
+            // the sample IS the index (small index): its top-k is the answer
+            if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
+            idx->timer_n += 1;
+            rc = launch_merge(w.sample, 1, 0, srows, Bc, (int)srows, k, id_offset, d_ids ? d_ids + b0 * k : nullptr,
+                              d_scores ? d_scores + b0 * k : nullptr, d_keys ? d_keys + b0 * k : nullptr, st);
+            if (rc) return rc;
+            continue;
+        }
+        rc = launch_merge(w.sample, 1, 0, srows, Bc, (int)srows, k, 0, nullptr, nullptr, w.tau_sorted, st);
+        if (rc) return rc;
+        dense_tau_kernel<<<(unsigned)((Bc + 255) / 256), 256, 0, st>>>(w.tau_sorted, k, k, Bc, w.tau);
+
+        // ---- phase 2: filtered sweep over the whole index; repeat with a tighter threshold on overflow
+        for (int attempt = 0;; ++attempt) {
+            VS_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)Bc * 4, st));
+            a.mode = 1; a.n_tiles_n = (int)(idx->n_pad / kBN);
+            rc = launch_dense(idx, tq, tx, a, st);
+            if (rc) return rc;
+            std::vector<uint32_t> h_cnt((size_t)Bc);
+            VS_CUDA(cudaMemcpyAsync(h_cnt.data(), w.cnt, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
+            VS_CUDA(cudaStreamSynchronize(st));
+            uint32_t mx = 0;
+            for (int64_t i = 0; i < Bc; ++i) mx = h_cnt[i] > mx ? h_cnt[i] : mx;
+            if (mx <= (uint32_t)kDenseCandCap) break;
+            VS_REQUIRE(attempt < 8, VS_ERR_UNSUPPORTED, "dense candidate lists keep overflowing");
+            // tighten: new tau = k-th best of the kDenseCandCap stored candidates (a valid lower bound)
+            rc = launch_merge_counted(w.cand, w.cnt, 1, 0, kDenseCandCap, Bc, (int)kDenseCandCap, k, 0, nullptr, nullptr,
+                                      w.tau_sorted, st);
+            if (rc) return rc;
+            dense_tau_kernel<<<(unsigned)((Bc + 255) / 256), 256, 0, st>>>(w.tau_sorted, k, k, Bc, w.tau);
+        }
+        if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
+        idx->timer_n += 1;
+        // exact top-k of the survivors (only the first cnt[q] entries of each list are valid)
+        rc = launch_merge_counted(w.cand, w.cnt, 1, 0, kDenseCandCap, Bc, (int)kDenseCandCap, k, id_offset,
+                                  d_ids ? d_ids + b0 * k : nullptr, d_scores ? d_scores + b0 * k : nullptr,
+                                  d_keys ? d_keys + b0 * k : nullptr, st);
+        if (rc) return rc;
+    }
+    return VS_OK;
+}
+
+}  // namespace vs

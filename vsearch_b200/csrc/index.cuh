@@ -51,8 +51,8 @@ struct vs_index {
     int64_t inv_bytes = 0;
 
     // ---- dense
-    int64_t dim = 0;
-    void *dense = nullptr;
+    int64_t dim = 0, d_pad = 0, n_pad = 0;   // logical width; width / rows padded to the GEMM tile
+    void *dense = nullptr;                   // [n_pad, d_pad] bf16 or fp16, K-major
 
     int64_t device_bytes = 0;
     int64_t stream_bytes = 0;
@@ -85,4 +85,5 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
                    const void *d_val, int val_dtype, cudaStream_t st);
 int export_ws_csr(const vs_index *idx, int64_t *d_crow, int64_t *d_col, float *d_val, cudaStream_t st);
 int build_inverted(vs_index *idx, cudaStream_t st);
+int build_dense_index(vs_index *idx, const void *d_x, int x_dtype, int64_t ld, cudaStream_t st);
 }  // namespace vs

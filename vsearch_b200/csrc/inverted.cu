@@ -262,20 +262,19 @@ struct SelectParams {
 __global__ void __launch_bounds__(kInvThreads, 1) inv_select_kernel(const SelectParams p) {
     extern __shared__ __align__(128) uint8_t ssmem[];
     uint64_t *cbuf = reinterpret_cast<uint64_t *>(ssmem);
-    uint64_t *stage_all = cbuf + p.cap;
-    uint32_t *hist = reinterpret_cast<uint32_t *>(stage_all + 32 * kStage);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(cbuf + kCapMax);
     __shared__ CtaState st;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kInvThreads / 32;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int g = blockIdx.y, b = p.b0 + g;
-    uint64_t *stage = stage_all + warp * kStage;
     const uint32_t lt = lanemask_lt();
-    if (tid == 0) { st.cnt = 0; st.tau = 0; st.tau_score = -INFINITY; st.lock = 0; }
+    if (tid == 0) { cta_state_reset(&st); st.lock = 0; }
     __syncthreads();
     float4 *acc4 = reinterpret_cast<float4 *>(p.acc + (size_t)g * p.n_pad);
     const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
     const int64_t r_end = min(p.n_rows, r_begin + p.rows_per_cta);
-    // ---- sampling phase: the first `cap` rows go straight into cbuf, then one CTA-wide select sets the threshold
-    for (int i = tid; i < (p.cap >> 2); i += kInvThreads) {
+    // ---- phase A: the first kCapMax rows go straight into cbuf, then one CTA-wide select sets the threshold
+    for (int i = tid; i < (kCapMax >> 2); i += kInvThreads) {
         const int64_t r = r_begin + (int64_t)i * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < r_end) {
@@ -288,33 +287,47 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_select_kernel(const Select
             cbuf[i * 4 + e] = (r + e < r_end) ? make_key(round_score(s[e], p.score_round), (uint32_t)(r + e)) : 0ull;
     }
     __syncthreads();
-    cta_sample_select<kInvThreads, 8192>(cbuf, p.cap, p.k, hist, &st);
-    int n_stage = 0;
-    // ---- the rest: warp-uniform trip count (every lane of a warp iterates the same number of times)
-    for (int64_t r = r_begin + p.cap + (int64_t)tid * 4; r - (int64_t)lane * 4 < r_end; r += (int64_t)kInvThreads * 4) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool in = r < r_end;
-        if (in) {
-            v = acc4[r >> 2];
-            acc4[r >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const float s[4] = {round_score(v.x, p.score_round), round_score(v.y, p.score_round),
-                            round_score(v.z, p.score_round), round_score(v.w, p.score_round)};
-        const float tau_s = *(volatile float *)&st.tau_score;
-        const float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
-        if (!__any_sync(0xffffffffu, in && mx >= tau_s)) continue;  // nothing in these 128 rows can qualify
-        const uint64_t tau = *(volatile uint64_t *)&st.tau;
+    cta_sample_select<kInvThreads>(cbuf, kCapMax, p.k, hist, &st);
+    int n_priv = 0;
+    // ---- phase B: warp-uniform trip count (every lane of a warp iterates the same number of times).
+    // kSelU float4 loads per thread are issued before any of the zeroing stores: interleaving a load and a store
+    // to the same line per trip runs 3-5x slower (scripts/micro/red_stream.cu, measured on B200).
+    constexpr int kSelU = 4;
+    for (int64_t r = r_begin + kCapMax + (int64_t)tid * 4; r - (int64_t)lane * 4 < r_end;
+         r += (int64_t)kInvThreads * 4 * kSelU) {
+        float4 v[kSelU];
+        bool in[kSelU];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int64_t rid = r + e;
-            const uint64_t key = make_key(s[e], (uint32_t)rid);
-            const bool ins = in && rid < r_end && key > tau;
-            stage_insert(ins, key, stage, n_stage, cbuf, p.k, p.cap, hist, &st, lt);
+        for (int u = 0; u < kSelU; ++u) {
+            const int64_t ru = r + (int64_t)u * kInvThreads * 4;
+            in[u] = ru < r_end;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in[u]) v[u] = acc4[ru >> 2];
+        }
+#pragma unroll
+        for (int u = 0; u < kSelU; ++u) {
+            const int64_t ru = r + (int64_t)u * kInvThreads * 4;
+            if (in[u]) acc4[ru >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kSelU; ++u) {
+            const int64_t ru = r + (int64_t)u * kInvThreads * 4;
+            const float s[4] = {round_score(v[u].x, p.score_round), round_score(v[u].y, p.score_round),
+                                round_score(v[u].z, p.score_round), round_score(v[u].w, p.score_round)};
+            const float tau_s = *(volatile float *)&st.tau_score;
+            const float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+            if (!__any_sync(0xffffffffu, in[u] && mx >= tau_s)) continue;  // nothing in these 128 rows can qualify
+            const uint64_t tau = *(volatile uint64_t *)&st.tau;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t rid = ru + e;
+                const uint64_t key = make_key(s[e], (uint32_t)rid);
+                private_insert<NW>(in[u] && rid < r_end && key > tau, key, cbuf, n_priv, p.k, hist, &st, lt);
+            }
         }
     }
-    if (n_stage) warp_flush(cbuf, stage, n_stage, p.k, p.cap, hist, &st);
-    __syncthreads();
-    cta_write_topk<kInvThreads>(cbuf, p.k, hist, &st, p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k);
+    cta_write_topk<kInvThreads, NW>(cbuf, n_priv, p.k, hist, &st,
+                                    p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k);
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -380,7 +393,7 @@ int launch_inverted(vs_index *idx, int64_t Bc, int k, int score_round, int group
     float *acc = (float *)acc_base;
     VS_CUDA(cudaMemsetAsync(acc, 0, (size_t)group * n_pad * 4, st));
     const int cap = scan_cap_for_k(k);
-    const size_t sel_smem = (size_t)cap * 8 + (size_t)32 * kStage * 8 + 256 * 4;
+    const size_t sel_smem = (size_t)kCapMax * 8 + 256 * 4;
     VS_CUDA(cudaFuncSetAttribute(inv_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     const size_t acc_smem = ((size_t)max_nnz + 1) * 4 + 16 + (size_t)max_nnz * 12 + 16;
     VS_CUDA(cudaFuncSetAttribute(inv_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_smem));

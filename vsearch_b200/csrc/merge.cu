@@ -11,6 +11,7 @@ constexpr int kMergeThreads = 512;
 
 struct MergeParams {
     const uint64_t *in;
+    const uint32_t *counts;   // optional [P, B]: only the first counts[p, b] entries of a list are valid
     int64_t P, stride_p, stride_b;
     int k_in, k_out;
     int64_t id_offset;
@@ -21,6 +22,7 @@ struct MergeParams {
 
 __device__ __forceinline__ uint64_t merge_load(const MergeParams &p, int64_t b, int64_t i) {
     int64_t pp = i / p.k_in, j = i - pp * p.k_in;
+    if (p.counts != nullptr && j >= (int64_t)p.counts[pp * gridDim.x + b]) return 0ull;
     return p.in[pp * p.stride_p + b * p.stride_b + j];
 }
 
@@ -112,14 +114,24 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
     }
 }
 
+int launch_merge_counted(const uint64_t *d_in, const uint32_t *d_counts, int64_t P, int64_t stride_p, int64_t stride_b,
+                         int64_t B, int k_in, int k_out, int64_t id_offset, int64_t *d_ids, float *d_scores,
+                         uint64_t *d_keys, cudaStream_t st);
+
 int launch_merge(const uint64_t *d_in, int64_t P, int64_t stride_p, int64_t stride_b, int64_t B, int k_in, int k_out,
                  int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, cudaStream_t st) {
+    return launch_merge_counted(d_in, nullptr, P, stride_p, stride_b, B, k_in, k_out, id_offset, d_ids, d_scores, d_keys, st);
+}
+
+int launch_merge_counted(const uint64_t *d_in, const uint32_t *d_counts, int64_t P, int64_t stride_p, int64_t stride_b,
+                         int64_t B, int k_in, int k_out, int64_t id_offset, int64_t *d_ids, float *d_scores,
+                         uint64_t *d_keys, cudaStream_t st) {
     if (B == 0) return VS_OK;
     VS_REQUIRE(k_out >= 1 && k_out <= VS_MAX_K, VS_ERR_INVALID, "k=%d outside [1, %d]", k_out, VS_MAX_K);
     int k_pow2 = 2;
     while (k_pow2 < k_out) k_pow2 <<= 1;
     MergeParams p;
-    p.in = d_in; p.P = P; p.stride_p = stride_p; p.stride_b = stride_b;
+    p.in = d_in; p.counts = d_counts; p.P = P; p.stride_p = stride_p; p.stride_b = stride_b;
     p.k_in = k_in; p.k_out = k_out; p.id_offset = id_offset;
     p.ids = d_ids; p.scores = d_scores; p.keys = d_keys;
     merge_topk_kernel<<<(unsigned)B, kMergeThreads, (size_t)k_pow2 * 8, st>>>(p, k_pow2);

@@ -22,9 +22,9 @@
 namespace vs {
 
 constexpr int kScanThreads = kScanWarps * 32;
-constexpr int kSampleRegion = 320;                      // sampling-phase keys per warp
-constexpr int kSampleKeys = kScanWarps * kSampleRegion;  // <= kCapMax
-constexpr int kCapMax = 8192;  static_assert(kScanWarps * 320 <= 8192, "sample must fit the candidate buffer");   // CTA candidate buffer entries (sampling phase fills it once per pass)
+using ScanGeom = TopkGeom<kScanWarps>;
+constexpr int kSampleRegion = ScanGeom::kSample;          // sampling-phase keys per warp
+constexpr int kSampleKeys = kScanWarps * kSampleRegion;   // <= kCapMax
 
 struct ScanParams {
     const uint4 *cols;
@@ -114,14 +114,13 @@ __device__ __forceinline__ float chunk_dot(const Chunk<VT> &ch, const uint32_t q
 // Rare paths of a window, kept out of line so the streaming loop stays small.  They recompute their
 // shared-memory pointers from the launch parameters instead of holding them in registers.
 struct SmemLayout {
-    uint64_t *cbuf, *stage;
+    uint64_t *cbuf;
     uint32_t *hist;
 };
 __device__ __forceinline__ SmemLayout smem_layout(uint8_t *smem, const ScanParams &p) {
     SmemLayout L;
     L.cbuf = reinterpret_cast<uint64_t *>(smem + (size_t)p.vpad * 4);
-    L.stage = L.cbuf + p.cap + (threadIdx.x >> 5) * kStage;
-    L.hist = reinterpret_cast<uint32_t *>(L.cbuf + p.cap + kScanWarps * kStage);
+    L.hist = reinterpret_cast<uint32_t *>(L.cbuf + kCapMax);
     return L;
 }
 
@@ -130,9 +129,8 @@ __device__ __forceinline__ SmemLayout smem_layout(uint8_t *smem, const ScanParam
 // PRE: every lane holds its chunk `cur`; T = tail mask of the window (warp-uniform).
 template <int VT, bool ROUND, bool DIAG, bool SAMPLE>
 __device__ __forceinline__ void process_window(const Chunk<VT> &cur, const uint32_t T, const uint32_t qs, const int lane,
-                                               const uint32_t lt, float &carry, uint32_t &row, int &n_stage,
-                                               int &n_sample, uint8_t *smem, CtaState *st, const ScanParams &p,
-                                               const int b) {
+                                               const uint32_t lt, float &carry, uint32_t &row, int &n_keys,
+                                               uint8_t *smem, CtaState *st, const ScanParams &p, const int b) {
     float v = chunk_dot<VT>(cur, qs);
     if (lane == 0) v += carry;
     // segmented inclusive scan: segments end at tail bits; `reach` = how many lanes back my segment extends
@@ -156,8 +154,8 @@ __device__ __forceinline__ void process_window(const Chunk<VT> &cur, const uint3
     }
     if constexpr (SAMPLE) {
         uint64_t *region = reinterpret_cast<uint64_t *>(smem + (size_t)p.vpad * 4) + (threadIdx.x >> 5) * kSampleRegion;
-        if (is_tail) region[n_sample + rank] = make_key(s, rid);
-        n_sample += __popc(T);
+        if (is_tail) region[n_keys + rank] = make_key(s, rid);
+        n_keys += __popc(T);
     } else {
         // cheap float pre-filter against the score part of the threshold; exact test only for survivors
         const float tau_s = *(volatile float *)&st->tau_score;
@@ -166,7 +164,7 @@ __device__ __forceinline__ void process_window(const Chunk<VT> &cur, const uint3
             const SmemLayout L = smem_layout(smem, p);
             const uint64_t key = make_key(s, rid);
             const uint64_t tau = *(volatile uint64_t *)&st->tau;
-            stage_insert(maybe && key > tau, key, L.stage, n_stage, L.cbuf, p.k, p.cap, L.hist, st, lt);
+            private_insert<kScanWarps>(maybe && key > tau, key, L.cbuf, n_keys, p.k, L.hist, st, lt);
         }
     }
 }
@@ -197,9 +195,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     for (int b = 0; b < p.B; ++b) {
         // ---- stage the query vector: bulk TMA into shared memory
         if (tid == 0) {
-            st.cnt = 0;
-            st.tau = 0;
-            st.tau_score = -INFINITY;
+            cta_state_reset(&st);
             fence_proxy_async();  // earlier generic-proxy reads of qs are ordered before the async writes
             mbar_arrive_expect_tx(&st.mbar, q_bytes);
             const uint8_t *src = reinterpret_cast<const uint8_t *>(p.q + (size_t)b * p.vpad);
@@ -226,12 +222,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         }
         float carry = 0.f;
         uint32_t row = row0;
-        int n_stage = 0, n_sample = 0;
+        int n_keys = 0;   // phase A: keys in this warp's sample slice; phase B: keys in its private region
         int w = 0;
 #define VS_STEP(SAMPLE, J)                                                                                         \
     {                                                                                                              \
-        process_window<VT, ROUND, DIAG, SAMPLE>(ring[J], tring[J], qs, lane, lt, carry, row, n_stage, n_sample,    \
-                                                smem, &st, p, b);                                                  \
+        process_window<VT, ROUND, DIAG, SAMPLE>(ring[J], tring[J], qs, lane, lt, carry, row, n_keys, smem, &st,    \
+                                                p, b);                                                             \
         load_chunk<VT>(ring[J], cp + (D + J) * 32, vp + (D + J) * (VT == 1 ? 64 : 32));                            \
         tring[J] = ldg_stream_u32(tp + D + J);                                                                     \
     }
@@ -244,16 +240,17 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     }
         // ---- phase A: sampling.  Every row's key goes straight into this warp's region of cbuf (no threshold,
         // no lock) until the region cannot take D more windows; then ONE CTA-wide select sets the threshold.
-        while (w + D <= nwin && n_sample + D * 32 <= kSampleRegion) {
+        while (w + D <= nwin && n_keys + D * 32 <= kSampleRegion) {
 #pragma unroll
             for (int j = 0; j < D; ++j) VS_STEP(true, j)
             VS_ADVANCE()
         }
         {
             const SmemLayout L = smem_layout(smem, p);
-            for (int i = n_sample + lane; i < kSampleRegion; i += 32) L.cbuf[warp * kSampleRegion + i] = 0ull;
+            for (int i = n_keys + lane; i < kSampleRegion; i += 32) L.cbuf[warp * kSampleRegion + i] = 0ull;
             __syncthreads();
-            cta_sample_select<kScanThreads, kCapMax>(L.cbuf, kSampleKeys, p.k, L.hist, &st);
+            cta_sample_select<kScanThreads>(L.cbuf, kSampleKeys, p.k, L.hist, &st);
+            n_keys = 0;
         }
         // ---- phase B: steady state
         while (w + D <= nwin) {
@@ -263,17 +260,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         }
 #pragma unroll
         for (int j = 0; j < D - 1; ++j)
-            if (w + j < nwin) process_window<VT, ROUND, DIAG, false>(ring[j], tring[j], qs, lane, lt, carry, row, n_stage,
-                                                                     n_sample, smem, &st, p, b);
+            if (w + j < nwin) process_window<VT, ROUND, DIAG, false>(ring[j], tring[j], qs, lane, lt, carry, row, n_keys,
+                                                                     smem, &st, p, b);
 #undef VS_STEP
 #undef VS_ADVANCE
         {
-            const SmemLayout L = smem_layout(smem, p);
-            if (n_stage) warp_flush(L.cbuf, L.stage, n_stage, p.k, p.cap, L.hist, &st);
-            __syncthreads();
             // ---- exact top-k of this CTA's rows, written unsorted (merge.cu sorts)
-            cta_write_topk<kScanThreads>(L.cbuf, p.k, L.hist, &st,
-                                         p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k);
+            const SmemLayout L = smem_layout(smem, p);
+            cta_write_topk<kScanThreads, kScanWarps>(L.cbuf, n_keys, p.k, L.hist, &st,
+                                                     p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k);
         }
         __syncthreads();  // everyone is done with qs / cbuf before the next pass overwrites them
     }
@@ -297,7 +292,8 @@ __global__ void prep_query_kernel(const void *q, int q_dtype, int64_t ldq, int64
 }
 
 size_t scan_smem_bytes(int vpad, int cap) {
-    return (size_t)vpad * 4 + (size_t)cap * 8 + (size_t)kScanWarps * kStage * 8 + 256 * 4;
+    (void)cap;
+    return (size_t)vpad * 4 + (size_t)kCapMax * 8 + 256 * 4;
 }
 
 int scan_cap_for_k(int k) { (void)k; return kCapMax; }

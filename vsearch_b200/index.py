@@ -97,6 +97,25 @@ class _Engine:
         nat.check(rc)
         return cls(handle, device)
 
+    @classmethod
+    def from_dense(cls, x: torch.Tensor, device, store_dtype) -> "_Engine":
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("vsearch_b200 searches on CUDA devices only (no CPU fallback)")
+        if x.dim() != 2:
+            raise ValueError("dense index must be [N, D]")
+        if x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            x = x.to(torch.float32)
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            rc = nat.LIB.vs_index_create_dense(device.index, x.shape[0], x.shape[1], x.data_ptr(), _TORCH2VS[x.dtype],
+                                               x.stride(0), _TORCH2VS[store_dtype], _stream_ptr(device),
+                                               ctypes.byref(handle))
+        nat.check(rc)
+        return cls(handle, device)
+
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
         if h:
@@ -281,7 +300,15 @@ class Index:
         return d
 
     def _build_engine(self, device):
-        raise NotImplementedError("dense index (K4) is not built yet")
+        """Dense ``[N, D]`` vector -> bf16 / fp16 K-major device copy for the tcgen05 kernel (K4)."""
+        dev = self._resolve(device)
+        v = self._vector
+        if v.layout != torch.strided:
+            raise TypeError("the dense Index needs a strided [N, D] vector; use SparseIndex / BoTIndex for CSR")
+        store = torch.float16 if v.dtype == torch.float16 else torch.bfloat16
+        if v.dtype not in (torch.float16, torch.bfloat16):
+            logger.warning("dense index of dtype %s is stored as bfloat16 on the device (tensor-core path)", v.dtype)
+        self._engine = _Engine.from_dense(v.to(dev), dev, store)
 
     def _require_engine(self) -> _Engine:
         if self._engine is None:
