@@ -105,14 +105,20 @@ __device__ __forceinline__ void group_sync() {
     if constexpr (BLOCK) __syncthreads(); else __syncwarp();
 }
 
-// Histogram increment with warp aggregation: lanes holding the same digit elect one leader that adds their
-// count.  Candidate sets are full of ties (binary index, untouched rows of the inverted path): without this the
-// same-address shared atomics serialise 32-way.  Must be called by all 32 lanes.
+// Histogram increment.  Candidate sets are full of ties (binary index, untouched rows of the inverted path): when
+// every active lane of the warp holds the same digit -- the case that would serialise 32-way on one shared-memory
+// word -- one leader adds the whole count; otherwise plain per-lane atomics.  (__match_any_sync would aggregate the
+// mixed case too, but MATCH.ANY costs more than the conflicts it removes: measured, profiles/README.md.)
+// Must be called by all 32 lanes.
 __device__ __forceinline__ void hist_add_aggregated(uint32_t *hist, uint32_t digit, bool active) {
     const uint32_t amask = __ballot_sync(0xffffffffu, active);
-    if (active) {
-        const uint32_t peers = __match_any_sync(amask, digit);
-        if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+    if (amask == 0) return;
+    const int leader = __ffs(amask) - 1;
+    const uint32_t d0 = __shfl_sync(0xffffffffu, digit, leader);
+    if (__all_sync(0xffffffffu, !active || digit == d0)) {
+        if ((int)(threadIdx.x & 31) == leader) atomicAdd(&hist[d0], (uint32_t)__popc(amask));
+    } else if (active) {
+        atomicAdd(&hist[digit], 1u);
     }
 }
 

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_select_kernel(const Select
     const int tid = threadIdx.x, lane = tid & 31;
     const int g = blockIdx.y, b = p.b0 + g;
     const uint32_t lt = lanemask_lt();
-    if (tid == 0) { cta_state_reset(&st); st.lock = 0; }
+    if (tid == 0) cta_state_reset(&st);
     __syncthreads();
     float4 *acc4 = reinterpret_cast<float4 *>(p.acc + (size_t)g * p.n_pad);
     const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
@@ -289,10 +289,12 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_select_kernel(const Select
     __syncthreads();
     cta_sample_select<kInvThreads>(cbuf, kCapMax, p.k, hist, &st);
     int n_priv = 0;
+    uint32_t epoch = 0;
     // ---- phase B: warp-uniform trip count (every lane of a warp iterates the same number of times).
     // kSelU float4 loads per thread are issued before any of the zeroing stores: interleaving a load and a store
     // to the same line per trip runs 3-5x slower (scripts/micro/red_stream.cu, measured on B200).
     constexpr int kSelU = 4;
+    static_assert(TopkGeom<NW>::kPrivate >= 128 + 32, "private region must take one 128-row step");
     for (int64_t r = r_begin + kCapMax + (int64_t)tid * 4; r - (int64_t)lane * 4 < r_end;
          r += (int64_t)kInvThreads * 4 * kSelU) {
         float4 v[kSelU];
@@ -314,18 +316,22 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_select_kernel(const Select
             const int64_t ru = r + (int64_t)u * kInvThreads * 4;
             const float s[4] = {round_score(v[u].x, p.score_round), round_score(v[u].y, p.score_round),
                                 round_score(v[u].z, p.score_round), round_score(v[u].w, p.score_round)};
-            const float tau_s = *(volatile float *)&st.tau_score;
+            const uint64_t gate = gate_load(&st);
+            const float tau_s = gate_tau_score(gate);
             const float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
-            if (!__any_sync(0xffffffffu, in[u] && mx >= tau_s)) continue;  // nothing in these 128 rows can qualify
-            const uint64_t tau = *(volatile uint64_t *)&st.tau;
+            if (__any_sync(0xffffffffu, in[u] && mx >= tau_s)) {  // else nothing in these 128 rows can qualify
+                const uint64_t tau = *(volatile uint64_t *)&st.tau;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int64_t rid = ru + e;
-                const uint64_t key = make_key(s[e], (uint32_t)rid);
-                private_insert<NW>(in[u] && rid < r_end && key > tau, key, cbuf, n_priv, p.k, hist, &st, lt);
+                for (int e = 0; e < 4; ++e) {
+                    const int64_t rid = ru + e;
+                    const uint64_t key = make_key(s[e], (uint32_t)rid);
+                    private_insert<NW>(in[u] && rid < r_end && key > tau, key, cbuf, n_priv, lt);
+                }
             }
+            join_if_needed<kInvThreads, NW>(gate, epoch, 128, cbuf, n_priv, p.k, hist, &st);
         }
     }
+    finish_streaming<kInvThreads, NW>(epoch, cbuf, n_priv, p.k, hist, &st);
     cta_write_topk<kInvThreads, NW>(cbuf, n_priv, p.k, hist, &st,
                                     p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k);
 }

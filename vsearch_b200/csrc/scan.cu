@@ -130,7 +130,8 @@ __device__ __forceinline__ SmemLayout smem_layout(uint8_t *smem, const ScanParam
 template <int VT, bool ROUND, bool DIAG, bool SAMPLE>
 __device__ __forceinline__ void process_window(const Chunk<VT> &cur, const uint32_t T, const uint32_t qs, const int lane,
                                                const uint32_t lt, float &carry, uint32_t &row, int &n_keys,
-                                               uint8_t *smem, CtaState *st, const ScanParams &p, const int b) {
+                                               const float tau_s, uint8_t *smem, CtaState *st, const ScanParams &p,
+                                               const int b) {
     float v = chunk_dot<VT>(cur, qs);
     if (lane == 0) v += carry;
     // segmented inclusive scan: segments end at tail bits; `reach` = how many lanes back my segment extends
@@ -157,14 +158,14 @@ __device__ __forceinline__ void process_window(const Chunk<VT> &cur, const uint3
         if (is_tail) region[n_keys + rank] = make_key(s, rid);
         n_keys += __popc(T);
     } else {
-        // cheap float pre-filter against the score part of the threshold; exact test only for survivors
-        const float tau_s = *(volatile float *)&st->tau_score;
+        // cheap float pre-filter against the score part of the threshold (read once per group of windows);
+        // exact 64-bit test only for survivors
         const bool maybe = is_tail && (s >= tau_s);
         if (__any_sync(0xffffffffu, maybe)) {
             const SmemLayout L = smem_layout(smem, p);
             const uint64_t key = make_key(s, rid);
             const uint64_t tau = *(volatile uint64_t *)&st->tau;
-            private_insert<kScanWarps>(maybe && key > tau, key, L.cbuf, n_keys, p.k, L.hist, st, lt);
+            private_insert<kScanWarps>(maybe && key > tau, key, L.cbuf, n_keys, lt);
         }
     }
 }
@@ -185,7 +186,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
 
     if (tid == 0) {
         mbar_init(&st.mbar, 1);
-        st.lock = 0;
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         int w = 0;
 #define VS_STEP(SAMPLE, J)                                                                                         \
     {                                                                                                              \
-        process_window<VT, ROUND, DIAG, SAMPLE>(ring[J], tring[J], qs, lane, lt, carry, row, n_keys, smem, &st,    \
-                                                p, b);                                                             \
+        process_window<VT, ROUND, DIAG, SAMPLE>(ring[J], tring[J], qs, lane, lt, carry, row, n_keys, tau_s, smem,  \
+                                                &st, p, b);                                                        \
         load_chunk<VT>(ring[J], cp + (D + J) * 32, vp + (D + J) * (VT == 1 ? 64 : 32));                            \
         tring[J] = ldg_stream_u32(tp + D + J);                                                                     \
     }
@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     }
         // ---- phase A: sampling.  Every row's key goes straight into this warp's region of cbuf (no threshold,
         // no lock) until the region cannot take D more windows; then ONE CTA-wide select sets the threshold.
+        float tau_s = -INFINITY;
         while (w + D <= nwin && n_keys + D * 32 <= kSampleRegion) {
 #pragma unroll
             for (int j = 0; j < D; ++j) VS_STEP(true, j)
@@ -252,21 +253,28 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             cta_sample_select<kScanThreads>(L.cbuf, kSampleKeys, p.k, L.hist, &st);
             n_keys = 0;
         }
-        // ---- phase B: steady state
+        // ---- phase B: steady state.  Once per group of D windows: one 64-bit "gate" load (float threshold + join
+        // epoch), and a join when somebody asked for a re-selection or this warp's region cannot take D more windows.
+        uint32_t epoch = 0;
+        const SmemLayout L = smem_layout(smem, p);
         while (w + D <= nwin) {
+            const uint64_t gate = gate_load(&st);
+            tau_s = gate_tau_score(gate);
 #pragma unroll
             for (int j = 0; j < D; ++j) VS_STEP(false, j)
             VS_ADVANCE()
+            join_if_needed<kScanThreads, kScanWarps>(gate, epoch, D * 32, L.cbuf, n_keys, p.k, L.hist, &st);
         }
+        tau_s = gate_tau_score(gate_load(&st));
 #pragma unroll
         for (int j = 0; j < D - 1; ++j)
             if (w + j < nwin) process_window<VT, ROUND, DIAG, false>(ring[j], tring[j], qs, lane, lt, carry, row, n_keys,
-                                                                     smem, &st, p, b);
+                                                                     tau_s, smem, &st, p, b);
+        finish_streaming<kScanThreads, kScanWarps>(epoch, L.cbuf, n_keys, p.k, L.hist, &st);
 #undef VS_STEP
 #undef VS_ADVANCE
         {
             // ---- exact top-k of this CTA's rows, written unsorted (merge.cu sorts)
-            const SmemLayout L = smem_layout(smem, p);
             cta_write_topk<kScanThreads, kScanWarps>(L.cbuf, n_keys, p.k, L.hist, &st,
                                                      p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k);
         }
@@ -348,6 +356,7 @@ int launch_scan(const vs_index *idx, const float *d_qprep, int vpad, int64_t B, 
                "n_cols=%lld needs %zu bytes of shared memory (> 227 KB): vocabulary too large for the scan kernel",
                (long long)idx->n_cols, smem);
     static_assert(kStreamSlack >= 8, "prefetch ring deeper than the stream slack");
+    static_assert(ScanGeom::kPrivate >= 2 * 4 * 32, "private region must hold two groups of windows");
     if (idx->kind == 2) return launch_scan_v<0, 4>(idx, p, smem, st);
     if (idx->store_dtype == VS_F32) return launch_scan_v<1, 2>(idx, p, smem, st);
     if (idx->store_dtype == VS_F16) return launch_scan_v<2, 3>(idx, p, smem, st);

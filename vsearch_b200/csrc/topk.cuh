@@ -6,9 +6,11 @@
 //                       threshold, no lock); ONE CTA-wide radix select keeps the k best in cbuf[0, k) and
 //                       publishes the threshold tau (and its score part, for a cheap float pre-filter);
 //   phase B  steady     only ~k/sample of the remaining rows beat tau.  Each warp appends them to its PRIVATE
-//                       region cbuf[kSharedKeys + warp*R, ...) with plain stores.  When a private region
-//                       fills (rare) that warp alone, under a shared-memory lock, merges it into the shared
-//                       top-k set cbuf[0, k) and raises tau; the other warps keep streaming;
+//                       region cbuf[kSharedKeys + warp*R, ...) with plain stores -- no lock, no atomics.  When
+//                       a private region runs low (rare; k ~ 1000 or adversarial order) the warp raises the
+//                       CTA's "join" epoch; every warp polls that word once per group of windows (it shares a
+//                       64-bit load with the float threshold) and joins ONE CTA-wide re-selection that folds all
+//                       private regions into the shared top-k set cbuf[0, k) and raises tau;
 //   end of pass         CTA-wide radix select over the shared set + all private regions -> k keys to HBM.
 #pragma once
 #include "common.cuh"
@@ -29,16 +31,32 @@ struct TopkGeom {
 struct CtaState {
     uint64_t mbar;
     uint64_t tau;       // current threshold key (0 = accept everything)
-    float tau_score;    // score part of tau (-inf while tau == 0): cheap pre-filter
+    // "gate": ONE 64-bit word polled by the streaming warps.  lo = float bits of tau's score (-inf while tau == 0,
+    // the cheap pre-filter), hi = join epoch requested.  The halves are written with separate 32-bit stores.
+    uint32_t gate_tau_score;
+    uint32_t gate_epoch;
     uint32_t cnt;       // keys in the shared set cbuf[0, cnt)
-    uint32_t lock;
-    uint32_t scratch;   // CTA-wide counters of the select routines
+    uint32_t scratch;   // CTA-wide counter of the select routines
+    uint32_t done;      // warps that finished streaming this pass
+    uint32_t pad_;
 };
+static_assert(offsetof(CtaState, gate_tau_score) % 8 == 0, "gate must be 8-byte aligned");
 
 __device__ __forceinline__ void cta_state_reset(CtaState *st) {
     st->cnt = 0;
     st->tau = 0;
-    st->tau_score = -INFINITY;
+    st->gate_tau_score = __float_as_uint(-INFINITY);
+    st->gate_epoch = 0;
+    st->done = 0;
+}
+__device__ __forceinline__ uint64_t gate_load(const CtaState *st) {
+    return *reinterpret_cast<const volatile uint64_t *>(&st->gate_tau_score);
+}
+__device__ __forceinline__ float gate_tau_score(uint64_t gate) { return __uint_as_float((uint32_t)gate); }
+__device__ __forceinline__ uint32_t gate_epoch(uint64_t gate) { return (uint32_t)(gate >> 32); }
+__device__ __forceinline__ void publish_tau(CtaState *st, uint64_t kth) {
+    *(volatile uint32_t *)&st->gate_tau_score = __float_as_uint(kth ? key_score(kth) : -INFINITY);
+    *(volatile uint64_t *)&st->tau = kth;
 }
 
 // k-th largest over two shared-memory segments (unique keys; zeros allowed as "absent", they rank last).
@@ -111,68 +129,88 @@ __device__ __forceinline__ void cta_sample_select(uint64_t *cbuf, int n, int k, 
 #pragma unroll
     for (int j = 0; j < PER; ++j)
         if (mine[j] != 0ull && mine[j] >= kth) cbuf[atomicAdd(&st->cnt, 1u)] = mine[j];
-    if (tid == 0) {
-        st->tau = kth;  // 0 when the sample held fewer than k real keys: keep accepting everything
-        st->tau_score = kth ? key_score(kth) : -INFINITY;
-    }
+    if (tid == 0) publish_tau(st, kth);  // 0 when the sample held fewer than k real keys: keep accepting everything
     __syncthreads();
 }
 
-// ---- phase B slow path: this warp's private region is full.  Under the lock, fold it into the shared set.
+// ---- phase B: append this window's qualifying keys (`ins` lanes) to the warp's private region (room is
+// guaranteed by the caller's join protocol).
 template <int NW>
-__device__ __forceinline__ void warp_merge_private(uint64_t *cbuf, int n_priv, int k, uint32_t *hist, CtaState *st) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t *priv = cbuf + kSharedKeys + warp * TopkGeom<NW>::kPrivate;
-    __syncwarp();
-    if (lane == 0) {
-        while (atomicCAS(&st->lock, 0u, 1u) != 0u) __nanosleep(64);
-    }
-    __syncwarp();
-    __threadfence_block();
-    const int n_sh = (int)*(volatile uint32_t *)&st->cnt;
-    int kept;
-    if (n_sh + n_priv <= k) {  // the shared set is not full yet: append
-        for (int i = lane; i < n_priv; i += 32) cbuf[n_sh + i] = priv[i];
-        kept = n_sh + n_priv;
-    } else {
-        const uint64_t kth = radix_kth_largest2<false>(cbuf, n_sh, lane, 32, priv, n_priv, lane, 32, k, hist, lane, 32);
-        kept = warp_compact_ge(cbuf, n_sh, kth);
-        for (int base = 0; base < n_priv; base += 32) {
-            const int i = base + lane;
-            const uint64_t x = (i < n_priv) ? priv[i] : 0ull;
-            const bool keep = (i < n_priv) && (x >= kth);
-            const uint32_t m = __ballot_sync(0xffffffffu, keep);
-            if (keep) cbuf[kept + __popc(m & lanemask_lt())] = x;
-            kept += __popc(m);
-        }
-        if (lane == 0) {
-            *(volatile float *)&st->tau_score = key_score(kth);
-            *(volatile uint64_t *)&st->tau = kth;
-        }
-    }
-    __syncwarp();
-    __threadfence_block();
-    if (lane == 0) {
-        *(volatile uint32_t *)&st->cnt = (uint32_t)kept;
-        __threadfence_block();
-        atomicExch(&st->lock, 0u);
-    }
-    __syncwarp();
-}
-
-// phase B fast path: append this window's qualifying keys (`ins` lanes) to the warp's private region.
-template <int NW>
-__device__ __forceinline__ void private_insert(bool ins, uint64_t key, uint64_t *cbuf, int &n_priv, int k,
-                                               uint32_t *hist, CtaState *st, uint32_t lt) {
+__device__ __forceinline__ void private_insert(bool ins, uint64_t key, uint64_t *cbuf, int &n_priv, uint32_t lt) {
     const uint32_t m = __ballot_sync(0xffffffffu, ins);
     if (m) {
         uint64_t *priv = cbuf + kSharedKeys + (threadIdx.x >> 5) * TopkGeom<NW>::kPrivate;
         if (ins) priv[n_priv + __popc(m & lt)] = key;
         n_priv += __popc(m);
-        if (n_priv + 32 > TopkGeom<NW>::kPrivate) {
-            warp_merge_private<NW>(cbuf, n_priv, k, hist, st);
+    }
+}
+
+// ---- phase B slow path: CTA-wide re-selection, executed by ALL warps of the CTA (each one gets here through
+// the epoch poll).  Folds every private region into the shared set, keeps the k best, raises tau, empties the
+// private regions.  No lock: the barrier is the synchronisation.
+template <int NT, int NW>
+__device__ __noinline__ void cta_join(uint64_t *cbuf, const int n_priv, int k, uint32_t *hist, CtaState *st) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t *priv = cbuf + kSharedKeys + warp * TopkGeom<NW>::kPrivate;
+    if (tid == 0) st->scratch = 0;
+    __syncthreads();
+    const int n_sh = (int)st->cnt;
+    if (lane == 0) atomicAdd(&st->scratch, (uint32_t)n_priv);
+    __syncthreads();
+    const int n_total = n_sh + (int)st->scratch;
+    uint64_t kth = 0;
+    if (n_total > k) kth = radix_kth_largest2<true>(cbuf, n_sh, tid, NT, priv, n_priv, lane, 32, k, hist, tid, NT);
+    // survivors -> registers, then rewrite the shared set
+    constexpr int SH_PER = (kSharedKeys + NT - 1) / NT;
+    constexpr int PR_PER = (TopkGeom<NW>::kPrivate + 31) / 32;
+    uint64_t keep_sh[SH_PER], keep_pr[PR_PER];
+#pragma unroll
+    for (int j = 0; j < SH_PER; ++j) { const int i = tid + j * NT; keep_sh[j] = (i < n_sh) ? cbuf[i] : 0ull; }
+#pragma unroll
+    for (int j = 0; j < PR_PER; ++j) { const int i = lane + j * 32; keep_pr[j] = (i < n_priv) ? priv[i] : 0ull; }
+    __syncthreads();
+    if (tid == 0) st->cnt = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SH_PER; ++j)
+        if (keep_sh[j] != 0ull && keep_sh[j] >= kth) cbuf[atomicAdd(&st->cnt, 1u)] = keep_sh[j];
+#pragma unroll
+    for (int j = 0; j < PR_PER; ++j)
+        if (keep_pr[j] != 0ull && keep_pr[j] >= kth) cbuf[atomicAdd(&st->cnt, 1u)] = keep_pr[j];
+    if (tid == 0 && kth) publish_tau(st, kth);
+    __syncthreads();
+}
+
+// Poll + join protocol of a streaming warp.  `gate` was loaded at the start of the current group of windows; the warp
+// joins when someone asked for a re-selection it has not served yet, or asks itself when its region cannot take
+// `need` more keys.
+template <int NT, int NW>
+__device__ __forceinline__ void join_if_needed(uint64_t gate, uint32_t &epoch, int need, uint64_t *cbuf, int &n_priv,
+                                               int k, uint32_t *hist, CtaState *st) {
+    const bool full = n_priv + need > TopkGeom<NW>::kPrivate;
+    if (gate_epoch(gate) != epoch || gate_epoch(gate_load(st)) != epoch || full) {
+        if (full && (threadIdx.x & 31) == 0) *(volatile uint32_t *)&st->gate_epoch = epoch + 1;
+        cta_join<NT, NW>(cbuf, n_priv, k, hist, st);
+        n_priv = 0;
+        ++epoch;
+    }
+}
+
+// A warp that has finished streaming must keep serving join requests until every warp of the CTA is done.
+template <int NT, int NW>
+__device__ __forceinline__ void finish_streaming(uint32_t &epoch, uint64_t *cbuf, int &n_priv, int k, uint32_t *hist,
+                                                 CtaState *st) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) atomicAdd(&st->done, 1u);
+    for (;;) {
+        if (gate_epoch(gate_load(st)) != epoch) {
+            cta_join<NT, NW>(cbuf, n_priv, k, hist, st);
             n_priv = 0;
+            ++epoch;
+            continue;
         }
+        if (*(volatile uint32_t *)&st->done >= (uint32_t)NW) break;
+        __nanosleep(200);
     }
 }
 
