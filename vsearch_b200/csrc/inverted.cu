@@ -10,6 +10,8 @@
 // Algorithmic bytes per query: sum_t len(post_t) * (4 + b_val) + 2 * N * 4.
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
+
 #include <vector>
 
 #include "index.cuh"
@@ -257,6 +259,7 @@ struct SelectParams {
     int64_t n_rows, n_pad;
     int b0, k, cap, score_round;
     int rows_per_cta;    // multiple of 4
+    int zero_behind;     // 1 (always, except timing experiments): clear the accumulator row behind the read
 };
 
 __global__ void __launch_bounds__(kInvThreads, 1) inv_select_kernel(const SelectParams p) {
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_select_kernel(const Select
 #pragma unroll
         for (int u = 0; u < kSelU; ++u) {
             const int64_t ru = r + (int64_t)u * kInvThreads * 4;
-            if (in[u]) acc4[ru >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in[u] && p.zero_behind) acc4[ru >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < kSelU; ++u) {
@@ -416,6 +419,7 @@ int launch_inverted(vs_index *idx, int64_t Bc, int k, int score_round, int group
         SelectParams sp;
         sp.acc = acc; sp.cand = d_cand; sp.n_rows = idx->n_rows; sp.n_pad = n_pad; sp.b0 = (int)b0; sp.k = k;
         sp.cap = cap; sp.score_round = score_round; sp.rows_per_cta = rows_per_cta;
+        sp.zero_behind = getenv("VSEARCH_B200_DEBUG_NOZERO") ? 0 : 1;
         inv_select_kernel<<<dim3(idx->n_ctas, G), kInvThreads, sel_smem, st>>>(sp);
     }
     if (ev1) VS_CUDA(cudaEventRecord(ev1, st));

@@ -118,7 +118,7 @@ class _Engine:
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
-        if h:
+        if h and nat is not None and getattr(nat, "LIB", None) is not None:  # module may be gone at interpreter exit
             nat.LIB.vs_index_destroy(h)
 
     def workspace(self, B: int, k: int) -> torch.Tensor:
