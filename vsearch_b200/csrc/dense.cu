@@ -14,8 +14,8 @@
 //               mode 0 (sample)    emit every score of the tile as a rank key (small sample prefix of the index)
 //               mode 1 (filter)    compare against the per-query threshold; survivors are appended to the
 //                                  query's candidate list with one global atomic
-// Each CTA owns passage tiles nt = blockIdx.x, +gridDim.x, ... and sweeps all query tiles for a passage tile, so X
-// is read from HBM once and re-read from L2.
+// Work items (passage tile, query tile) are dealt round-robin with the query tile fastest, so the CTAs that run
+// concurrently share a handful of passage tiles: X is read from HBM once and re-read from L2.
 //
 // Host side (search_dense): threshold from an exact top-k of a sample prefix -> one filtered sweep over the whole
 // index -> exact top-k of the survivors with the K6 merge kernel.  If a candidate list overflows (adversarial
@@ -125,13 +125,16 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // work item = (passage tile, query tile), query tile fastest, dealt round-robin over the CTAs: at any moment the
+    // grid works on ~#CTAs / n_tiles_m consecutive passage tiles, so X is fetched from HBM once and shared through L2
+    const int64_t n_work = (int64_t)a.n_tiles_n * a.n_tiles_m;
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int nt = blockIdx.x; nt < a.n_tiles_n; nt += gridDim.x)
-                for (int mt = 0; mt < a.n_tiles_m; ++mt)
+            for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+                const int nt = (int)(wk / a.n_tiles_m), mt = (int)(wk % a.n_tiles_m);
                     for (int kb = 0; kb < a.k_blocks; ++kb) {
                         mbar_wait_u32(bar_empty + stage * 8, phase ^ 1u);
                         mbar_expect_tx(bar_full + stage * 8, kStageBytes);
@@ -140,14 +143,15 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                         tma_load_2d(sa + kStageBytesA, &tmap_x, kb * kBK, (int)(a.row_offset) + nt * kBN, bar_full + stage * 8);
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
+            }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int nt = blockIdx.x; nt < a.n_tiles_n; nt += gridDim.x)
-                for (int mt = 0; mt < a.n_tiles_m; ++mt) {
+            for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+                {
                     mbar_wait_u32(bar_tempty + acc * 8, acc_phase ^ 1u);  // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)acc * kBN;
@@ -165,13 +169,15 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     tc_commit(bar_tfull + acc * 8);            // accumulator complete
                     acc ^= 1; if (acc == 0) acc_phase ^= 1u;
                 }
+            }
         }
     } else {
         // ================= epilogue (warps 2..5 <-> TMEM lane quarters 2,3,0,1) =================
         const int quarter = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int nt = blockIdx.x; nt < a.n_tiles_n; nt += gridDim.x)
-            for (int mt = 0; mt < a.n_tiles_m; ++mt) {
+        for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+            const int nt = (int)(wk / a.n_tiles_m), mt = (int)(wk % a.n_tiles_m);
+            {
                 mbar_wait_u32(bar_tfull + acc * 8, acc_phase);
                 tc_fence_after();
                 const int64_t q = (int64_t)mt * kBM + quarter * 32 + lane;   // this thread's query row
@@ -221,6 +227,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
                 acc ^= 1; if (acc == 0) acc_phase ^= 1u;
             }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -348,7 +355,8 @@ size_t dense_workspace_bytes(const vs_index *idx, int64_t B, int k) {
 static int launch_dense(const vs_index *idx, const CUtensorMap &tq, const CUtensorMap &tx, DenseArgs a, cudaStream_t st) {
     const size_t smem = (size_t)kStages * kStageBytes + 256 + 1024;
     VS_CUDA(cudaFuncSetAttribute(dense_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = idx->n_ctas < a.n_tiles_n ? idx->n_ctas : a.n_tiles_n;
+    const int64_t n_work = (int64_t)a.n_tiles_n * a.n_tiles_m;
+    int grid = (int64_t)idx->n_ctas < n_work ? idx->n_ctas : (int)n_work;
     dense_topk_kernel<<<grid, kDenseThreads, smem, st>>>(tq, tx, a);
     VS_CUDA(cudaGetLastError());
     return VS_OK;
