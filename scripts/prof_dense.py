@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vsearch_b200.index import _Engine
 from vsearch_b200 import _native as nat
 dev = torch.device("cuda:0")
-n, d, B, k = 1_000_000, 768, 2048, 100
+n, d, B, k = 6_000_000, 768, 2048, 100
 g = torch.Generator(device=dev).manual_seed(7)
 x = torch.randn((n, d), generator=g, device=dev).to(torch.bfloat16)
 q = torch.randn((B, d), generator=g, device=dev).to(torch.bfloat16)

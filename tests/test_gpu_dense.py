@@ -46,6 +46,7 @@ def test_golden_dense(name, cuda_device):
     (70_000, 768, 130, 100, torch.bfloat16),  # sample + filtered sweep, 2 query tiles, ragged N
     (40_000, 128, 33, 1000, torch.float16),   # k = 1000, fp16 storage, D = 128
     (300, 96, 3, 300, torch.bfloat16),        # k == N, D not a multiple of 64
+    (1_200_000, 64, 5, 100, torch.bfloat16),  # all three sweeps: sample, 64x sample with tau1, the rest with tau2
 ])
 def test_dense_grid_exact(n, d, B, k, dtype, cuda_device):
     x, q = _grid((n, d), 1), _grid((B, d), 2)

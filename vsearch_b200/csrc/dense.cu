@@ -108,6 +108,12 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + kStages * 8;
     const uint32_t bar_tfull = bar_empty + kStages * 8, bar_tempty = bar_tfull + 2 * 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+    float *s_tau = reinterpret_cast<float *>(bars + 2 * kStages + 6);   // [n_queries <= 4096] threshold scores (mode 1)
+    if (a.mode == 1)
+        for (int64_t i = threadIdx.x; i < a.n_queries; i += kDenseThreads) {
+            const uint64_t t = a.tau[i];
+            s_tau[i] = t ? key_score(t) : -INFINITY;
+        }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -183,39 +189,66 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 const int64_t q = (int64_t)mt * kBM + quarter * 32 + lane;   // this thread's query row
                 const bool q_ok = q < a.n_queries;
                 const int64_t n0 = a.row_offset + (int64_t)nt * kBN;         // first passage of the tile
-                uint64_t tau = 0; float tau_s = -INFINITY;
-                if (a.mode == 1 && q_ok) { tau = a.tau[q]; tau_s = tau ? key_score(tau) : -INFINITY; }
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kBN;
+                if (a.mode == 0) {
+                    // ---- sample sweep: every score of the tile becomes a rank key
 #pragma unroll 1
-                for (int c = 0; c < kBN / 32; ++c) {
-                    uint32_t r[32];
-                    tc_ld32(taddr + c * 32, r);
-                    const int64_t nb = n0 + c * 32;
-                    if (!q_ok) {
-                        // padded query row: nothing to emit
-                    } else if (a.mode == 0) {
-                        uint64_t *dst = a.sample_keys + q * a.sample_ld + (nb - a.row_offset);
+                    for (int c = 0; c < kBN / 32; ++c) {
+                        uint32_t r[32];
+                        tc_ld32(taddr + c * 32, r);
+                        const int64_t nb = n0 + c * 32;
+                        if (q_ok) {
+                            uint64_t *dst = a.sample_keys + q * a.sample_ld + (nb - a.row_offset);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int64_t n = nb + j;
-                            const float s = round_score(__uint_as_float(r[j]), a.score_round);
-                            dst[j] = (n < a.n_rows) ? make_key(s, (uint32_t)n) : 0ull;
+                            for (int j = 0; j < 32; ++j) {
+                                const int64_t n = nb + j;
+                                const float s = round_score(__uint_as_float(r[j]), a.score_round);
+                                dst[j] = (n < a.n_rows) ? make_key(s, (uint32_t)n) : 0ull;
+                            }
                         }
-                    } else {
+                    }
+                } else {
+                    // ---- filtered sweep.  Pass 1 over the accumulator counts this query's survivors (float
+                    // pre-filter against the threshold score staged in shared memory, exact key test for the few that
+                    // pass); ONE global atomic reserves their slots; pass 2 (only for warps that have any) re-reads
+                    // the accumulator from TMEM and writes the keys.
+                    const float tau_s = q_ok ? s_tau[q] : INFINITY;
+                    uint64_t tau = 0;
+                    uint32_t n_surv = 0;
+#pragma unroll 1
+                    for (int c = 0; c < kBN / 32; ++c) {
+                        uint32_t r[32];
+                        tc_ld32(taddr + c * 32, r);
                         float mx = -INFINITY;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
                         if (a.score_round != VS_F32) mx = round_score(mx, a.score_round);
                         if (mx >= tau_s) {
+                            if (tau == 0) tau = a.tau[q];
+                            const int64_t nb = n0 + c * 32;
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
-                                const int64_t n = nb + j;
                                 const float s = round_score(__uint_as_float(r[j]), a.score_round);
-                                if (s >= tau_s && n < a.n_rows) {
-                                    const uint64_t key = make_key(s, (uint32_t)n);
-                                    if (key >= tau) {
-                                        const uint32_t pos = atomicAdd(a.cand_cnt + q, 1u);
-                                        if (pos < (uint32_t)a.cand_cap) a.cand[q * a.cand_cap + pos] = key;
+                                n_surv += (s >= tau_s && nb + j < a.n_rows && make_key(s, (uint32_t)(nb + j)) >= tau) ? 1u : 0u;
+                            }
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, n_surv != 0)) {
+                        uint32_t pos = 0;
+                        if (n_surv) pos = atomicAdd(a.cand_cnt + q, n_surv);
+                        uint64_t *dst = a.cand + q * a.cand_cap;
+#pragma unroll 1
+                        for (int c = 0; c < kBN / 32; ++c) {
+                            uint32_t r[32];
+                            tc_ld32(taddr + c * 32, r);
+                            if (n_surv) {
+                                const int64_t nb = n0 + c * 32;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const float s = round_score(__uint_as_float(r[j]), a.score_round);
+                                    if (s >= tau_s && nb + j < a.n_rows) {
+                                        const uint64_t key = make_key(s, (uint32_t)(nb + j));
+                                        if (key >= tau) { if (pos < (uint32_t)a.cand_cap) dst[pos] = key; ++pos; }
                                     }
                                 }
                             }
@@ -254,10 +287,13 @@ __global__ void dense_convert_kernel(const void *in, int in_dtype, int64_t rows,
     }
 }
 
-// tau[q] = keys[q * ld + k - 1] (k-th best of the sample), or 0 when the sample has fewer than k rows
-__global__ void dense_tau_kernel(const uint64_t *sorted_keys, int64_t ld, int k, int64_t n_queries, uint64_t *tau) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < n_queries) tau[q] = sorted_keys[q * ld + (k - 1)];
+// Start of a filtered sweep: every query's candidate list is seeded with its current top-k (sorted keys, one block
+// per query), the threshold is the k-th of them.
+__global__ void dense_seed_lists_kernel(const uint64_t *sorted_keys, int k, uint64_t *cand, int64_t cap, uint32_t *cnt,
+                                        uint64_t *tau) {
+    const int64_t q = blockIdx.x;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) cand[q * cap + i] = sorted_keys[q * k + i];
+    if (threadIdx.x == 0) { cnt[q] = (uint32_t)k; tau[q] = sorted_keys[q * k + (k - 1)]; }
 }
 
 static PFN_cuTensorMapEncodeTiled get_encode_fn() {
@@ -324,8 +360,8 @@ constexpr int64_t kDenseQueryChunk = 4096;
 constexpr int64_t kDenseCandCap = 1 << 16;   // per-query survivor list (keys)
 
 static int64_t dense_sample_rows(const vs_index *idx, int k) {
-    // sample prefix: ~256*k rows (>= 16 K), a whole number of tiles, at most the index
-    int64_t s = (int64_t)k * 256;
+    // sample prefix: ~64*k rows (>= 16 K), a whole number of tiles, at most the index
+    int64_t s = (int64_t)k * 64;
     if (s < 16384) s = 16384;
     s = (s + kBN - 1) / kBN * kBN;
     return s < idx->n_pad ? s : idx->n_pad;
@@ -353,7 +389,7 @@ size_t dense_workspace_bytes(const vs_index *idx, int64_t B, int k) {
 }
 
 static int launch_dense(const vs_index *idx, const CUtensorMap &tq, const CUtensorMap &tx, DenseArgs a, cudaStream_t st) {
-    const size_t smem = (size_t)kStages * kStageBytes + 256 + 1024;
+    const size_t smem = (size_t)kStages * kStageBytes + 256 + (size_t)kDenseQueryChunk * 4 + 1024;
     VS_CUDA(cudaFuncSetAttribute(dense_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_work = (int64_t)a.n_tiles_n * a.n_tiles_m;
     int grid = (int64_t)idx->n_ctas < n_work ? idx->n_ctas : (int)n_work;
@@ -388,45 +424,57 @@ int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t
         a.score_round = score_round; a.idesc = idesc;
         a.sample_keys = w.sample; a.tau = w.tau; a.cand = w.cand; a.cand_cnt = w.cnt; a.cand_cap = kDenseCandCap;
 
-        // ---- phase 1: exact top-k of a sample prefix -> per-query threshold
-        const int64_t srows = dense_sample_rows(idx, k);
-        a.mode = 0; a.n_tiles_n = (int)(srows / kBN); a.sample_ld = srows;
+        // ---- pass 1 (sample sweep): exact top-k of the first S1 rows -> threshold tau1
+        const int64_t s1 = dense_sample_rows(idx, k);
+        a.mode = 0; a.n_tiles_n = (int)(s1 / kBN); a.sample_ld = s1; a.row_offset = 0;
         const int slot = idx->timer_n < VS_TIMER_SLOTS ? idx->timer_n : -1;
         if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev0[slot], st));
         rc = launch_dense(idx, tq, tx, a, st);
         if (rc) return rc;
-        const int64_t s_real = srows < idx->n_rows ? srows : idx->n_rows;
-        if (s_real >= idx->n_rows) {
+        if (s1 >= idx->n_rows) {
             // the sample IS the index (small index): its top-k is the answer
             if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
             idx->timer_n += 1;
-            rc = launch_merge(w.sample, 1, 0, srows, Bc, (int)srows, k, id_offset, d_ids ? d_ids + b0 * k : nullptr,
+            rc = launch_merge(w.sample, 1, 0, s1, Bc, (int)s1, k, id_offset, d_ids ? d_ids + b0 * k : nullptr,
                               d_scores ? d_scores + b0 * k : nullptr, d_keys ? d_keys + b0 * k : nullptr, st);
             if (rc) return rc;
             continue;
         }
-        rc = launch_merge(w.sample, 1, 0, srows, Bc, (int)srows, k, 0, nullptr, nullptr, w.tau_sorted, st);
+        rc = launch_merge(w.sample, 1, 0, s1, Bc, (int)s1, k, 0, nullptr, nullptr, w.tau_sorted, st);
         if (rc) return rc;
-        dense_tau_kernel<<<(unsigned)((Bc + 255) / 256), 256, 0, st>>>(w.tau_sorted, k, k, Bc, w.tau);
 
-        // ---- phase 2: filtered sweep over the whole index; repeat with a tighter threshold on overflow
-        for (int attempt = 0;; ++attempt) {
-            VS_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)Bc * 4, st));
-            a.mode = 1; a.n_tiles_n = (int)(idx->n_pad / kBN);
-            rc = launch_dense(idx, tq, tx, a, st);
-            if (rc) return rc;
-            std::vector<uint32_t> h_cnt((size_t)Bc);
-            VS_CUDA(cudaMemcpyAsync(h_cnt.data(), w.cnt, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
-            VS_CUDA(cudaStreamSynchronize(st));
-            uint32_t mx = 0;
-            for (int64_t i = 0; i < Bc; ++i) mx = h_cnt[i] > mx ? h_cnt[i] : mx;
-            if (mx <= (uint32_t)kDenseCandCap) break;
-            VS_REQUIRE(attempt < 8, VS_ERR_UNSUPPORTED, "dense candidate lists keep overflowing");
-            // tighten: new tau = k-th best of the kDenseCandCap stored candidates (a valid lower bound)
-            rc = launch_merge_counted(w.cand, w.cnt, 1, 0, kDenseCandCap, Bc, (int)kDenseCandCap, k, 0, nullptr, nullptr,
-                                      w.tau_sorted, st);
-            if (rc) return rc;
-            dense_tau_kernel<<<(unsigned)((Bc + 255) / 256), 256, 0, st>>>(w.tau_sorted, k, k, Bc, w.tau);
+        // ---- passes 2 and 3 (filtered sweeps).  Pass 2 covers the next ~64 x S1 rows with tau1 and tightens the
+        // threshold to the k-th best of everything seen so far; pass 3 covers the rest of the index with that
+        // threshold, so only ~k * N / (65 * S1) rows per query survive it.  Every list starts with the current top-k.
+        int64_t row = s1;
+        for (int pass = 2; row < idx->n_pad; ++pass) {
+            int64_t rows = (pass == 2) ? 64 * s1 : idx->n_pad - row;
+            if (rows > idx->n_pad - row) rows = idx->n_pad - row;
+            for (int attempt = 0;; ++attempt) {
+                dense_seed_lists_kernel<<<(unsigned)Bc, 128, 0, st>>>(w.tau_sorted, k, w.cand, kDenseCandCap, w.cnt, w.tau);
+                a.mode = 1; a.row_offset = row; a.n_tiles_n = (int)(rows / kBN);
+                rc = launch_dense(idx, tq, tx, a, st);
+                if (rc) return rc;
+                std::vector<uint32_t> h_cnt((size_t)Bc);
+                VS_CUDA(cudaMemcpyAsync(h_cnt.data(), w.cnt, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
+                VS_CUDA(cudaStreamSynchronize(st));
+                uint32_t mx = 0;
+                for (int64_t i = 0; i < Bc; ++i) mx = h_cnt[i] > mx ? h_cnt[i] : mx;
+                if (mx <= (uint32_t)kDenseCandCap) break;
+                VS_REQUIRE(attempt < 8, VS_ERR_UNSUPPORTED, "dense candidate lists keep overflowing");
+                // overflow (adversarial row order): the k-th best of the kDenseCandCap stored candidates is a valid,
+                // strictly tighter threshold; redo this sweep with it
+                // (lists that did not overflow keep their own count: only their first cnt[q] entries are valid)
+                rc = launch_merge_counted(w.cand, w.cnt, 1, 0, kDenseCandCap, Bc, (int)kDenseCandCap, k, 0, nullptr, nullptr,
+                                          w.tau_sorted, st);
+                if (rc) return rc;
+            }
+            row += rows;
+            if (row < idx->n_pad) {  // tighten for the next sweep: top-k of everything seen so far
+                rc = launch_merge_counted(w.cand, w.cnt, 1, 0, kDenseCandCap, Bc, (int)kDenseCandCap, k, 0, nullptr, nullptr,
+                                          w.tau_sorted, st);
+                if (rc) return rc;
+            }
         }
         if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
         idx->timer_n += 1;
