@@ -46,6 +46,7 @@ struct DenseArgs {
     uint64_t *sample_keys; int64_t sample_ld;
     const uint64_t *tau;   // [n_queries] threshold keys (mode 1)
     uint64_t *cand; uint32_t *cand_cnt; int64_t cand_cap;  // [n_queries, cand_cap], [n_queries]
+    unsigned long long *work_counter;   // dynamic tile scheduler (zeroed before every launch)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -107,8 +108,10 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + kStages * kStageBytes);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + kStages * 8;
     const uint32_t bar_tfull = bar_empty + kStages * 8, bar_tempty = bar_tfull + 2 * 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
-    float *s_tau = reinterpret_cast<float *>(bars + 2 * kStages + 6);   // [n_queries <= 4096] threshold scores (mode 1)
+    const uint32_t bar_sfull = bar_tempty + 2 * 8, bar_sempty = bar_sfull + 2 * 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 8);
+    volatile long long *sched_slot = reinterpret_cast<volatile long long *>(bars + 2 * kStages + 10);   // [2] work items
+    float *s_tau = reinterpret_cast<float *>(bars + 2 * kStages + 12);   // [n_queries <= 4096] threshold scores (mode 1)
     if (a.mode == 1)
         for (int64_t i = threadIdx.x; i < a.n_queries; i += kDenseThreads) {
             const uint64_t t = a.tau[i];
@@ -120,7 +123,12 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_x) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(bars + s, 1); mbar_init(bars + kStages + s, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bars + 2 * kStages + i, 1); mbar_init(bars + 2 * kStages + 2 + i, 4); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bars + 2 * kStages + i, 1);          // tfull: one tcgen05.commit
+            mbar_init(bars + 2 * kStages + 2 + i, 4);      // tempty: the four epilogue warps
+            mbar_init(bars + 2 * kStages + 4 + i, 1);      // sfull: the scheduler (producer thread)
+            mbar_init(bars + 2 * kStages + 6 + i, 5);      // sempty: MMA thread + four epilogue warps
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -131,24 +139,38 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // work item = (passage tile, query tile), query tile fastest, dealt round-robin over the CTAs: at any moment the
-    // grid works on ~#CTAs / n_tiles_m consecutive passage tiles, so X is fetched from HBM once and shared through L2
-    const int64_t n_work = (int64_t)a.n_tiles_n * a.n_tiles_m;
+    // work item = (passage tile, query tile), query tile fastest
+    const long long n_work = (int64_t)a.n_tiles_n * a.n_tiles_m;
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer + tile scheduler =================
+        // Work items (passage tile, query tile; query tile fastest) are handed out by a global atomic counter, so
+        // the CTAs that run concurrently always work on neighbouring items: the X tile a CTA needs is being read
+        // by its neighbours right now and comes from L2 (a static round-robin drifts apart and re-reads X from HBM
+        // ~9x: measured, profiles/README.md).  The item is published to the MMA / epilogue warps through a 2-slot ring.
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+            int ss = 0; uint32_t sphase = 0;
+            long long wk = (long long)atomicAdd(a.work_counter, 1ull);
+            for (;;) {
+                const bool live = wk < n_work;
+                long long wk_next = 0;
+                if (live) wk_next = (long long)atomicAdd(a.work_counter, 1ull);  // latency hidden behind this tile's loads
+                mbar_wait_u32(bar_sempty + ss * 8, sphase ^ 1u);
+                sched_slot[ss] = live ? wk : -1ll;
+                mbar_arrive(bar_sfull + ss * 8);
+                if (++ss == 2) { ss = 0; sphase ^= 1u; }
+                if (!live) break;
                 const int nt = (int)(wk / a.n_tiles_m), mt = (int)(wk % a.n_tiles_m);
-                    for (int kb = 0; kb < a.k_blocks; ++kb) {
-                        mbar_wait_u32(bar_empty + stage * 8, phase ^ 1u);
-                        mbar_expect_tx(bar_full + stage * 8, kStageBytes);
-                        const uint32_t sa = smem_base + stage * kStageBytes;
-                        tma_load_2d(sa, &tmap_q, kb * kBK, mt * kBM, bar_full + stage * 8);
-                        tma_load_2d(sa + kStageBytesA, &tmap_x, kb * kBK, (int)(a.row_offset) + nt * kBN, bar_full + stage * 8);
-                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                    }
+                for (int kb = 0; kb < a.k_blocks; ++kb) {
+                    mbar_wait_u32(bar_empty + stage * 8, phase ^ 1u);
+                    mbar_expect_tx(bar_full + stage * 8, kStageBytes);
+                    const uint32_t sa = smem_base + stage * kStageBytes;
+                    tma_load_2d(sa, &tmap_q, kb * kBK, mt * kBM, bar_full + stage * 8);
+                    tma_load_2d(sa + kStageBytesA, &tmap_x, kb * kBK, (int)(a.row_offset) + nt * kBN, bar_full + stage * 8);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                wk = wk_next;
             }
         }
     } else if (warp == 1) {
@@ -156,7 +178,13 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+            int ss = 0; uint32_t sphase = 0;
+            for (;;) {
+                mbar_wait_u32(bar_sfull + ss * 8, sphase);
+                const long long wk = sched_slot[ss];
+                mbar_arrive(bar_sempty + ss * 8);
+                if (++ss == 2) { ss = 0; sphase ^= 1u; }
+                if (wk < 0) break;
                 {
                     mbar_wait_u32(bar_tempty + acc * 8, acc_phase ^ 1u);  // epilogue has drained this accumulator
                     tc_fence_after();
@@ -181,7 +209,14 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // ================= epilogue (warps 2..5 <-> TMEM lane quarters 2,3,0,1) =================
         const int quarter = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+        int ss = 0; uint32_t sphase = 0;
+        for (;;) {
+            mbar_wait_u32(bar_sfull + ss * 8, sphase);
+            const long long wk = sched_slot[ss];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sempty + ss * 8);
+            if (++ss == 2) { ss = 0; sphase ^= 1u; }
+            if (wk < 0) break;
             const int nt = (int)(wk / a.n_tiles_m), mt = (int)(wk % a.n_tiles_m);
             {
                 mbar_wait_u32(bar_tfull + acc * 8, acc_phase);
@@ -353,6 +388,7 @@ struct DenseWs {
     uint64_t *tau;        // [Bc]
     uint64_t *tau_sorted; // [Bc, k]
     uint32_t *cnt;        // [Bc]
+    unsigned long long *work_counter;
     uint64_t *cand;       // [Bc, cap]
     size_t bytes;
 };
@@ -378,6 +414,7 @@ static DenseWs carve_dense(const vs_index *idx, void *base, int64_t Bc, int k) {
     w.tau = (uint64_t *)(p + o); o += al((size_t)Bc * 8);
     w.tau_sorted = (uint64_t *)(p + o); o += al((size_t)Bc * k * 8);
     w.cnt = (uint32_t *)(p + o); o += al((size_t)Bc * 4);
+    w.work_counter = (unsigned long long *)(p + o); o += al(8);
     w.cand = (uint64_t *)(p + o); o += al((size_t)Bc * kDenseCandCap * 8);
     w.bytes = o;
     return w;
@@ -393,6 +430,7 @@ static int launch_dense(const vs_index *idx, const CUtensorMap &tq, const CUtens
     VS_CUDA(cudaFuncSetAttribute(dense_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_work = (int64_t)a.n_tiles_n * a.n_tiles_m;
     int grid = (int64_t)idx->n_ctas < n_work ? idx->n_ctas : (int)n_work;
+    VS_CUDA(cudaMemsetAsync(a.work_counter, 0, 8, st));
     dense_topk_kernel<<<grid, kDenseThreads, smem, st>>>(tq, tx, a);
     VS_CUDA(cudaGetLastError());
     return VS_OK;
@@ -423,6 +461,7 @@ int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t
         a.n_rows = idx->n_rows; a.n_queries = Bc; a.row_offset = 0;
         a.score_round = score_round; a.idesc = idesc;
         a.sample_keys = w.sample; a.tau = w.tau; a.cand = w.cand; a.cand_cnt = w.cnt; a.cand_cap = kDenseCandCap;
+        a.work_counter = w.work_counter;
 
         // ---- pass 1 (sample sweep): exact top-k of the first S1 rows -> threshold tau1
         const int64_t s1 = dense_sample_rows(idx, k);
