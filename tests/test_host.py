@@ -36,7 +36,7 @@ def test_abi_argument_validation_without_gpu():
     out = ctypes.c_void_p()
     rc = lib.vs_index_create_csr(0, 10, 70000, 0, None, _native.VS_I64, None, _native.VS_I64, None, _native.VS_NONE,
                                  _native.VS_NONE, None, ctypes.byref(out))
-    assert rc == _native.VS_ERR_UNSUPPORTED and "uint16" in _native.last_error()
+    assert rc == _native.VS_ERR_UNSUPPORTED and "uint16" in _native.last_error()  # V must be < 32768
     rc = lib.vs_index_create_csr(0, 10, 100, 0, None, _native.VS_F32, None, _native.VS_I64, None, _native.VS_NONE,
                                  _native.VS_NONE, None, ctypes.byref(out))
     assert rc == _native.VS_ERR_INVALID

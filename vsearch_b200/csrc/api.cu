@@ -107,7 +107,8 @@ int vs_index_create_csr(int device, int64_t n_rows, int64_t n_cols, int64_t nnz,
     VS_REQUIRE(out != nullptr, VS_ERR_INVALID, "out is NULL");
     *out = nullptr;
     VS_REQUIRE(n_rows >= 0 && n_cols >= 1 && nnz >= 0, VS_ERR_INVALID, "bad shape");
-    VS_REQUIRE(n_cols <= 65535, VS_ERR_UNSUPPORTED, "n_cols=%lld does not fit the uint16 column format", (long long)n_cols);
+    VS_REQUIRE(n_cols <= 32767, VS_ERR_UNSUPPORTED,
+               "n_cols=%lld does not fit the uint16 column format (15 bits + the row-end flag)", (long long)n_cols);
     VS_REQUIRE(n_rows < 0xffffffffll, VS_ERR_UNSUPPORTED, "n_rows must be < 2^32 - 1 per shard");
     VS_REQUIRE(crow_dtype == VS_I32 || crow_dtype == VS_I64, VS_ERR_INVALID, "crow dtype must be int32/int64");
     VS_REQUIRE(col_dtype == VS_I32 || col_dtype == VS_I64, VS_ERR_INVALID, "col dtype must be int32/int64");

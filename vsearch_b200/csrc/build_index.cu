@@ -52,7 +52,7 @@ __global__ void part_windows_kernel(const uint64_t *cptr, const uint32_t *part_r
     for (int p = 0; p < n_parts; ++p) {
         part_win_begin[p] = (uint32_t)w;
         uint64_t chunks = cptr[part_row_begin[p + 1]] - cptr[part_row_begin[p]];
-        w += (chunks + 31) / 32;
+        w += (chunks + 63) / 64 * 2;   // whole 64-chunk steps: the scan kernel takes two chunks per lane per step
     }
     part_win_begin[n_parts] = (uint32_t)w;
     *n_windows_out = w;
@@ -106,8 +106,9 @@ __global__ void fill_rows_kernel(const void *crow, int crow_dtype, const void *c
 }
 
 // ---- bank-aware entry placement ---------------------------------------------------------------------------
-// The scan kernel's gather #j of a window reads slot j of all 32 chunks at once; the shared-memory cost of that
-// instruction is the largest number of lanes hitting one bank (bank = column mod 32).  A dot product does not
+// A scan step covers 64 chunks, lane l holding chunks 2l and 2l+1: gather #j of the even (odd) chunks reads slot j of
+// the 32 even (odd) chunks of the step at once; the shared-memory cost of that instruction is the largest number of
+// lanes hitting one bank (bank = column mod 32).  A dot product does not
 // care about the order of a row's entries, so each row's entries are re-dealt over its (chunk, slot) positions:
 //   pass 1  slot by slot, take the row's most plentiful bank that this window has not used yet in that slot;
 //   pass 2  what is left must collide: put it in the latest free slot, on the bank with the fewest lanes there.
@@ -117,7 +118,8 @@ constexpr int kPlaceMaxRow = 512;   // longer rows keep their original order
 
 template <typename VT>
 __global__ void __launch_bounds__(32) place_entries_kernel(uint16_t *cols16, VT *vals, const uint32_t *tails,
-                                                           const uint32_t *part_win_begin, int n_parts, int n_cols) {
+                                                           const uint32_t *part_win_begin, int n_parts, int n_cols,
+                                                           int pair_mode) {
     const int part = blockIdx.x * blockDim.x + threadIdx.x;
     if (part >= n_parts) return;
     const uint64_t c_begin = (uint64_t)part_win_begin[part] * 32ull, c_end = (uint64_t)part_win_begin[part + 1] * 32ull;
@@ -126,10 +128,10 @@ __global__ void __launch_bounds__(32) place_entries_kernel(uint16_t *cols16, VT 
     uint16_t ecol[kPlaceMaxRow];
     uint16_t order[kPlaceMaxRow];    // entry indices grouped by bank
     VT eval[kPlaceMaxRow];
-    uint8_t mult[8][32];             // lanes per (slot, bank) in the current window
-    uint32_t used[8];
+    uint8_t mult2[2][8][32];         // lanes per (chunk parity, slot, bank) in the current 64-chunk step
+    uint32_t used2[2][8];
     uint16_t cnt[32], head[32];
-    for (int j = 0; j < 8; ++j) { used[j] = 0; for (int b = 0; b < 32; ++b) mult[j][b] = 0; }
+    for (int q = 0; q < 2; ++q) for (int j = 0; j < 8; ++j) { used2[q][j] = 0; for (int b = 0; b < 32; ++b) mult2[q][j][b] = 0; }
 
     uint64_t c = c_begin;
     while (c < c_end) {
@@ -164,8 +166,12 @@ __global__ void __launch_bounds__(32) place_entries_kernel(uint16_t *cols16, VT 
         int remaining = n;
         for (int ch = 0; ch < nch; ++ch) {
             const uint64_t cc = c + ch;
-            if ((cc & 31) == 0) { for (int j = 0; j < 8; ++j) { used[j] = 0; for (int b = 0; b < 32; ++b) mult[j][b] = 0; } }
+            // conflict set of a gather: the 32 even (odd) chunks of a 64-chunk step in pair mode, else 32 consecutive chunks
+            if ((cc & (pair_mode ? 63 : 31)) == 0)
+                for (int q = 0; q < 2; ++q) for (int j = 0; j < 8; ++j) { used2[q][j] = 0; for (int b = 0; b < 32; ++b) mult2[q][j][b] = 0; }
             if (!fits) continue;
+            uint32_t *used = used2[pair_mode ? (cc & 1) : 0];
+            uint8_t (*mult)[32] = mult2[pair_mode ? (cc & 1) : 0];
             int slot_entry[8];
             for (int j = 0; j < 8; ++j) slot_entry[j] = -1;
             int n_here = remaining < 8 ? remaining : 8;
@@ -216,6 +222,15 @@ __global__ void __launch_bounds__(32) place_entries_kernel(uint16_t *cols16, VT 
         }
         c = r_end + 1;
     }
+}
+
+// The scan kernel reads a chunk's "last chunk of its row" flag from bit 15 of the chunk's first entry
+// (columns are < 32768), so it needs no row pointers and no separate mask stream.
+__global__ void mark_tails_kernel(uint16_t *cols16, const uint32_t *tails, uint64_t n_chunks) {
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; c < n_chunks; c += stride)
+        if ((tails[c >> 5] >> (c & 31)) & 1u) cols16[c * 8] |= 0x8000u;
 }
 
 struct NoVal { char c; };  // sizeof == 1: "no values" marker type
@@ -288,15 +303,17 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
     }
     if (N > 0 && idx->bank_aware) {
         const unsigned pblocks = (unsigned)((P + 31) / 32);
+        const int pair_mode = !(idx->kind == 1 && idx->store_dtype == VS_F32);  // scan.cu: fp32 values keep one chunk per lane
 #define VS_PLACE(VT)                                                                                            \
     place_entries_kernel<VT><<<pblocks, 32, 0, st>>>((uint16_t *)idx->cols, (VT *)idx->vals, idx->tails,        \
-                                                     idx->part_win_begin, P, (int)idx->n_cols)
+                                                     idx->part_win_begin, P, (int)idx->n_cols, pair_mode)
         if (idx->kind == 2) VS_PLACE(NoVal);
         else if (idx->store_dtype == VS_F32) VS_PLACE(float);
         else if (idx->store_dtype == VS_F16) VS_PLACE(__half);
         else VS_PLACE(__nv_bfloat16);
 #undef VS_PLACE
     }
+    if (n_windows) mark_tails_kernel<<<2048, 256, 0, st>>>((uint16_t *)idx->cols, idx->tails, n_windows * 32ull);
     int h_err = 0;
     VS_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     VS_CUDA(cudaStreamSynchronize(st));
@@ -322,7 +339,7 @@ __global__ void export_len_kernel(const WsView idx, const uint32_t *row_chunk, u
     while (!((idx.tails[ch >> 5] >> (ch & 31)) & 1u)) ++ch;
     uint64_t e = (ch + 1) * 8ull;
     uint64_t n = 0;
-    for (uint64_t j = a; j < e; ++j) n += (c16[j] != (uint16_t)idx.n_cols);
+    for (uint64_t j = a; j < e; ++j) n += ((c16[j] & 0x7fffu) != (uint16_t)idx.n_cols);
     len[r] = n;
 }
 
@@ -336,7 +353,7 @@ __global__ void export_fill_kernel(const WsView idx, const uint32_t *row_chunk, 
     uint64_t a = (uint64_t)row_chunk[r] * 8ull;
     uint64_t o = crow[r], n = crow[r + 1] - crow[r];
     for (uint64_t j = 0, w = 0; w < n; ++j) {
-        uint16_t c = c16[a + j];
+        uint16_t c = c16[a + j] & 0x7fffu;   // bit 15 of a chunk's first entry is the tail flag
         if (c == (uint16_t)idx.n_cols) continue;
         out_col[o + w] = c;
         float v = 1.0f;

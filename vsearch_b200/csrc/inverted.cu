@@ -48,7 +48,7 @@ inv_build_kernel(const WsView idx, uint32_t *cta_hist /* [n_ctas, V] counts (cou
         const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const uint32_t c = (e & 1) ? (wv[e >> 1] >> 16) : (wv[e >> 1] & 0xffffu);
+            const uint32_t c = ((e & 1) ? (wv[e >> 1] >> 16) : (wv[e >> 1] & 0xffffu)) & 0x7fffu;  // bit 15 = tail flag
             if (c >= (uint32_t)V) continue;  // padding
             const uint32_t slot = atomicAdd(&s_cnt[c], 1u);
             if constexpr (FILL) {

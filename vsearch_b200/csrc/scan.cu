@@ -5,10 +5,11 @@
 // One persistent CTA per SM, kScanWarps (24) warps.  Per query ("pass"):
 //   1. the dense fp32 query vector (V+1 slots, slot V = 0 for padding) is pulled into shared
 //      memory with 1-D bulk TMA copies (cp.async.bulk + mbarrier);
-//   2. every warp streams ITS part of the WS index (index.cuh): one 512-byte window per step,
-//      16 bytes per lane, D windows in flight per warp (register ring) -- loads never depend on
-//      row pointers; each lane gathers q[col] for its 8 entries from shared memory;
-//   3. a segmented warp scan over the window's tail mask turns lane partials into row scores;
+//   2. every warp streams ITS part of the WS index (index.cuh): one 1024-byte double window (64
+//      chunks) per step, two adjacent 16-byte chunks per lane, D steps in flight per warp (register
+//      ring) -- loads never depend on row pointers, the row-end ("tail") flag of a chunk rides in
+//      bit 15 of its first entry; each lane gathers q[col] for its 16 entries from shared memory;
+//   3. ONE segmented warp scan per 64 chunks (6 shuffles) turns lane partials into row scores;
 //   4. rows whose rank key beats the CTA threshold go to a per-warp staging buffer, which is
 //      flushed under a shared-memory lock into the CTA candidate buffer; when that fills, the
 //      flushing warp alone radix-selects it down to k and raises the threshold while the other
@@ -85,7 +86,8 @@ __device__ __forceinline__ float chunk_dot(const Chunk<VT> &ch, const uint32_t q
     float g[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        g[2 * i] = lds_f32(qs + (__byte_perm(w[i], 0, 0x4410) << 2));
+        // entry 0 carries the chunk's tail flag in bit 15 (columns are < 32768)
+        g[2 * i] = lds_f32(qs + ((i == 0 ? (w[i] & 0x7fffu) : __byte_perm(w[i], 0, 0x4410)) << 2));
         g[2 * i + 1] = lds_f32(qs + (__byte_perm(w[i], 0, 0x4432) << 2));
     }
     if constexpr (VT == 0) {
@@ -124,14 +126,69 @@ __device__ __forceinline__ SmemLayout smem_layout(uint8_t *smem, const ScanParam
     return L;
 }
 
-// One window of one warp: lane partial -> segmented scan -> row scores -> (SAMPLE) key into this warp's
-// sampling region, or (!SAMPLE) threshold test + staging.
-// PRE: every lane holds its chunk `cur`; T = tail mask of the window (warp-uniform).
+// One step of one warp = 64 chunks; lane l holds chunks 2l (A) and 2l+1 (B).  Lane partials -> ONE segmented warp
+// scan -> row scores -> (SAMPLE) keys into this warp's sampling slice, or (!SAMPLE) threshold test + private region.
 template <int VT, bool ROUND, bool DIAG, bool SAMPLE>
-__device__ __forceinline__ void process_window(const Chunk<VT> &cur, const uint32_t T, const uint32_t qs, const int lane,
-                                               const uint32_t lt, float &carry, uint32_t &row, int &n_keys,
-                                               const float tau_s, uint8_t *smem, CtaState *st, const ScanParams &p,
-                                               const int b) {
+__device__ __forceinline__ void process_pair(const Chunk<VT> &ca, const Chunk<VT> &cb, const uint32_t qs, const int lane,
+                                             const uint32_t lt, float &carry, uint32_t &row, int &n_keys,
+                                             const float tau_s, uint8_t *smem, CtaState *st, const ScanParams &p,
+                                             const int b) {
+    const bool tail_a = (ca.c.x & 0x8000u) != 0, tail_b = (cb.c.x & 0x8000u) != 0;
+    const float a = chunk_dot<VT>(ca, qs), bsum = chunk_dot<VT>(cb, qs);
+    const uint32_t TA = __ballot_sync(0xffffffffu, tail_a), TB = __ballot_sync(0xffffffffu, tail_b);
+    const uint32_t F = TA | TB;  // lanes in which a row ends
+    // v = what this lane hands on to its right neighbour: the part after its last row end
+    float v = tail_b ? 0.f : (tail_a ? bsum : a + bsum);
+    if (lane == 0 && !(F & 1u)) v += carry;  // lane 0 passes the carry through unless a row ends inside it
+    // inclusive segmented scan of v; a flagged lane RESTARTS the sum (its v is already post-row-end)
+    const uint32_t upto = F & (lt | (1u << lane));
+    const int reach = upto ? lane - (31 - __clz(upto)) : lane;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float o = __shfl_up_sync(0xffffffffu, v, d);
+        if (reach >= d) v += o;
+    }
+    const float rot = __shfl_sync(0xffffffffu, v, (lane + 31) & 31);  // left neighbour's running sum; lane 0 gets lane 31's
+    const float incoming = (lane == 0) ? carry : rot;
+    carry = rot;  // only lane 0's copy is used: the open row's partial sum at the end of this step
+    float sa = incoming + a;                        // score of the row ending in chunk A
+    float sb = tail_a ? bsum : incoming + a + bsum;  // score of the row ending in chunk B
+    const int rank = __popc(TA & lt) + __popc(TB & lt);  // rows completed by the lanes before me
+    const uint32_t rid_a = row + rank, rid_b = rid_a + (tail_a ? 1u : 0u);
+    const int n_rows_step = __popc(TA) + __popc(TB);
+    row += n_rows_step;
+    if constexpr (ROUND) { sa = round_score(sa, p.score_round); sb = round_score(sb, p.score_round); }
+    if constexpr (DIAG) {
+        if (tail_a) p.scores_out[(size_t)b * p.n_rows + rid_a] = sa + 0.0f;
+        if (tail_b) p.scores_out[(size_t)b * p.n_rows + rid_b] = sb + 0.0f;
+    }
+    if constexpr (SAMPLE) {
+        uint64_t *region = reinterpret_cast<uint64_t *>(smem + (size_t)p.vpad * 4) + (threadIdx.x >> 5) * kSampleRegion;
+        if (tail_a) region[n_keys + rank] = make_key(sa, rid_a);
+        if (tail_b) region[n_keys + rank + (tail_a ? 1 : 0)] = make_key(sb, rid_b);
+        n_keys += n_rows_step;
+    } else {
+        // cheap float pre-filter against the score part of the threshold (read once per group of steps);
+        // exact 64-bit test only for survivors
+        const bool maybe_a = tail_a && (sa >= tau_s), maybe_b = tail_b && (sb >= tau_s);
+        if (__any_sync(0xffffffffu, maybe_a || maybe_b)) {
+            const SmemLayout L = smem_layout(smem, p);
+            const uint64_t tau = *(volatile uint64_t *)&st->tau;
+            const uint64_t ka = make_key(sa, rid_a), kb = make_key(sb, rid_b);
+            private_insert<kScanWarps>(maybe_a && ka > tau, ka, L.cbuf, n_keys, lt);
+            private_insert<kScanWarps>(maybe_b && kb > tau, kb, L.cbuf, n_keys, lt);
+        }
+    }
+}
+
+// Single-chunk variant (one chunk per lane, 32 chunks per step): used for fp32 values, where a lane's two chunks
+// (96 bytes of payload) would not fit the register budget twice over and the kernel is HBM-bound anyway.
+template <int VT, bool ROUND, bool DIAG, bool SAMPLE>
+__device__ __forceinline__ void process_window(const Chunk<VT> &cur, const uint32_t qs, const int lane, const uint32_t lt,
+                                               float &carry, uint32_t &row, int &n_keys, const float tau_s, uint8_t *smem,
+                                               CtaState *st, const ScanParams &p, const int b) {
+    const bool is_tail = (cur.c.x & 0x8000u) != 0;
+    const uint32_t T = __ballot_sync(0xffffffffu, is_tail);
     float v = chunk_dot<VT>(cur, qs);
     if (lane == 0) v += carry;
     // segmented inclusive scan: segments end at tail bits; `reach` = how many lanes back my segment extends
@@ -147,7 +204,6 @@ __device__ __forceinline__ void process_window(const Chunk<VT> &cur, const uint3
     const int rank = __popc(before);
     const uint32_t rid = row + rank;
     row += __popc(T);
-    const bool is_tail = (T >> lane) & 1u;
     float s = v;
     if constexpr (ROUND) s = round_score(v, p.score_round);
     if constexpr (DIAG) {
@@ -158,8 +214,6 @@ __device__ __forceinline__ void process_window(const Chunk<VT> &cur, const uint3
         if (is_tail) region[n_keys + rank] = make_key(s, rid);
         n_keys += __popc(T);
     } else {
-        // cheap float pre-filter against the score part of the threshold (read once per group of windows);
-        // exact 64-bit test only for survivors
         const bool maybe = is_tail && (s >= tau_s);
         if (__any_sync(0xffffffffu, maybe)) {
             const SmemLayout L = smem_layout(smem, p);
@@ -170,7 +224,7 @@ __device__ __forceinline__ void process_window(const Chunk<VT> &cur, const uint3
     }
 }
 
-template <int VT, int D, bool ROUND, bool DIAG>
+template <int VT, int D, bool PAIR, bool ROUND, bool DIAG>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ CtaState st;
@@ -181,7 +235,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     const uint32_t w_begin = p.part_win_begin[part];
     const int nwin = (int)(p.part_win_begin[part + 1] - w_begin);
     const uint32_t row0 = p.part_row_begin[part];
-    const uint64_t chunk0 = (uint64_t)w_begin * 32ull + lane;
     const uint32_t q_bytes = (uint32_t)p.vpad * 4u;
 
     if (tid == 0) {
@@ -208,70 +261,79 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         mbar_wait(&st.mbar, phase);
         phase ^= 1u;
 
-        // ---- stream this warp's part.  The stream carries kStreamSlack windows of slack past its end, so the
-        // prefetch ring never needs a bounds check: loads are unconditional, addresses are base + immediate.
-        const uint4 *cp = p.cols + chunk0;
-        const uint4 *vp = (VT == 1) ? (const uint4 *)p.vals + chunk0 * 2 : (const uint4 *)p.vals + chunk0;
-        const uint32_t *tp = p.tails + w_begin;
-        Chunk<VT> ring[D];
-        uint32_t tring[D];
+        // ---- stream this warp's part, 64 chunks (two per lane) per step.  The stream carries kStreamSlack windows
+        // of slack past its end, so the prefetch ring never needs a bounds check: loads are unconditional,
+        // addresses are base + immediate.  Parts are a whole number of 64-chunk steps (build_index.cu).
+        constexpr int CPL = PAIR ? 2 : 1;       // chunks per lane per step
+        constexpr int CPS = 32 * CPL;           // chunks per step
+        constexpr int VS = (VT == 1) ? 2 : 1;   // uint4 of values per chunk
+        const uint4 *cp = p.cols + (uint64_t)w_begin * 32ull + CPL * lane;
+        const uint4 *vp = (const uint4 *)p.vals + ((uint64_t)w_begin * 32ull + CPL * lane) * VS;
+        Chunk<VT> ra[D], rb[PAIR ? D : 1];
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            load_chunk<VT>(ring[j], cp + j * 32, vp + j * (VT == 1 ? 64 : 32));
-            tring[j] = ldg_stream_u32(tp + j);
+            load_chunk<VT>(ra[j], cp + j * CPS, vp + j * CPS * VS);
+            if constexpr (PAIR) load_chunk<VT>(rb[j], cp + j * CPS + 1, vp + (j * CPS + 1) * VS);
         }
         float carry = 0.f;
         uint32_t row = row0;
         int n_keys = 0;   // phase A: keys in this warp's sample slice; phase B: keys in its private region
         int w = 0;
+        const int nstep = PAIR ? (nwin >> 1) : nwin;
+#define VS_PROCESS(SAMPLE, J)                                                                                      \
+    {                                                                                                              \
+        if constexpr (PAIR)                                                                                        \
+            process_pair<VT, ROUND, DIAG, SAMPLE>(ra[J], rb[J], qs, lane, lt, carry, row, n_keys, tau_s, smem,     \
+                                                  &st, p, b);                                                      \
+        else                                                                                                       \
+            process_window<VT, ROUND, DIAG, SAMPLE>(ra[J], qs, lane, lt, carry, row, n_keys, tau_s, smem, &st, p,  \
+                                                    b);                                                            \
+    }
 #define VS_STEP(SAMPLE, J)                                                                                         \
     {                                                                                                              \
-        process_window<VT, ROUND, DIAG, SAMPLE>(ring[J], tring[J], qs, lane, lt, carry, row, n_keys, tau_s, smem,  \
-                                                &st, p, b);                                                        \
-        load_chunk<VT>(ring[J], cp + (D + J) * 32, vp + (D + J) * (VT == 1 ? 64 : 32));                            \
-        tring[J] = ldg_stream_u32(tp + D + J);                                                                     \
+        VS_PROCESS(SAMPLE, J)                                                                                      \
+        load_chunk<VT>(ra[J], cp + (D + J) * CPS, vp + (D + J) * CPS * VS);                                        \
+        if constexpr (PAIR) load_chunk<VT>(rb[J], cp + (D + J) * CPS + 1, vp + ((D + J) * CPS + 1) * VS);          \
     }
 #define VS_ADVANCE()                                                                                               \
     {                                                                                                              \
-        cp += D * 32;                                                                                              \
-        vp += D * (VT == 1 ? 64 : 32);                                                                             \
-        tp += D;                                                                                                   \
+        cp += D * CPS;                                                                                             \
+        vp += D * CPS * VS;                                                                                        \
         w += D;                                                                                                    \
     }
-        // ---- phase A: sampling.  Every row's key goes straight into this warp's region of cbuf (no threshold,
-        // no lock) until the region cannot take D more windows; then ONE CTA-wide select sets the threshold.
+        // ---- phase A: sampling.  Every row's key goes straight into this warp's slice of cbuf (no threshold, no
+        // lock) until the slice cannot take D more steps; then ONE CTA-wide select sets the threshold.
         float tau_s = -INFINITY;
-        while (w + D <= nwin && n_keys + D * 32 <= kSampleRegion) {
+        while (w + D <= nstep && n_keys + D * CPS <= kSampleRegion) {
 #pragma unroll
             for (int j = 0; j < D; ++j) VS_STEP(true, j)
             VS_ADVANCE()
         }
+        const SmemLayout L = smem_layout(smem, p);
         {
-            const SmemLayout L = smem_layout(smem, p);
             for (int i = n_keys + lane; i < kSampleRegion; i += 32) L.cbuf[warp * kSampleRegion + i] = 0ull;
             __syncthreads();
             cta_sample_select<kScanThreads>(L.cbuf, kSampleKeys, p.k, L.hist, &st);
             n_keys = 0;
         }
-        // ---- phase B: steady state.  Once per group of D windows: one 64-bit "gate" load (float threshold + join
-        // epoch), and a join when somebody asked for a re-selection or this warp's region cannot take D more windows.
+        // ---- phase B: steady state.  Once per group of D steps: one 64-bit "gate" load (float threshold + join
+        // epoch), and a join when somebody asked for a re-selection or this warp's region cannot take D more steps.
         uint32_t epoch = 0;
-        const SmemLayout L = smem_layout(smem, p);
-        while (w + D <= nwin) {
+        while (w + D <= nstep) {
             const uint64_t gate = gate_load(&st);
             tau_s = gate_tau_score(gate);
 #pragma unroll
             for (int j = 0; j < D; ++j) VS_STEP(false, j)
             VS_ADVANCE()
-            join_if_needed<kScanThreads, kScanWarps>(gate, epoch, D * 32, L.cbuf, n_keys, p.k, L.hist, &st);
+            join_if_needed<kScanThreads, kScanWarps>(gate, epoch, D * CPS, L.cbuf, n_keys, p.k, L.hist, &st);
         }
         tau_s = gate_tau_score(gate_load(&st));
 #pragma unroll
         for (int j = 0; j < D - 1; ++j)
-            if (w + j < nwin) process_window<VT, ROUND, DIAG, false>(ring[j], tring[j], qs, lane, lt, carry, row, n_keys,
-                                                                     tau_s, smem, &st, p, b);
+            if (w + j < nstep) VS_PROCESS(false, j)
         finish_streaming<kScanThreads, kScanWarps>(epoch, L.cbuf, n_keys, p.k, L.hist, &st);
 #undef VS_STEP
+#undef VS_PROCESS
 #undef VS_ADVANCE
         {
             // ---- exact top-k of this CTA's rows, written unsorted (merge.cu sorts)
@@ -316,20 +378,20 @@ int launch_prep_query(const void *d_q, int q_dtype, int64_t B, int64_t ldq, int6
     return VS_OK;
 }
 
-template <int VT, int D, bool ROUND, bool DIAG>
+template <int VT, int D, bool PAIR, bool ROUND, bool DIAG>
 static int launch_scan_t(const vs_index *idx, const ScanParams &p, size_t smem, cudaStream_t st) {
-    auto kern = scan_topk_kernel<VT, D, ROUND, DIAG>;
+    auto kern = scan_topk_kernel<VT, D, PAIR, ROUND, DIAG>;
     VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<idx->n_ctas, kScanThreads, smem, st>>>(p);
     VS_CUDA(cudaGetLastError());
     return VS_OK;
 }
 
-template <int VT, int D>
+template <int VT, int D, bool PAIR>
 static int launch_scan_v(const vs_index *idx, const ScanParams &p, size_t smem, cudaStream_t st) {
-    if (p.scores_out) return launch_scan_t<VT, D, true, true>(idx, p, smem, st);  // diagnostic path
-    if (p.score_round != VS_F32) return launch_scan_t<VT, D, true, false>(idx, p, smem, st);
-    return launch_scan_t<VT, D, false, false>(idx, p, smem, st);
+    if (p.scores_out) return launch_scan_t<VT, D, PAIR, true, true>(idx, p, smem, st);  // diagnostic path
+    if (p.score_round != VS_F32) return launch_scan_t<VT, D, PAIR, true, false>(idx, p, smem, st);
+    return launch_scan_t<VT, D, PAIR, false, false>(idx, p, smem, st);
 }
 
 // d_qprep: [B, vpad] fp32; d_cand: [B, n_ctas, k] keys; d_scores_out optional [B, N]
@@ -356,11 +418,12 @@ int launch_scan(const vs_index *idx, const float *d_qprep, int vpad, int64_t B, 
                "n_cols=%lld needs %zu bytes of shared memory (> 227 KB): vocabulary too large for the scan kernel",
                (long long)idx->n_cols, smem);
     static_assert(kStreamSlack >= 8, "prefetch ring deeper than the stream slack");
-    static_assert(ScanGeom::kPrivate >= 2 * 4 * 32, "private region must hold two groups of windows");
-    if (idx->kind == 2) return launch_scan_v<0, 4>(idx, p, smem, st);
-    if (idx->store_dtype == VS_F32) return launch_scan_v<1, 2>(idx, p, smem, st);
-    if (idx->store_dtype == VS_F16) return launch_scan_v<2, 3>(idx, p, smem, st);
-    return launch_scan_v<3, 3>(idx, p, smem, st);
+    static_assert(ScanGeom::kPrivate >= 3 * 64 + 32, "private region must take one group of steps");
+    // <value type, steps in flight per warp, two chunks per lane?>; the placement at build uses the same mode
+    if (idx->kind == 2) return launch_scan_v<0, 3, true>(idx, p, smem, st);
+    if (idx->store_dtype == VS_F32) return launch_scan_v<1, 2, false>(idx, p, smem, st);
+    if (idx->store_dtype == VS_F16) return launch_scan_v<2, 2, true>(idx, p, smem, st);
+    return launch_scan_v<3, 2, true>(idx, p, smem, st);
 }
 
 }  // namespace vs
