@@ -145,8 +145,30 @@ def cfg4():
          ms_per_call=ms, qps_shard=B / ms * 1e3, TFLOPs=2.0 * B * n_s * d / (ms * 1e-3) / 1e12)
 
 
+def cfg2_torch():
+    """B2 baseline of BASELINE.md: the reference's own torch path (cuSPARSE SpMM + topk) on the SAME B200 for the
+    headline config (21M x 120 binary).  The [B, N] score matrix limits the batch (B=64 -> 5.4 GB)."""
+    from oracle import ref_search
+    n, m = 21_015_324, 120
+    cols = strat_cols(n, m, 1234).reshape(-1).to(torch.int64)
+    crow = torch.arange(n + 1, device=dev, dtype=torch.int64) * m
+    for dtype in (torch.float32, torch.float16):
+        try:
+            vals = torch.ones(n * m, device=dev, dtype=dtype)
+            X = torch.sparse_csr_tensor(crow, cols, vals, size=(n, V))
+            for B in (1, 64):
+                q = queries(B, 64)
+                ms = timed(lambda: ref_search.ref_search(q, X, 100), reps=3, warm=1)
+                emit(config="cfg2", impl=f"reference torch CSR matmul+topk on the SAME B200 (cuSPARSE), values {dtype}", B=B,
+                     ms_per_call=ms, qps=B / ms * 1e3, peak_mem_GB=torch.cuda.max_memory_allocated() / 1e9)
+            del X, vals
+        except Exception as e:  # noqa: BLE001
+            emit(config="cfg2", impl=f"reference torch GPU {dtype}", error=str(e)[:300])
+        torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg1", "cfg3", "cfg4"]
     for w in which:
-        {"cfg1": cfg1, "cfg3": cfg3, "cfg4": cfg4}[w]()
+        {"cfg1": cfg1, "cfg3": cfg3, "cfg4": cfg4, "cfg2_torch": cfg2_torch}[w]()
         torch.cuda.empty_cache()
