@@ -105,123 +105,181 @@ __global__ void fill_rows_kernel(const void *crow, int crow_dtype, const void *c
     }
 }
 
+struct NoVal { char c; };  // sizeof == 1: "no values" marker type
+
 // ---- bank-aware entry placement ---------------------------------------------------------------------------
-// A scan step covers 64 chunks, lane l holding chunks 2l and 2l+1: gather #j of the even (odd) chunks reads slot j of
-// the 32 even (odd) chunks of the step at once; the shared-memory cost of that instruction is the largest number of
-// lanes hitting one bank (bank = column mod 32).  A dot product does not
-// care about the order of a row's entries, so each row's entries are re-dealt over its (chunk, slot) positions:
-//   pass 1  slot by slot, take the row's most plentiful bank that this window has not used yet in that slot;
-//   pass 2  what is left must collide: put it in the latest free slot, on the bank with the fewest lanes there.
-// Random order costs 3.5 wavefronts per gather, this greedy ~2.0 (lower bound ~1.8 for 256-entry windows).
-// One thread per stream part, rows in order; one-off work at index build.
-constexpr int kPlaceMaxRow = 512;   // longer rows keep their original order
+// A scan step covers 32*CPL chunks (CPL = chunks per lane: 2 for the binary / 16-bit-value kernels, 1 for fp32 values).
+// Gather #j of sub-chunk q reads slot j of the 32 chunks {CPL*l + q} of the step at once; the shared-memory cost of
+// that instruction is the largest number of lanes hitting one bank (bank = column mod 32).  A dot product does not
+// care about the order of a row's entries, so inside every step each row's entries are re-dealt over the row's
+// (chunk, slot) positions of that step: for every gather group (slot, sub-chunk) a maximum bipartite matching
+// lanes -> banks (edge = the lane's row still has an entry in that bank; banks tried in order of the row's remaining
+// supply; Kuhn's augmenting paths) gives every lane a DISTINCT bank whenever one exists; unmatched lanes collide on
+// the emptiest bank their row can still supply.
+// Random order costs 3.5 wavefronts per gather, a greedy deal 2.0-2.1, the matching 1.83 = the bound set by the
+// per-step bank imbalance of random columns (simulated; measured numbers in profiles/README.md).
+// One warp per step (steps are independent: entries never leave their step), state in shared memory; the search
+// itself is sequential but every inner loop over banks is one ballot / redux.  One-off work at index build.
+template <typename VT, int CPL>
+struct alignas(16) PlaceScratch {
+    static constexpr int SC = 32 * CPL;   // chunks per step
+    static constexpr int NP = SC * 8;     // entry positions per step
+    static constexpr int NV = sizeof(VT) > 1 ? NP : 8;
+    uint16_t ecol[NP];                    // the step's entries as loaded (sentinel = padding)
+    uint16_t ocol[NP];                    // ... and as re-dealt
+    VT eval[NV];
+    VT oval[NV];
+    int16_t nxt[NP];                      // per (segment, bank) linked lists of unused entries
+    int16_t head[SC][32];
+    uint16_t sup[SC][32];                 // remaining entries per (segment, bank); segment = piece of a row in the step
+    int16_t rem[SC];                      // remaining entries per segment
+    uint8_t chunk_seg[SC];
+};
 
-template <typename VT>
-__global__ void __launch_bounds__(32) place_entries_kernel(uint16_t *cols16, VT *vals, const uint32_t *tails,
-                                                           const uint32_t *part_win_begin, int n_parts, int n_cols,
-                                                           int pair_mode) {
-    const int part = blockIdx.x * blockDim.x + threadIdx.x;
-    if (part >= n_parts) return;
-    const uint64_t c_begin = (uint64_t)part_win_begin[part] * 32ull, c_end = (uint64_t)part_win_begin[part + 1] * 32ull;
+constexpr int kPlaceWarps = 8;
+
+template <typename VT, int CPL>
+__global__ void __launch_bounds__(kPlaceWarps * 32) place_step_kernel(uint16_t *cols16, VT *vals, const uint32_t *tails,
+                                                                      uint64_t n_steps, int n_cols) {
+    using S = PlaceScratch<VT, CPL>;
+    constexpr int SC = S::SC, NP = S::NP;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr bool kVals = sizeof(VT) > 1;
+    extern __shared__ __align__(16) unsigned char place_smem[];
+    S &s = reinterpret_cast<S *>(place_smem)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const uint16_t sent = (uint16_t)n_cols;
-    const int sent_bank = n_cols & 31;
-    uint16_t ecol[kPlaceMaxRow];
-    uint16_t order[kPlaceMaxRow];    // entry indices grouped by bank
-    VT eval[kPlaceMaxRow];
-    uint8_t mult2[2][8][32];         // lanes per (chunk parity, slot, bank) in the current 64-chunk step
-    uint32_t used2[2][8];
-    uint16_t cnt[32], head[32];
-    for (int q = 0; q < 2; ++q) for (int j = 0; j < 8; ++j) { used2[q][j] = 0; for (int b = 0; b < 32; ++b) mult2[q][j][b] = 0; }
+    const uint64_t n_warps = (uint64_t)gridDim.x * kPlaceWarps;
 
-    uint64_t c = c_begin;
-    while (c < c_end) {
-        // row = chunks [c, r_end]: r_end is the first chunk at or after c whose tail bit is set
-        uint64_t r_end = c;
-        while (r_end < c_end && !((tails[r_end >> 5] >> (r_end & 31)) & 1u)) ++r_end;
-        if (r_end >= c_end) break;  // trailing padding chunks of the part (no row)
-        const int nch = (int)(r_end - c + 1);
-        int n = 0;
-        bool fits = nch * 8 <= kPlaceMaxRow;
-        if (fits) {
-            for (int i = 0; i < nch * 8; ++i) {
-                const uint16_t col = cols16[c * 8 + i];
-                if (col != sent) {
-                    ecol[n] = col;
-                    if constexpr (sizeof(VT) > 1) eval[n] = vals[c * 8 + i];
-                    ++n;
-                }
+    for (uint64_t step = (uint64_t)blockIdx.x * kPlaceWarps + (threadIdx.x >> 5); step < n_steps; step += n_warps) {
+        const uint64_t c0 = step * SC;
+        uint64_t T;  // row-end flags of the step's chunks
+        if constexpr (CPL == 2) T = (uint64_t)tails[2 * step] | ((uint64_t)tails[2 * step + 1] << 32);
+        else T = tails[step];
+        const int n_seg = __popcll(T & ((1ull << (SC - 1)) - 1ull)) + 1;
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            const int c = CPL * lane + q;
+            *reinterpret_cast<uint4 *>(&s.ecol[c * 8]) = *reinterpret_cast<const uint4 *>(cols16 + (c0 + c) * 8);
+            if constexpr (kVals) {
+                constexpr int kVec = (int)sizeof(VT) * 8 / 16;
+#pragma unroll
+                for (int t = 0; t < kVec; ++t)
+                    reinterpret_cast<uint4 *>(&s.eval[c * 8])[t] = reinterpret_cast<const uint4 *>(vals + (c0 + c) * 8)[t];
             }
-            for (int b = 0; b < 32; ++b) cnt[b] = 0;
-            for (int i = 0; i < n; ++i) ++cnt[ecol[i] & 31];
-            uint16_t run = 0;
-            for (int b = 0; b < 32; ++b) { head[b] = run; run += cnt[b]; }
-            {
-                uint16_t fill[32];
-                for (int b = 0; b < 32; ++b) fill[b] = head[b];
-                for (int i = 0; i < n; ++i) order[fill[ecol[i] & 31]++] = (uint16_t)i;
+            s.chunk_seg[c] = (uint8_t)__popcll(T & ((1ull << c) - 1ull));
+        }
+        for (int r = 0; r < n_seg; ++r) { s.head[r][lane] = -1; s.sup[r][lane] = 0; }
+        __syncwarp();
+        // lane = bank: thread every entry of that bank onto its segment's list (no two lanes touch the same list)
+        for (int pos = 0; pos < NP; ++pos) {
+            const uint16_t col = s.ecol[pos];
+            if (col != sent && (col & 31) == lane) {
+                const int r = s.chunk_seg[pos >> 3];
+                s.nxt[pos] = s.head[r][lane];
+                s.head[r][lane] = (int16_t)pos;
+                ++s.sup[r][lane];
             }
         }
-        uint32_t avail = 0;
-        if (fits) for (int b = 0; b < 32; ++b) if (cnt[b]) avail |= 1u << b;
-        int remaining = n;
-        for (int ch = 0; ch < nch; ++ch) {
-            const uint64_t cc = c + ch;
-            // conflict set of a gather: the 32 even (odd) chunks of a 64-chunk step in pair mode, else 32 consecutive chunks
-            if ((cc & (pair_mode ? 63 : 31)) == 0)
-                for (int q = 0; q < 2; ++q) for (int j = 0; j < 8; ++j) { used2[q][j] = 0; for (int b = 0; b < 32; ++b) mult2[q][j][b] = 0; }
-            if (!fits) continue;
-            uint32_t *used = used2[pair_mode ? (cc & 1) : 0];
-            uint8_t (*mult)[32] = mult2[pair_mode ? (cc & 1) : 0];
-            int slot_entry[8];
-            for (int j = 0; j < 8; ++j) slot_entry[j] = -1;
-            int n_here = remaining < 8 ? remaining : 8;
-            int placed = 0;
-            for (int j = 0; j < 8 && placed < n_here; ++j) {  // pass 1: conflict-free picks
-                uint32_t cand = avail & ~used[j];
-                int best = -1, bc = 0;
-                while (cand) {
-                    const int b = __ffs(cand) - 1;
-                    cand &= cand - 1;
-                    if (cnt[b] > bc) { bc = cnt[b]; best = b; }
+        __syncwarp();
+        for (int r = lane; r < n_seg; r += 32) {
+            int t = 0;
+            for (int b = 0; b < 32; ++b) t += s.sup[r][b];
+            s.rem[r] = (int16_t)t;
+        }
+        __syncwarp();
+
+        // ---- gather groups: slot j of sub-chunk q -> one position per lane
+        for (int j = 0; j < 8; ++j)
+            for (int q = 0; q < CPL; ++q) {
+                const int c = CPL * lane + q;
+                const int r = s.chunk_seg[c];
+                const unsigned same = __match_any_sync(FULL, r);
+                const int rank = __popc(same & lt), remr = s.rem[r];
+                const bool part = rank < remr;  // the segment still has an entry for this lane
+                const int ls = part ? r : -1;
+                __syncwarp();
+                if (rank == 0) s.rem[r] = (int16_t)(remr - min(__popc(same), remr));
+                int bl = -1;   // lane b: the lane matched to bank b
+                int lb = -1;   // the bank matched to this lane
+                int st_lane = 0, st_bank = 0;  // lane t: DFS stack entry t
+                for (unsigned pm = __ballot_sync(FULL, part); pm; pm &= pm - 1) {  // Kuhn's augmenting paths
+                    const int l0 = __ffs(pm) - 1;
+                    unsigned visited = 0;
+                    int sp = 0;
+                    if (lane == 0) st_lane = l0;
+                    while (sp >= 0) {
+                        const int l = __shfl_sync(FULL, st_lane, sp);
+                        const int rr = __shfl_sync(FULL, ls, l);
+                        const unsigned sv = s.sup[rr][lane];
+                        const unsigned key = (sv > 0 && !((visited >> lane) & 1u)) ? ((sv << 5) | (31u - lane)) + 1u : 0u;
+                        const unsigned mx = __reduce_max_sync(FULL, key);  // unvisited bank with the largest supply
+                        if (mx == 0) { --sp; continue; }
+                        const int b = 31 - (int)((mx - 1u) & 31u);
+                        visited |= 1u << b;
+                        if (lane == sp) st_bank = b;
+                        const int cur = __shfl_sync(FULL, bl, b);
+                        if (cur < 0) {  // free bank: flip the path
+                            for (int t = 0; t <= sp; ++t) {
+                                const int tl = __shfl_sync(FULL, st_lane, t), tb = __shfl_sync(FULL, st_bank, t);
+                                if (lane == tb) bl = tl;
+                                if (lane == tl) lb = tb;
+                            }
+                            break;
+                        }
+                        ++sp;
+                        if (lane == sp) st_lane = cur;
+                    }
                 }
-                if (best >= 0) {
-                    slot_entry[j] = order[head[best] + --cnt[best]];
-                    if (cnt[best] == 0) avail &= ~(1u << best);
-                    used[j] |= 1u << best;
-                    ++mult[j][best];
-                    ++placed;
+                int e = -1;
+                if (lb >= 0) { e = s.head[ls][lb]; s.head[ls][lb] = s.nxt[e]; --s.sup[ls][lb]; }
+                __syncwarp();
+                // lanes without a distinct bank collide on the emptiest bank their segment can still supply
+                unsigned mult = bl >= 0 ? 1u : 0u;
+                for (unsigned um = __ballot_sync(FULL, part && lb < 0); um; um &= um - 1) {
+                    const int l = __ffs(um) - 1;
+                    const int rr = __shfl_sync(FULL, ls, l);
+                    const unsigned sv = s.sup[rr][lane];
+                    const unsigned key = sv > 0 ? (((255u - mult) << 21) | (min(sv, 0xffffu) << 5) | (31u - lane)) + 1u : 0u;
+                    const unsigned mx = __reduce_max_sync(FULL, key);
+                    if (mx == 0) continue;  // cannot happen: part guarantees supply
+                    const int b = 31 - (int)((mx - 1u) & 31u);
+                    if (lane == b) ++mult;
+                    if (lane == l) { e = s.head[rr][b]; s.head[rr][b] = s.nxt[e]; --s.sup[rr][b]; }
+                    __syncwarp();
                 }
+                const int pos = c * 8 + j;
+                s.ocol[pos] = e >= 0 ? s.ecol[e] : sent;
+                if constexpr (kVals) {
+                    if (e >= 0) s.oval[pos] = s.eval[e];
+                    else memset(&s.oval[pos], 0, sizeof(VT));
+                }
+                __syncwarp();
             }
-            for (int j = 7; j >= 0 && placed < n_here; --j) {  // pass 2: unavoidable collisions, latest slots first
-                if (slot_entry[j] >= 0) continue;
-                uint32_t cand = avail;
-                int best = -1, bm = 255, bc = -1;
-                while (cand) {
-                    const int b = __ffs(cand) - 1;
-                    cand &= cand - 1;
-                    if (mult[j][b] < bm || (mult[j][b] == bm && cnt[b] > bc)) { bm = mult[j][b]; bc = cnt[b]; best = b; }
-                }
-                slot_entry[j] = order[head[best] + --cnt[best]];
-                if (cnt[best] == 0) avail &= ~(1u << best);
-                used[j] |= 1u << best;
-                ++mult[j][best];
-                ++placed;
-            }
-            remaining -= n_here;
-            for (int j = 0; j < 8; ++j) {
-                const int e = slot_entry[j];
-                if (e >= 0) {
-                    cols16[cc * 8 + j] = ecol[e];
-                    if constexpr (sizeof(VT) > 1) vals[cc * 8 + j] = eval[e];
-                } else {
-                    cols16[cc * 8 + j] = sent;
-                    if constexpr (sizeof(VT) > 1) vals[cc * 8 + j] = VT(0);
-                    used[j] |= 1u << sent_bank;  // padding lanes all read the same (zero) slot: a broadcast
-                }
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            const int c = CPL * lane + q;
+            *reinterpret_cast<uint4 *>(cols16 + (c0 + c) * 8) = *reinterpret_cast<const uint4 *>(&s.ocol[c * 8]);
+            if constexpr (kVals) {
+                constexpr int kVec = (int)sizeof(VT) * 8 / 16;
+#pragma unroll
+                for (int t = 0; t < kVec; ++t)
+                    reinterpret_cast<uint4 *>(vals + (c0 + c) * 8)[t] = reinterpret_cast<const uint4 *>(&s.oval[c * 8])[t];
             }
         }
-        c = r_end + 1;
+        __syncwarp();
     }
+}
+
+template <typename VT, int CPL>
+static int launch_place(uint16_t *cols16, VT *vals, const uint32_t *tails, uint64_t n_steps, int n_cols, int sms, cudaStream_t st) {
+    const size_t smem = sizeof(PlaceScratch<VT, CPL>) * kPlaceWarps;
+    VS_CUDA(cudaFuncSetAttribute(place_step_kernel<VT, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n_steps + kPlaceWarps - 1) / kPlaceWarps, (uint64_t)sms * 2);
+    place_step_kernel<VT, CPL><<<blocks, kPlaceWarps * 32, smem, st>>>(cols16, vals, tails, n_steps, n_cols);
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
 }
 
 // The scan kernel reads a chunk's "last chunk of its row" flag from bit 15 of the chunk's first entry
@@ -233,7 +291,6 @@ __global__ void mark_tails_kernel(uint16_t *cols16, const uint32_t *tails, uint6
         if ((tails[c >> 5] >> (c & 31)) & 1u) cols16[c * 8] |= 0x8000u;
 }
 
-struct NoVal { char c; };  // sizeof == 1: "no values" marker type
 
 int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void *d_col, int col_dtype,
                    const void *d_val, int val_dtype, cudaStream_t st) {
@@ -301,17 +358,16 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
         else VS_FILL(__nv_bfloat16);
 #undef VS_FILL
     }
-    if (N > 0 && idx->bank_aware) {
-        const unsigned pblocks = (unsigned)((P + 31) / 32);
-        const int pair_mode = !(idx->kind == 1 && idx->store_dtype == VS_F32);  // scan.cu: fp32 values keep one chunk per lane
-#define VS_PLACE(VT)                                                                                            \
-    place_entries_kernel<VT><<<pblocks, 32, 0, st>>>((uint16_t *)idx->cols, (VT *)idx->vals, idx->tails,        \
-                                                     idx->part_win_begin, P, (int)idx->n_cols, pair_mode)
-        if (idx->kind == 2) VS_PLACE(NoVal);
-        else if (idx->store_dtype == VS_F32) VS_PLACE(float);
-        else if (idx->store_dtype == VS_F16) VS_PLACE(__half);
-        else VS_PLACE(__nv_bfloat16);
-#undef VS_PLACE
+    if (N > 0 && idx->bank_aware && n_windows) {
+        // scan.cu: fp32 values keep one chunk per lane (32-chunk steps), everything else two (64-chunk steps)
+        const bool pair = !(idx->kind == 1 && idx->store_dtype == VS_F32);
+        const uint64_t n_steps = pair ? n_windows / 2 : n_windows;
+        int rc;
+        if (idx->kind == 2) rc = launch_place<NoVal, 2>((uint16_t *)idx->cols, (NoVal *)nullptr, idx->tails, n_steps, (int)idx->n_cols, idx->n_ctas, st);
+        else if (idx->store_dtype == VS_F32) rc = launch_place<float, 1>((uint16_t *)idx->cols, (float *)idx->vals, idx->tails, n_steps, (int)idx->n_cols, idx->n_ctas, st);
+        else if (idx->store_dtype == VS_F16) rc = launch_place<__half, 2>((uint16_t *)idx->cols, (__half *)idx->vals, idx->tails, n_steps, (int)idx->n_cols, idx->n_ctas, st);
+        else rc = launch_place<__nv_bfloat16, 2>((uint16_t *)idx->cols, (__nv_bfloat16 *)idx->vals, idx->tails, n_steps, (int)idx->n_cols, idx->n_ctas, st);
+        if (rc != VS_OK) return rc;
     }
     if (n_windows) mark_tails_kernel<<<2048, 256, 0, st>>>((uint16_t *)idx->cols, idx->tails, n_windows * 32ull);
     int h_err = 0;
