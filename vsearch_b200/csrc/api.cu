@@ -189,6 +189,7 @@ int vs_index_destroy(vs_index *idx) {
     cudaFree(idx->cols); cudaFree(idx->vals); cudaFree(idx->tails);
     cudaFree(idx->part_win_begin); cudaFree(idx->part_row_begin); cudaFree(idx->row_chunk);
     cudaFree(idx->dense);
+    cudaFree(idx->post_ptr); cudaFree(idx->blk_ptr); cudaFree(idx->blk_base); cudaFree(idx->post_row); cudaFree(idx->post_val);
     for (int i = 0; i < VS_TIMER_SLOTS; ++i) {
         if (idx->ev0[i]) cudaEventDestroy(idx->ev0[i]);
         if (idx->ev1[i]) cudaEventDestroy(idx->ev1[i]);

@@ -43,10 +43,14 @@ struct vs_index {
     uint32_t *part_row_begin = nullptr;  // n_parts + 1
     uint32_t *row_chunk = nullptr;       // N + 1: first chunk of each row in the stream (export, rerank)
 
-    // ---- K3 token-major inverted lists (built lazily from the WS stream on first use)
+    // ---- K3 block-partitioned token-major inverted lists (built lazily from the WS stream on first use)
     bool inv_built = false;
-    uint64_t *post_ptr = nullptr;   // n_cols + 1
-    uint32_t *post_doc = nullptr;   // nnz: passage ids, grouped by token (CTA-range order inside a token)
+    // rows are cut into n_blocks blocks of blk_rows rows; each block has its own token-major lists (inverted.cu)
+    int blk_rows = 0, n_blocks = 0, blocks_per_cta = 0;
+    uint64_t *post_ptr = nullptr;   // n_cols + 1: global postings per token (exclusive prefix; cost model)
+    uint32_t *blk_ptr = nullptr;    // n_blocks x (n_cols + 1): list offsets inside the block
+    uint64_t *blk_base = nullptr;   // n_blocks + 1: first posting of each block
+    uint16_t *post_row = nullptr;   // nnz: block-local row ids, grouped by (block, token)
     void *post_val = nullptr;       // nnz values in store_dtype (valued index only)
     int64_t inv_bytes = 0;
 
@@ -67,7 +71,6 @@ struct vs_index {
 struct WsView {
     const uint4 *cols; const void *vals; const uint32_t *tails;
     const uint32_t *part_win_begin; const uint32_t *part_row_begin; const uint32_t *row_chunk;
-    uint64_t *post_ptr; uint32_t *post_doc; void *post_val;
     int64_t n_rows, n_cols;
     int kind, store_dtype;
 };
@@ -75,7 +78,6 @@ inline WsView ws_view(const vs_index *i) {
     WsView v;
     v.cols = i->cols; v.vals = i->vals; v.tails = i->tails;
     v.part_win_begin = i->part_win_begin; v.part_row_begin = i->part_row_begin; v.row_chunk = i->row_chunk;
-    v.post_ptr = i->post_ptr; v.post_doc = i->post_doc; v.post_val = i->post_val;
     v.n_rows = i->n_rows; v.n_cols = i->n_cols; v.kind = i->kind; v.store_dtype = i->store_dtype;
     return v;
 }

@@ -1,13 +1,19 @@
 // inverted.cu -- K3: token-major inverted-list scoring for sparse queries, sm_100a.
-// Same contract as the scan (replaces upstream index.py:91-92) but touches only the posting lists of
-// the query's non-zero tokens:
-//   build   : WS stream -> post_ptr[V+1], post_doc[nnz] (+ post_val) grouped by token (one-off, lazy)
-//   extract : prepared query [vpad] -> compact (token, weight) list + prefix of posting-list lengths
-//   accum   : flattened postings of the query -> RED.ADD.F32 into a zeroed fp32 accumulator row [N]
-//             (L2-resident: 21 M x 4 B = 84 MB)
-//   select  : stream the accumulator once, zero it behind, fused top-k (topk.cuh) -> per-CTA key lists
-//             -> merge.cu.  Rows never touched keep score 0 and compete like any other row.
-// Algorithmic bytes per query: sum_t len(post_t) * (4 + b_val) + 2 * N * 4.
+// Same contract as the scan (replaces upstream index.py:91-92) but touches only the posting lists of the query's
+// non-zero tokens.  The lists are BLOCK-PARTITIONED: the rows are cut into blocks of R <= 36,864 consecutive rows
+// (a multiple of the SM count of them when the index is large), and every block keeps its own token-major posting
+// lists with 16-bit block-local row ids.  A block's fp32 score accumulator (R x 4 B <= 144 KB) lives in SHARED
+// memory, so scoring one query against one block is
+//   zero the accumulator -> add w_t (x value) at every posting of the query's tokens (shared-memory atomics)
+//   -> stream the accumulator through the fused top-k (topk.cuh)
+// without a byte of accumulator traffic to L2/HBM (the first version kept an [N] fp32 row in global memory:
+// RED.ADD.F32 into L2 + a read-and-clear pass over 2 x 4N bytes per query = 200 us per query at 21M rows).
+//   build   : WS stream -> blk_ptr[n_blocks][V+1] (uint32 offsets inside the block), blk_base[n_blocks] (uint64),
+//             post_row[nnz] (uint16) (+ post_val[nnz]), post_ptr[V+1] = global list lengths (cost model) -- lazy
+//   extract : prepared query [vpad] -> compact (token, weight) list + total postings
+//   search  : grid (n_ctas, queries); CTA x owns blocks [x*bpc, (x+1)*bpc) -> one candidate list per CTA -> merge.cu
+// Rows never touched keep score 0 and compete like any other row.
+// Algorithmic bytes per query: sum_t len(post_t) * (2 + b_val)  (+ 8 B of block pointers per (block, token)).
 #include <cub/device/device_scan.cuh>
 
 #include <stdlib.h>
@@ -19,104 +25,160 @@
 
 namespace vs {
 
-constexpr int kInvThreads = 1024;
-constexpr int kBuildThreads = kScanWarps * 32;   // the builders walk the stream with the scan kernel's partition
-constexpr int kMaxQueryNnz = 4096;   // queries denser than this are served by the scan kernels
+constexpr int kInvThreads = 768;      // 24 warps, one CTA per SM (shared memory bound)
+constexpr int kInvWarps = kInvThreads / 32;
+constexpr int kInvBuildThreads = 1024;
+constexpr int kMaxQueryNnz = 4096;    // queries denser than this are served by the scan kernels
+constexpr int kBlockRowsMax = 36864;  // accumulator rows per block: 144 KB of the 227 KB
+constexpr int kBlockRowsMin = 8192;   // small indices: fewer, longer lists rather than one tiny block per SM
+constexpr int kTokTile = 512;         // query tokens staged per pass over a block
+
+struct BlockLists {
+    uint32_t *blk_ptr;     // [n_blocks, V + 1]
+    uint64_t *blk_base;    // [n_blocks + 1]
+    uint16_t *post_row;    // [nnz]
+    void *post_val;        // [nnz] in store_dtype, or nullptr
+    uint64_t *tok_total;   // [V + 1] global postings per token (counts, then exclusive prefix = post_ptr)
+    int rows_per_block, n_blocks, V;
+};
+
+template <int NT>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s_warp, uint32_t &block_total) {
+    constexpr int NWARP = NT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < NWARP; ++i) { uint32_t x = s_warp[i]; if (i < warp) base += x; tot += x; }
+    __syncthreads();
+    block_total = tot;
+    return base + incl - v;
+}
 
 // ------------------------------------------------------------------------------------------- build
-// Both build kernels walk the WS stream exactly like the scan kernel: warp = part, window by window.
+// One CTA per row block, one thread per row (rows are runs of 16-byte chunks in the WS stream, row_chunk[] = first
+// chunk of each row).  Count pass: per-token histogram in shared memory -> exclusive offsets blk_ptr[b][*];
+// fill pass: the same walk with the offsets as cursors.
 template <bool FILL>
-__global__ void __launch_bounds__(kBuildThreads, 1)
-inv_build_kernel(const WsView idx, uint32_t *cta_hist /* [n_ctas, V] counts (count pass) / offsets (fill pass) */) {
-    extern __shared__ uint32_t s_cnt[];  // V counters
-    const int V = (int)idx.n_cols;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t *mine = cta_hist + (size_t)blockIdx.x * V;
-    for (int i = tid; i < V; i += kBuildThreads) s_cnt[i] = FILL ? mine[i] : 0u;
+__global__ void __launch_bounds__(kInvBuildThreads, 1) inv_build_kernel(const WsView idx, const BlockLists bl, int *err) {
+    extern __shared__ uint32_t s_cnt[];  // V counters / cursors
+    __shared__ uint32_t s_warp[kInvBuildThreads / 32];
+    __shared__ unsigned long long s_total;
+    const int V = bl.V, tid = threadIdx.x, b = blockIdx.x;
+    if (tid == 0) s_total = 0;
+    uint32_t *my_ptr = bl.blk_ptr + (size_t)b * (V + 1);
+    for (int i = tid; i < V; i += kInvBuildThreads) s_cnt[i] = FILL ? my_ptr[i] : 0u;
     __syncthreads();
-    const int part = blockIdx.x * kScanWarps + warp;
-    const uint32_t w_begin = idx.part_win_begin[part];
-    const int nwin = (int)(idx.part_win_begin[part + 1] - w_begin);
-    uint32_t row = idx.part_row_begin[part];
-    const uint32_t lt = lanemask_lt();
-    for (int w = 0; w < nwin; ++w) {
-        const uint64_t chunk = ((uint64_t)w_begin + w) * 32ull + lane;
-        const uint32_t T = idx.tails[w_begin + w];
-        const uint32_t rid = row + __popc(T & lt);
-        row += __popc(T);
-        const uint4 u = idx.cols[chunk];
-        const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+    const int64_t r0 = (int64_t)b * bl.rows_per_block;
+    const int64_t r1 = min(idx.n_rows, r0 + bl.rows_per_block);
+    const uint64_t base = FILL ? bl.blk_base[b] : 0ull;
+    for (int64_t r = r0 + tid; r < r1; r += kInvBuildThreads) {
+        const uint32_t c0 = idx.row_chunk[r], c1 = idx.row_chunk[r + 1];
+        for (uint32_t ch = c0; ch < c1; ++ch) {
+            const uint4 u = idx.cols[ch];
+            const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const uint32_t c = ((e & 1) ? (wv[e >> 1] >> 16) : (wv[e >> 1] & 0xffffu)) & 0x7fffu;  // bit 15 = tail flag
-            if (c >= (uint32_t)V) continue;  // padding
-            const uint32_t slot = atomicAdd(&s_cnt[c], 1u);
-            if constexpr (FILL) {
-                const uint64_t pos = idx.post_ptr[c] + slot;
-                idx.post_doc[pos] = rid;
-                if (idx.kind == 1) {
-                    const uint64_t src = chunk * 8ull + e;
-                    if (idx.store_dtype == VS_F32) ((float *)idx.post_val)[pos] = ((const float *)idx.vals)[src];
-                    else ((uint16_t *)idx.post_val)[pos] = ((const uint16_t *)idx.vals)[src];
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t c = ((e & 1) ? (wv[e >> 1] >> 16) : (wv[e >> 1] & 0xffffu)) & 0x7fffu;  // bit 15 = row-end flag
+                if (c >= (uint32_t)V) continue;  // padding
+                const uint32_t slot = atomicAdd(&s_cnt[c], 1u);
+                if constexpr (FILL) {
+                    const uint64_t pos = base + slot;
+                    bl.post_row[pos] = (uint16_t)(r - r0);
+                    if (idx.kind == 1) {
+                        const uint64_t src = (uint64_t)ch * 8ull + e;
+                        if (idx.store_dtype == VS_F32) ((float *)bl.post_val)[pos] = ((const float *)idx.vals)[src];
+                        else ((uint16_t *)bl.post_val)[pos] = ((const uint16_t *)idx.vals)[src];
+                    }
                 }
             }
         }
     }
     if constexpr (!FILL) {
         __syncthreads();
-        for (int i = tid; i < V; i += kBuildThreads) mine[i] = s_cnt[i];
+        const int per = (V + kInvBuildThreads - 1) / kInvBuildThreads;
+        const int lo = min(V, tid * per), hi = min(V, lo + per);
+        uint64_t sum = 0;
+        for (int i = lo; i < hi; ++i) sum += s_cnt[i];
+        atomicAdd(&s_total, (unsigned long long)sum);
+        uint32_t total;
+        uint32_t run = block_exclusive_scan<kInvBuildThreads>((uint32_t)sum, s_warp, total);
+        for (int i = lo; i < hi; ++i) {
+            const uint32_t c = s_cnt[i];
+            my_ptr[i] = run;
+            run += c;
+            if (c) atomicAdd((unsigned long long *)&bl.tok_total[i], (unsigned long long)c);
+        }
+        if (tid == 0) {
+            if (s_total >= (1ull << 32)) atomicExch(err, 1);
+            my_ptr[V] = total;
+            bl.blk_base[b] = s_total;  // sizes now, exclusive prefix after the host-side scan
+        }
     }
 }
 
-// per token: counts per CTA -> exclusive offsets per CTA (in place) and the token total
-__global__ void inv_offsets_kernel(uint32_t *cta_hist, int n_ctas, int V, uint64_t *totals, int *err) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > V) return;
-    if (t == V) { totals[t] = 0; return; }
-    uint64_t run = 0;
-    for (int c = 0; c < n_ctas; ++c) {
-        uint32_t h = cta_hist[(size_t)c * V + t];
-        cta_hist[(size_t)c * V + t] = (uint32_t)run;
-        run += h;
-    }
-    if (run >= (1ull << 32)) atomicExch(err, 1);
-    totals[t] = run;
+static void block_geometry(const vs_index *idx, int *rows_per_block, int *n_blocks, int *blocks_per_cta) {
+    const int64_t N = idx->n_rows > 0 ? idx->n_rows : 1;
+    const int64_t per_cta = (N + idx->n_ctas - 1) / idx->n_ctas;
+    int64_t R, bpc = 1;
+    if (per_cta <= kBlockRowsMax) R = per_cta < kBlockRowsMin ? kBlockRowsMin : per_cta;
+    else { bpc = (per_cta + kBlockRowsMax - 1) / kBlockRowsMax; R = (N + idx->n_ctas * bpc - 1) / (idx->n_ctas * bpc); }
+    R = (R + 3) / 4 * 4;
+    *rows_per_block = (int)R;
+    *n_blocks = (int)((N + R - 1) / R);
+    *blocks_per_cta = (int)bpc;
 }
 
 int build_inverted(vs_index *idx, cudaStream_t st) {
     if (idx->inv_built) return VS_OK;
     const int V = (int)idx->n_cols;
     const size_t smem = (size_t)V * 4;
-    VS_REQUIRE(smem <= 227 * 1024, VS_ERR_UNSUPPORTED, "vocabulary too large for the inverted-list builder");
-    uint32_t *d_hist = nullptr;
+    VS_REQUIRE(smem <= 200 * 1024, VS_ERR_UNSUPPORTED, "vocabulary too large for the inverted-list builder");
+    block_geometry(idx, &idx->blk_rows, &idx->n_blocks, &idx->blocks_per_cta);
+    const int nb = idx->n_blocks;
     int *d_err = nullptr;
     void *d_tmp = nullptr;
-    size_t tmp_bytes = 0;
-    auto cleanup = [&]() { cudaFree(d_hist); cudaFree(d_err); cudaFree(d_tmp); };
-    VS_CUDA(cudaMalloc(&d_hist, (size_t)idx->n_ctas * V * 4));
+    size_t tmp_bytes = 0, tmp2 = 0;
+    auto cleanup = [&]() { cudaFree(d_err); cudaFree(d_tmp); };
     VS_CUDA(cudaMalloc(&d_err, 4));
     VS_CUDA(cudaMemsetAsync(d_err, 0, 4, st));
     VS_CUDA(cudaMalloc(&idx->post_ptr, (size_t)(V + 1) * 8));
-    VS_CUDA(cudaMalloc(&idx->post_doc, idx->nnz ? (size_t)idx->nnz * 4 : 4));
-    size_t vbytes = idx->kind == 1 ? (idx->store_dtype == VS_F32 ? 4 : 2) : 0;
+    VS_CUDA(cudaMemsetAsync(idx->post_ptr, 0, (size_t)(V + 1) * 8, st));
+    VS_CUDA(cudaMalloc(&idx->blk_ptr, (size_t)nb * (V + 1) * 4));
+    VS_CUDA(cudaMalloc(&idx->blk_base, (size_t)(nb + 1) * 8));
+    VS_CUDA(cudaMemsetAsync(idx->blk_base, 0, (size_t)(nb + 1) * 8, st));
+    VS_CUDA(cudaMalloc(&idx->post_row, idx->nnz ? (size_t)idx->nnz * 2 : 4));
+    const size_t vbytes = idx->kind == 1 ? (idx->store_dtype == VS_F32 ? 4 : 2) : 0;
     if (vbytes) VS_CUDA(cudaMalloc(&idx->post_val, idx->nnz ? (size_t)idx->nnz * vbytes : 4));
+    BlockLists bl;
+    bl.blk_ptr = idx->blk_ptr; bl.blk_base = idx->blk_base; bl.post_row = idx->post_row; bl.post_val = idx->post_val;
+    bl.tok_total = idx->post_ptr; bl.rows_per_block = idx->blk_rows; bl.n_blocks = nb; bl.V = V;
 
     VS_CUDA(cudaFuncSetAttribute(inv_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VS_CUDA(cudaFuncSetAttribute(inv_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    inv_build_kernel<false><<<idx->n_ctas, kBuildThreads, smem, st>>>(ws_view(idx), d_hist);
-    inv_offsets_kernel<<<(V + 1 + 255) / 256, 256, 0, st>>>(d_hist, idx->n_ctas, V, idx->post_ptr, d_err);
+    inv_build_kernel<false><<<nb, kInvBuildThreads, smem, st>>>(ws_view(idx), bl, d_err);
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, idx->post_ptr, idx->post_ptr, V + 1, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, idx->blk_base, idx->blk_base, nb + 1, st);
+    tmp_bytes = tmp_bytes > tmp2 ? tmp_bytes : tmp2;
     VS_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16));
     cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, idx->post_ptr, idx->post_ptr, V + 1, st);
-    inv_build_kernel<true><<<idx->n_ctas, kBuildThreads, smem, st>>>(ws_view(idx), d_hist);
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, idx->blk_base, idx->blk_base, nb + 1, st);
+    inv_build_kernel<true><<<nb, kInvBuildThreads, smem, st>>>(ws_view(idx), bl, d_err);
     int h_err = 0;
     cudaError_t e = cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
     cleanup();
     VS_CUDA(e);
-    VS_REQUIRE(h_err == 0, VS_ERR_UNSUPPORTED, "a posting list exceeds 2^32 entries");
-    idx->inv_bytes = (int64_t)((size_t)idx->nnz * (4 + vbytes) + (size_t)(V + 1) * 8);
+    VS_REQUIRE(h_err == 0, VS_ERR_UNSUPPORTED, "a row block holds 2^32 or more postings");
+    idx->inv_bytes = (int64_t)((size_t)idx->nnz * (2 + vbytes) + (size_t)nb * (V + 1) * 4 + (size_t)(V + 1) * 8);
     idx->device_bytes += idx->inv_bytes;
     idx->inv_built = true;
     return VS_OK;
@@ -194,156 +256,173 @@ __global__ void __launch_bounds__(256) inv_extract_kernel(const float *q, int vp
     if (tid == 0) { pref[m] = (uint32_t)run; L.total[b] = s_total; }
 }
 
-// ------------------------------------------------------------------------------------------- accumulate
-struct AccumParams {
+// ------------------------------------------------------------------------------------------- search
+struct InvSearchParams {
     QueryLists L;
-    const uint64_t *post_ptr;
-    const uint32_t *post_doc;
+    const uint32_t *blk_ptr;
+    const uint64_t *blk_base;
+    const uint16_t *post_row;
     const void *post_val;
-    int val_kind;       // 0 none (binary), 1 f32, 2 f16, 3 bf16
-    float *acc;         // [G, n_pad]
-    int64_t n_pad;
-    int b0;             // first query of the group
+    int val_kind;        // 0 none (binary), 1 f32, 2 f16, 3 bf16
+    int V, rows_per_block, n_blocks, blocks_per_cta;
+    int64_t n_rows;
+    uint64_t *cand;      // [B, gridDim.x, k]
+    int k, score_round;
 };
 
-__global__ void __launch_bounds__(256) inv_accum_kernel(const AccumParams p) {
-    extern __shared__ __align__(16) uint8_t asmem[];
-    const int g = blockIdx.y, b = p.b0 + g, tid = threadIdx.x;
-    const uint32_t cnt = min(p.L.cnt[b], (uint32_t)kMaxQueryNnz);
-    uint32_t *s_pref = reinterpret_cast<uint32_t *>(asmem);                    // cnt + 1
-    uint64_t *s_base = reinterpret_cast<uint64_t *>(asmem + (((size_t)cnt + 1) * 4 + 15) / 16 * 16);  // cnt
-    float *s_w = reinterpret_cast<float *>(s_base + cnt);                     // cnt
-    const uint32_t *pref = p.L.pref + (size_t)b * (kMaxQueryNnz + 1);
-    const uint32_t *tok = p.L.tok + (size_t)b * kMaxQueryNnz;
-    const float *w = p.L.w + (size_t)b * kMaxQueryNnz;
-    for (uint32_t i = tid; i <= cnt; i += 256) s_pref[i] = pref[i];
-    for (uint32_t i = tid; i < cnt; i += 256) { s_base[i] = p.post_ptr[tok[i]]; s_w[i] = w[i]; }
-    __syncthreads();
-    const uint32_t total = s_pref[cnt];
-    float *acc = p.acc + (size_t)g * p.n_pad;
-    const uint32_t stride = gridDim.x * 256u;
-    // 4 independent postings per thread per trip: the id loads overlap, then the reductions are issued back to back
-    for (uint64_t idx64 = (uint64_t)blockIdx.x * 256u + tid; idx64 < total; idx64 += 4ull * stride) {
-        uint32_t doc[4];
-        float v[4];
-        bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint64_t i64 = idx64 + (uint64_t)u * stride;
-            ok[u] = i64 < total;
-            const uint32_t idx = ok[u] ? (uint32_t)i64 : 0u;
-            uint32_t lo = 0, hi = cnt;  // largest lo with s_pref[lo] <= idx
-            while (hi - lo > 1) {
-                uint32_t mid = (lo + hi) >> 1;
-                if (s_pref[mid] <= idx) lo = mid; else hi = mid;
-            }
-            const uint64_t pos = s_base[lo] + (idx - s_pref[lo]);
-            doc[u] = ok[u] ? p.post_doc[pos] : 0u;
-            v[u] = s_w[lo];
-            if (ok[u]) {
-                if (p.val_kind == 1) v[u] *= ((const float *)p.post_val)[pos];
-                else if (p.val_kind == 2) v[u] *= __half2float(((const __half *)p.post_val)[pos]);
-                else if (p.val_kind == 3) v[u] *= __bfloat162float(((const __nv_bfloat16 *)p.post_val)[pos]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (ok[u]) atomicAdd(acc + doc[u], v[u]);  // result unused -> RED.E.ADD.F32
-    }
+__device__ __forceinline__ float posting_value(const void *vals, int kind, uint64_t pos) {
+    if (kind == 1) return ((const float *)vals)[pos];
+    if (kind == 2) return __half2float(((const __half *)vals)[pos]);
+    return __bfloat162float(((const __nv_bfloat16 *)vals)[pos]);
 }
 
-// ------------------------------------------------------------------------------------------- select
-struct SelectParams {
-    float *acc;          // [G, n_pad]; zeroed behind the read
-    uint64_t *cand;      // [B, n_ctas, k]
-    int64_t n_rows, n_pad;
-    int b0, k, cap, score_round;
-    int rows_per_cta;    // multiple of 4
-    int zero_behind;     // 1 (always, except timing experiments): clear the accumulator row behind the read
-};
-
-__global__ void __launch_bounds__(kInvThreads, 1) inv_select_kernel(const SelectParams p) {
+__global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSearchParams p) {
+    constexpr int NT = kInvThreads, NW = kInvWarps;
     extern __shared__ __align__(128) uint8_t ssmem[];
-    uint64_t *cbuf = reinterpret_cast<uint64_t *>(ssmem);
-    uint32_t *hist = reinterpret_cast<uint32_t *>(cbuf + kCapMax);
+    uint64_t *cbuf = reinterpret_cast<uint64_t *>(ssmem);                      // kCapMax keys
+    uint32_t *hist = reinterpret_cast<uint32_t *>(cbuf + kCapMax);             // 256
+    uint32_t *s_tok = hist + 256;                                              // kTokTile each
+    float *s_w = reinterpret_cast<float *>(s_tok + kTokTile);
+    uint32_t *s_beg = reinterpret_cast<uint32_t *>(s_w + kTokTile);
+    uint32_t *s_len = s_beg + kTokTile;
+    uint32_t *s_spref = s_len + kTokTile;                                      // kTokTile + 4
+    uint32_t *s_warp = s_spref + kTokTile + 4;                                 // 32
+    float *acc = reinterpret_cast<float *>(s_warp + 32);                       // rows_per_block
     __shared__ CtaState st;
-    constexpr int NW = kInvThreads / 32;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int g = blockIdx.y, b = p.b0 + g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
+    const int q = blockIdx.y;
+    const int cnt = (int)min(p.L.cnt[q], (uint32_t)kMaxQueryNnz);
+    const uint32_t *tok = p.L.tok + (size_t)q * kMaxQueryNnz;
+    const float *w = p.L.w + (size_t)q * kMaxQueryNnz;
+    const int R = p.rows_per_block;
+    const int blk0 = blockIdx.x * p.blocks_per_cta, blk1 = min(p.n_blocks, blk0 + p.blocks_per_cta);
+    const bool cached = cnt <= kTokTile;   // the whole token list stays in shared memory across blocks
     if (tid == 0) cta_state_reset(&st);
+    if (cached && tid < cnt) { s_tok[tid] = tok[tid]; s_w[tid] = w[tid]; }
     __syncthreads();
-    float4 *acc4 = reinterpret_cast<float4 *>(p.acc + (size_t)g * p.n_pad);
-    const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
-    const int64_t r_end = min(p.n_rows, r_begin + p.rows_per_cta);
-    // ---- phase A: the first kCapMax rows go straight into cbuf, then one CTA-wide select sets the threshold
-    for (int i = tid; i < (kCapMax >> 2); i += kInvThreads) {
-        const int64_t r = r_begin + (int64_t)i * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < r_end) {
-            v = acc4[r >> 2];
-            acc4[r >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const float s[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            cbuf[i * 4 + e] = (r + e < r_end) ? make_key(round_score(s[e], p.score_round), (uint32_t)(r + e)) : 0ull;
+    uint32_t np0 = 0, np1 = 0;             // next block's list bounds of token `tid` (prefetched under the select)
+    if (cached && blk0 < blk1 && tid < cnt) {
+        const uint32_t *bp = p.blk_ptr + (size_t)blk0 * (p.V + 1) + s_tok[tid];
+        np0 = bp[0]; np1 = bp[1];
     }
-    __syncthreads();
-    cta_sample_select<kInvThreads>(cbuf, kCapMax, p.k, hist, &st);
     int n_priv = 0;
-    uint32_t epoch = 0;
-    // ---- phase B: warp-uniform trip count (every lane of a warp iterates the same number of times).
-    // kSelU float4 loads per thread are issued before any of the zeroing stores: interleaving a load and a store
-    // to the same line per trip runs 3-5x slower (scripts/micro/red_stream.cu, measured on B200).
-    constexpr int kSelU = 4;
-    static_assert(TopkGeom<NW>::kPrivate >= 128 + 32, "private region must take one 128-row step");
-    for (int64_t r = r_begin + kCapMax + (int64_t)tid * 4; r - (int64_t)lane * 4 < r_end;
-         r += (int64_t)kInvThreads * 4 * kSelU) {
-        float4 v[kSelU];
-        bool in[kSelU];
+    bool sampled = false;
+    float4 *acc4 = reinterpret_cast<float4 *>(acc);
+
+    for (int b = blk0; b < blk1; ++b) {
+        const int64_t row0 = (int64_t)b * R;
+        const int rows_b = (int)min((int64_t)R, p.n_rows - row0);
+        const uint64_t base = p.blk_base[b];
+        for (int i = tid; i < (R >> 2); i += NT) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // ---- accumulate: tiles of <= kTokTile query tokens
+        for (int t0 = 0; t0 < cnt; t0 += kTokTile) {
+            const int tn = min(kTokTile, cnt - t0);
+            uint32_t p0 = np0, p1 = np1;
+            if (!cached) {
+                __syncthreads();  // previous tile fully consumed
+                if (tid < tn) {
+                    const uint32_t t = tok[t0 + tid];
+                    s_tok[tid] = t; s_w[tid] = w[t0 + tid];
+                    const uint32_t *bp = p.blk_ptr + (size_t)b * (p.V + 1) + t;
+                    p0 = bp[0]; p1 = bp[1];
+                }
+            }
+            const uint32_t len = tid < tn ? p1 - p0 : 0u;
+            uint32_t n_strips;
+            const uint32_t ex = block_exclusive_scan<NT>((len + 31u) >> 5, s_warp, n_strips);  // strips of 32 postings
+            if (tid < tn) { s_beg[tid] = p0; s_len[tid] = len; s_spref[tid] = ex; }
+            if (tid == tn) s_spref[tn] = n_strips;
+            __syncthreads();
+            // warp `warp` takes a contiguous range of strips, four at a time
+            const uint32_t s_lo = (uint32_t)(((uint64_t)n_strips * warp) / NW);
+            const uint32_t s_hi = (uint32_t)(((uint64_t)n_strips * (warp + 1)) / NW);
+            if (s_lo < s_hi) {
+                int lo = 0, hi = tn;  // largest ti with s_spref[ti] <= s_lo
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_spref[mid] <= s_lo) lo = mid; else hi = mid;
+                }
+                int ti = lo;
+                for (uint32_t s = s_lo; s < s_hi; s += 4) {
+                    uint32_t row[4];
+                    float v[4];
+                    bool ok[4];
 #pragma unroll
-        for (int u = 0; u < kSelU; ++u) {
-            const int64_t ru = r + (int64_t)u * kInvThreads * 4;
-            in[u] = ru < r_end;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (in[u]) v[u] = acc4[ru >> 2];
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t su = s + u;
+                        ok[u] = false; row[u] = 0; v[u] = 0.f;
+                        if (su < s_hi) {
+                            while (su >= s_spref[ti + 1]) ++ti;
+                            const uint32_t off = (su - s_spref[ti]) * 32u + lane;
+                            if (off < s_len[ti]) {
+                                const uint64_t pos = base + s_beg[ti] + off;
+                                ok[u] = true;
+                                row[u] = p.post_row[pos];
+                                v[u] = s_w[ti];
+                                if (p.val_kind) v[u] *= posting_value(p.post_val, p.val_kind, pos);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (ok[u]) atomicAdd(&acc[row[u]], v[u]);
+                }
+            }
         }
-#pragma unroll
-        for (int u = 0; u < kSelU; ++u) {
-            const int64_t ru = r + (int64_t)u * kInvThreads * 4;
-            if (in[u] && p.zero_behind) acc4[ru >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        if (cached && b + 1 < blk1 && tid < cnt) {
+            const uint32_t *bp = p.blk_ptr + (size_t)(b + 1) * (p.V + 1) + s_tok[tid];
+            np0 = bp[0]; np1 = bp[1];
         }
+        // ---- select: the block's scores go through the fused top-k
+        int i0 = 0;
+        if (!sampled) {  // phase A: the CTA's first kCapMax rows set the threshold
+            for (int i = tid; i < (kCapMax >> 2); i += NT) {
+                const int r = i * 4;
+                const float4 v = r < rows_b ? acc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float s[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int u = 0; u < kSelU; ++u) {
-            const int64_t ru = r + (int64_t)u * kInvThreads * 4;
-            const float s[4] = {round_score(v[u].x, p.score_round), round_score(v[u].y, p.score_round),
-                                round_score(v[u].z, p.score_round), round_score(v[u].w, p.score_round)};
-            const uint64_t gate = gate_load(&st);
-            const float tau_s = gate_tau_score(gate);
+                for (int e = 0; e < 4; ++e)
+                    cbuf[r + e] = (r + e < rows_b) ? make_key(round_score(s[e], p.score_round), (uint32_t)(row0 + r + e)) : 0ull;
+            }
+            __syncthreads();
+            cta_sample_select<NT>(cbuf, kCapMax, p.k, hist, &st);
+            sampled = true;
+            i0 = kCapMax;
+        }
+        // phase B: CTA-uniform steps of NT*4 rows; a join when some warp's private region could overflow next step
+        for (int rb = i0; rb < rows_b; rb += NT * 4) {
+            const int r = rb + tid * 4;
+            const bool in = r < rows_b;
+            const float4 v = in ? acc4[r >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float s[4] = {round_score(v.x, p.score_round), round_score(v.y, p.score_round),
+                                round_score(v.z, p.score_round), round_score(v.w, p.score_round)};
+            const float tau_s = gate_tau_score(gate_load(&st));
             const float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
-            if (__any_sync(0xffffffffu, in[u] && mx >= tau_s)) {  // else nothing in these 128 rows can qualify
+            if (__any_sync(0xffffffffu, in && mx >= tau_s)) {
                 const uint64_t tau = *(volatile uint64_t *)&st.tau;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int64_t rid = ru + e;
-                    const uint64_t key = make_key(s[e], (uint32_t)rid);
-                    private_insert<NW>(in[u] && rid < r_end && key > tau, key, cbuf, n_priv, lt);
+                    const uint64_t key = make_key(s[e], (uint32_t)(row0 + r + e));
+                    private_insert<NW>(in && r + e < rows_b && key > tau, key, cbuf, n_priv, lt);
                 }
             }
-            join_if_needed<kInvThreads, NW>(gate, epoch, 128, cbuf, n_priv, p.k, hist, &st);
+            if (__syncthreads_or(n_priv + 128 > TopkGeom<NW>::kPrivate)) {
+                cta_join<NT, NW>(cbuf, n_priv, p.k, hist, &st);
+                n_priv = 0;
+            }
         }
+        __syncthreads();
     }
-    finish_streaming<kInvThreads, NW>(epoch, cbuf, n_priv, p.k, hist, &st);
-    cta_write_topk<kInvThreads, NW>(cbuf, n_priv, p.k, hist, &st,
-                                    p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k);
+    cta_write_topk<NT, NW>(cbuf, n_priv, p.k, hist, &st, p.cand + ((size_t)q * gridDim.x + blockIdx.x) * (size_t)p.k);
 }
 
 // ------------------------------------------------------------------------------------------- host side
 size_t inverted_workspace_bytes(const vs_index *idx, int64_t Bc, int group) {
-    size_t n_pad = ((size_t)idx->n_rows + 3) / 4 * 4;
+    (void)idx; (void)group;
     size_t lists = (size_t)Bc * ((size_t)kMaxQueryNnz * 8 + ((size_t)kMaxQueryNnz + 1) * 4 + 4 + 8);
-    return (lists + 255) / 256 * 256 + ((size_t)group * n_pad * 4 + 255) / 256 * 256 + 1024;
+    return (lists + 255) / 256 * 256 + 1024;
 }
 
 static QueryLists carve_lists(uint8_t *base, int64_t Bc, uint8_t **end) {
@@ -396,32 +475,19 @@ bool inverted_usable(uint32_t max_nnz, uint64_t max_postings) {
 // Score Bc extracted queries (lists already in d_ws) -> cand [Bc, n_ctas, k].
 int launch_inverted(vs_index *idx, int64_t Bc, int k, int score_round, int group, uint32_t max_nnz, void *d_ws, uint64_t *d_cand,
                     cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t st) {
-    uint8_t *acc_base;
-    QueryLists L = carve_lists((uint8_t *)d_ws, Bc, &acc_base);
-    const int64_t n_pad = (idx->n_rows + 3) / 4 * 4;
-    float *acc = (float *)acc_base;
-    VS_CUDA(cudaMemsetAsync(acc, 0, (size_t)group * n_pad * 4, st));
-    const int cap = scan_cap_for_k(k);
-    const size_t sel_smem = (size_t)kCapMax * 8 + 256 * 4;
-    VS_CUDA(cudaFuncSetAttribute(inv_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-    const size_t acc_smem = ((size_t)max_nnz + 1) * 4 + 16 + (size_t)max_nnz * 12 + 16;
-    VS_CUDA(cudaFuncSetAttribute(inv_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_smem));
-    int rows_per_cta = (int)((idx->n_rows + idx->n_ctas - 1) / idx->n_ctas);
-    rows_per_cta = (rows_per_cta + 3) / 4 * 4;
+    (void)group; (void)max_nnz;
+    uint8_t *end;
+    QueryLists L = carve_lists((uint8_t *)d_ws, Bc, &end);
+    const size_t smem = (size_t)kCapMax * 8 + 256 * 4 + (size_t)kTokTile * 4 * 5 + 16 + 32 * 4 + (size_t)idx->blk_rows * 4;
+    VS_REQUIRE(smem <= 227 * 1024, VS_ERR_UNSUPPORTED, "inverted-list search needs %zu bytes of shared memory", smem);
+    VS_CUDA(cudaFuncSetAttribute(inv_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    InvSearchParams p;
+    p.L = L; p.blk_ptr = idx->blk_ptr; p.blk_base = idx->blk_base; p.post_row = idx->post_row; p.post_val = idx->post_val;
+    p.val_kind = idx->kind == 1 ? (idx->store_dtype == VS_F32 ? 1 : (idx->store_dtype == VS_F16 ? 2 : 3)) : 0;
+    p.V = (int)idx->n_cols; p.rows_per_block = idx->blk_rows; p.n_blocks = idx->n_blocks; p.blocks_per_cta = idx->blocks_per_cta;
+    p.n_rows = idx->n_rows; p.cand = d_cand; p.k = k; p.score_round = score_round;
     if (ev0) VS_CUDA(cudaEventRecord(ev0, st));
-    for (int64_t b0 = 0; b0 < Bc; b0 += group) {
-        const int G = (int)((Bc - b0) < group ? (Bc - b0) : group);
-        AccumParams ap;
-        ap.L = L; ap.post_ptr = idx->post_ptr; ap.post_doc = idx->post_doc; ap.post_val = idx->post_val;
-        ap.val_kind = idx->kind == 1 ? (idx->store_dtype == VS_F32 ? 1 : (idx->store_dtype == VS_F16 ? 2 : 3)) : 0;
-        ap.acc = acc; ap.n_pad = n_pad; ap.b0 = (int)b0;
-        inv_accum_kernel<<<dim3(idx->n_ctas * 4, G), 256, acc_smem, st>>>(ap);
-        SelectParams sp;
-        sp.acc = acc; sp.cand = d_cand; sp.n_rows = idx->n_rows; sp.n_pad = n_pad; sp.b0 = (int)b0; sp.k = k;
-        sp.cap = cap; sp.score_round = score_round; sp.rows_per_cta = rows_per_cta;
-        sp.zero_behind = getenv("VSEARCH_B200_DEBUG_NOZERO") ? 0 : 1;
-        inv_select_kernel<<<dim3(idx->n_ctas, G), kInvThreads, sel_smem, st>>>(sp);
-    }
+    inv_search_kernel<<<dim3(idx->n_ctas, (unsigned)Bc), kInvThreads, smem, st>>>(p);
     if (ev1) VS_CUDA(cudaEventRecord(ev1, st));
     VS_CUDA(cudaGetLastError());
     return VS_OK;
