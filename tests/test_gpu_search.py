@@ -302,6 +302,53 @@ def test_inverted_heavy_ties_and_continuous(cuda_device):
     assert msg is None, msg
 
 
+def test_inverted_ascending_scores_replay_path(cuda_device):
+    """K3 worst case: scores increase with the row id, so after the sampling phase EVERY row beats the threshold;
+    the optimistic whole-block pass overflows the append region and each block is replayed stepwise with joins.
+    One token owns the whole list (n postings per block > kLongList): the cooperative long-list path."""
+    n, v = 300_000, 64
+    crow = torch.arange(n + 1, dtype=torch.int64)
+    col = torch.zeros(n, dtype=torch.int64)
+    val = (torch.arange(n, dtype=torch.float32) % 65536) / 8.0 + (torch.arange(n) // 65536).float() * 8192.0
+    X = ref_search.torch_csr(crow, col, val, (n, v))
+    idx = _mk("SparseIndex", crow, col, val, (n, v))
+    idx.search_mode = "inverted"
+    q = torch.zeros(2, v)
+    q[0, 0], q[1, 0] = 1.0, -1.0
+    for k in (100, 1500):
+        res = idx.search(q, k)
+        assert idx.last_mode() == "inverted"
+        assert ref_search.compare_results(res, ref_search.ref_scores(q, X), k, exact=True) is None
+
+
+def test_inverted_multi_block_ctas_and_zipf_lists(cuda_device):
+    """> 148 x 36,864 rows: several row blocks per CTA; heavy-tailed token popularity (one token in every row)."""
+    n, m = 5_600_000, 6
+    g = torch.Generator(device="cuda").manual_seed(5)
+    col = torch.randint(1, 4000, (n, m), generator=g, device="cuda", dtype=torch.int64)
+    col[:, 0] = 0                                   # token 0 is in every row
+    col[:, 1] = torch.randint(1, 9, (n,), generator=g, device="cuda")   # 8 very popular tokens
+    col[:, 2:] += 4000 * torch.arange(1, m - 1, device="cuda")[None, :]  # distinct ranges: no duplicates in a row
+    col, _ = torch.sort(col, dim=1)
+    val = torch.randint(1, 64, (n, m), generator=g, device="cuda").float() / 16.0
+    crow = torch.arange(n + 1, device="cuda", dtype=torch.int64) * m
+    idx = _mk("SparseIndex", crow, col.reshape(-1), val.reshape(-1), (n, V))
+    q = torch.zeros(3, V)
+    q[0, 0] = 1.0
+    q[1, [0, 3, 5, 4100, 9000]] = torch.tensor([0.5, 2.0, 1.0, 3.0, 1.5])
+    q[2, [2, 8, 5000, 13000, 17000, 20001]] = torch.tensor([1.0, -1.0, 2.0, 0.25, 4.0, 1.0])
+    idx.search_mode = "inverted"
+    a = idx.search(q, 100)
+    assert idx.last_mode() == "inverted"
+    idx.search_mode = "scan"
+    b = idx.search(q, 100)
+    assert torch.equal(a.ids, b.ids) and torch.equal(a.scores, b.scores)   # grid values: both paths are exact
+    Xs = ref_search.torch_csr(crow[:200_001].cpu(), col[:200_000].reshape(-1).cpu(), val[:200_000].reshape(-1).cpu(), (200_000, V))
+    sub = _mk("SparseIndex", crow[:200_001], col[:200_000].reshape(-1), val[:200_000].reshape(-1), (200_000, V))
+    sub.search_mode = "inverted"
+    assert ref_search.compare_results(sub.search(q, 100), ref_search.ref_scores(q, Xs), 100, exact=True) is None
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_inverted_half_precision_values(dtype, cuda_device):
     n, m = 30_000, 64

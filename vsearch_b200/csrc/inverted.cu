@@ -276,6 +276,32 @@ __device__ __forceinline__ float posting_value(const void *vals, int kind, uint6
     return __bfloat162float(((const __nv_bfloat16 *)vals)[pos]);
 }
 
+// Add w * value at every posting of one list slice: lanes stride the slice, kInvUnroll loads in flight per lane.
+constexpr int kInvUnroll = 8;
+constexpr uint32_t kLongList = 1024;   // postings; longer (block, token) lists are shared by all warps of the CTA
+
+__device__ __forceinline__ void accumulate_slice(float *acc, const uint16_t *rows, const void *vals, int val_kind,
+                                                 uint64_t pos0, uint32_t begin, uint32_t end, uint32_t stride, float w) {
+    // offsets begin + lane, begin + lane + stride, ... < end
+    for (uint32_t off = begin; off < end; off += stride * kInvUnroll) {
+        uint32_t row[kInvUnroll];
+        float v[kInvUnroll];
+#pragma unroll
+        for (int u = 0; u < kInvUnroll; ++u) {
+            const uint32_t o = off + (uint32_t)u * stride;
+            row[u] = 0xffffffffu;
+            v[u] = w;
+            if (o < end) {
+                row[u] = rows[pos0 + o];
+                if (val_kind) v[u] *= posting_value(vals, val_kind, pos0 + o);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kInvUnroll; ++u)
+            if (row[u] != 0xffffffffu) atomicAdd(&acc[row[u]], v[u]);
+    }
+}
+
 __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSearchParams p) {
     constexpr int NT = kInvThreads, NW = kInvWarps;
     extern __shared__ __align__(128) uint8_t ssmem[];
@@ -285,12 +311,9 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     float *s_w = reinterpret_cast<float *>(s_tok + kTokTile);
     uint32_t *s_beg = reinterpret_cast<uint32_t *>(s_w + kTokTile);
     uint32_t *s_len = s_beg + kTokTile;
-    uint32_t *s_spref = s_len + kTokTile;                                      // kTokTile + 4
-    uint32_t *s_warp = s_spref + kTokTile + 4;                                 // 32
-    float *acc = reinterpret_cast<float *>(s_warp + 32);                       // rows_per_block
+    float *acc = reinterpret_cast<float *>(s_len + kTokTile);                  // rows_per_block
     __shared__ CtaState st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt = lanemask_lt();
     const int q = blockIdx.y;
     const int cnt = (int)min(p.L.cnt[q], (uint32_t)kMaxQueryNnz);
     const uint32_t *tok = p.L.tok + (size_t)q * kMaxQueryNnz;
@@ -306,9 +329,9 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
         const uint32_t *bp = p.blk_ptr + (size_t)blk0 * (p.V + 1) + s_tok[tid];
         np0 = bp[0]; np1 = bp[1];
     }
-    int n_priv = 0;
     bool sampled = false;
     float4 *acc4 = reinterpret_cast<float4 *>(acc);
+    uint64_t *app = cbuf + kSharedKeys;    // CTA-wide append region of the top-k machinery (topk.cuh)
 
     for (int b = blk0; b < blk1; ++b) {
         const int64_t row0 = (int64_t)b * R;
@@ -328,45 +351,22 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                     p0 = bp[0]; p1 = bp[1];
                 }
             }
-            const uint32_t len = tid < tn ? p1 - p0 : 0u;
-            uint32_t n_strips;
-            const uint32_t ex = block_exclusive_scan<NT>((len + 31u) >> 5, s_warp, n_strips);  // strips of 32 postings
-            if (tid < tn) { s_beg[tid] = p0; s_len[tid] = len; s_spref[tid] = ex; }
-            if (tid == tn) s_spref[tn] = n_strips;
-            __syncthreads();
-            // warp `warp` takes a contiguous range of strips, four at a time
-            const uint32_t s_lo = (uint32_t)(((uint64_t)n_strips * warp) / NW);
-            const uint32_t s_hi = (uint32_t)(((uint64_t)n_strips * (warp + 1)) / NW);
-            if (s_lo < s_hi) {
-                int lo = 0, hi = tn;  // largest ti with s_spref[ti] <= s_lo
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (s_spref[mid] <= s_lo) lo = mid; else hi = mid;
-                }
-                int ti = lo;
-                for (uint32_t s = s_lo; s < s_hi; s += 4) {
-                    uint32_t row[4];
-                    float v[4];
-                    bool ok[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t su = s + u;
-                        ok[u] = false; row[u] = 0; v[u] = 0.f;
-                        if (su < s_hi) {
-                            while (su >= s_spref[ti + 1]) ++ti;
-                            const uint32_t off = (su - s_spref[ti]) * 32u + lane;
-                            if (off < s_len[ti]) {
-                                const uint64_t pos = base + s_beg[ti] + off;
-                                ok[u] = true;
-                                row[u] = p.post_row[pos];
-                                v[u] = s_w[ti];
-                                if (p.val_kind) v[u] *= posting_value(p.post_val, p.val_kind, pos);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (ok[u]) atomicAdd(&acc[row[u]], v[u]);
+            if (tid < tn) { s_beg[tid] = p0; s_len[tid] = p1 - p0; }
+            __syncthreads();  // also orders the zeroing above before the first atomic
+            // short lists: one warp per token, round robin
+            for (int ti = warp; ti < tn; ti += NW) {
+                const uint32_t len = s_len[ti];
+                if (len - 1u < kLongList)
+                    accumulate_slice(acc, p.post_row, p.post_val, p.val_kind, base + s_beg[ti], lane, len, 32u, s_w[ti]);
+            }
+            // long lists (heavy-tailed token popularity): every warp takes a share
+            for (int tb = 0; tb < tn; tb += 32) {
+                const int ti_l = tb + lane;
+                uint32_t longm = __ballot_sync(0xffffffffu, ti_l < tn && s_len[ti_l] > kLongList);
+                for (; longm; longm &= longm - 1) {
+                    const int ti = tb + __ffs(longm) - 1;
+                    accumulate_slice(acc, p.post_row, p.post_val, p.val_kind, base + s_beg[ti], (uint32_t)tid, s_len[ti],
+                                     (uint32_t)NT, s_w[ti]);
                 }
             }
         }
@@ -387,35 +387,57 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                     cbuf[r + e] = (r + e < rows_b) ? make_key(round_score(s[e], p.score_round), (uint32_t)(row0 + r + e)) : 0ull;
             }
             __syncthreads();
-            cta_sample_select<NT>(cbuf, kCapMax, p.k, hist, &st);
+            cta_sample_select<NT, true>(cbuf, kCapMax, p.k, hist, &st, max(2 * p.k, 512) < kSharedKeys ? max(2 * p.k, 512) : kSharedKeys);
             sampled = true;
             i0 = kCapMax;
         }
-        // phase B: CTA-uniform steps of NT*4 rows; a join when some warp's private region could overflow next step
-        for (int rb = i0; rb < rows_b; rb += NT * 4) {
-            const int r = rb + tid * 4;
-            const bool in = r < rows_b;
-            const float4 v = in ? acc4[r >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float s[4] = {round_score(v.x, p.score_round), round_score(v.y, p.score_round),
-                                round_score(v.z, p.score_round), round_score(v.w, p.score_round)};
-            const float tau_s = gate_tau_score(gate_load(&st));
-            const float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
-            if (__any_sync(0xffffffffu, in && mx >= tau_s)) {
-                const uint64_t tau = *(volatile uint64_t *)&st.tau;
+        // phase B.  Optimistic: the whole block in one go, survivors appended through a CTA-wide counter; when the
+        // append region overflows (adversarial score order) the block is replayed in steps of NT*4 rows with a
+        // re-selection whenever the next step might not fit.
+        const uint32_t app0 = *(volatile uint32_t *)&st.n_app;
+        bool stepwise = false;
+        for (;;) {
+            const float tau_s0 = gate_tau_score(gate_load(&st));
+            float tau_s = tau_s0;
+            uint64_t tau = *(volatile uint64_t *)&st.tau;
+            for (int rb = i0; rb < rows_b; rb += NT * 4) {
+                if (stepwise) {
+                    __syncthreads();
+                    if (*(volatile uint32_t *)&st.n_app + NT * 4 > (uint32_t)kAppendCap) {
+                        cta_join_flat<NT>(cbuf, p.k, hist, &st);
+                        tau_s = gate_tau_score(gate_load(&st));
+                        tau = *(volatile uint64_t *)&st.tau;
+                    }
+                }
+                const int r = rb + tid * 4;
+                if (r < rows_b) {
+                    const float4 v = acc4[r >> 2];
+                    const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+                    if (round_score(mx, p.score_round) >= tau_s) {   // rounding is monotonic
+                        const float s[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint64_t key = make_key(s[e], (uint32_t)(row0 + r + e));
-                    private_insert<NW>(in && r + e < rows_b && key > tau, key, cbuf, n_priv, lt);
+                        for (int e = 0; e < 4; ++e) {
+                            const uint64_t key = make_key(round_score(s[e], p.score_round), (uint32_t)(row0 + r + e));
+                            if (r + e < rows_b && key > tau) {
+                                const uint32_t slot = atomicAdd(&st.n_app, 1u);
+                                if (slot < (uint32_t)kAppendCap) app[slot] = key;
+                            }
+                        }
+                    }
                 }
             }
-            if (__syncthreads_or(n_priv + 128 > TopkGeom<NW>::kPrivate)) {
-                cta_join<NT, NW>(cbuf, n_priv, p.k, hist, &st);
-                n_priv = 0;
-            }
+            __syncthreads();
+            if (stepwise || *(volatile uint32_t *)&st.n_app <= (uint32_t)kAppendCap) break;
+            __syncthreads();
+            if (tid == 0) st.n_app = app0;   // drop this block's partial appends and replay it safely
+            stepwise = true;
+            (void)tau_s0;
         }
+        // keep room for the next block's optimistic pass and a tight threshold
+        if (*(volatile uint32_t *)&st.n_app > (uint32_t)(kAppendCap / 4)) cta_join_flat<NT>(cbuf, p.k, hist, &st);
         __syncthreads();
     }
-    cta_write_topk<NT, NW>(cbuf, n_priv, p.k, hist, &st, p.cand + ((size_t)q * gridDim.x + blockIdx.x) * (size_t)p.k);
+    cta_write_topk_flat<NT>(cbuf, p.k, hist, &st, p.cand + ((size_t)q * gridDim.x + blockIdx.x) * (size_t)p.k);
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -478,7 +500,7 @@ int launch_inverted(vs_index *idx, int64_t Bc, int k, int score_round, int group
     (void)group; (void)max_nnz;
     uint8_t *end;
     QueryLists L = carve_lists((uint8_t *)d_ws, Bc, &end);
-    const size_t smem = (size_t)kCapMax * 8 + 256 * 4 + (size_t)kTokTile * 4 * 5 + 16 + 32 * 4 + (size_t)idx->blk_rows * 4;
+    const size_t smem = (size_t)kCapMax * 8 + 256 * 4 + (size_t)kTokTile * 4 * 4 + (size_t)idx->blk_rows * 4;
     VS_REQUIRE(smem <= 227 * 1024, VS_ERR_UNSUPPORTED, "inverted-list search needs %zu bytes of shared memory", smem);
     VS_CUDA(cudaFuncSetAttribute(inv_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     InvSearchParams p;

@@ -38,7 +38,7 @@ struct CtaState {
     uint32_t cnt;       // keys in the shared set cbuf[0, cnt)
     uint32_t scratch;   // CTA-wide counter of the select routines
     uint32_t done;      // warps that finished streaming this pass
-    uint32_t pad_;
+    uint32_t n_app;     // K3: keys in the CTA-wide append region cbuf[kSharedKeys, kCapMax) (may count past the end)
 };
 static_assert(offsetof(CtaState, gate_tau_score) % 8 == 0, "gate must be 8-byte aligned");
 
@@ -48,6 +48,7 @@ __device__ __forceinline__ void cta_state_reset(CtaState *st) {
     st->gate_tau_score = __float_as_uint(-INFINITY);
     st->gate_epoch = 0;
     st->done = 0;
+    st->n_app = 0;
 }
 __device__ __forceinline__ uint64_t gate_load(const CtaState *st) {
     return *reinterpret_cast<const volatile uint64_t *>(&st->gate_tau_score);
@@ -59,11 +60,15 @@ __device__ __forceinline__ void publish_tau(CtaState *st, uint64_t kth) {
     *(volatile uint64_t *)&st->tau = kth;
 }
 
-// k-th largest over two shared-memory segments (unique keys; zeros allowed as "absent", they rank last).
-// PRE: at least k keys in total.  Same radix select as radix_kth_largest, group = warp or CTA.
-template <bool BLOCK>
+// Threshold of the k largest over two shared-memory segments (unique keys; zeros allowed as "absent", they rank
+// last).  PRE: at least k keys in total.  Same MSD radix select as radix_kth_largest, group = warp or CTA, but it
+// with EARLY it returns as soon as the answer is decided: the result T is then a THRESHOLD (k-th key with its undecided low bits
+// cleared) such that exactly k keys are >= T -- or, with APPROX, at least k and at most max(k, approx_cap) keys
+// (phase A only needs a safe filter, not the exact k-th: 2-3 passes instead of 8).
+template <bool BLOCK, bool EARLY = false, bool APPROX = false>
 __device__ __forceinline__ uint64_t radix_kth_largest2(const uint64_t *a, int na, int ta, int nta, const uint64_t *b,
-                                                       int nb, int tb, int ntb, int k, uint32_t *hist, int t, int nt) {
+                                                       int nb, int tb, int ntb, int k, uint32_t *hist, int t, int nt,
+                                                       int approx_cap = 0) {
     const int lane = threadIdx.x & 31;
     uint64_t prefix = 0, mask = 0;
     int rem = k;
@@ -92,12 +97,15 @@ __device__ __forceinline__ uint64_t radix_kth_largest2(const uint64_t *a, int na
         }
         const uint32_t above = incl - s;
         const bool mine = (above < (uint32_t)rem) && ((uint32_t)rem <= incl);
-        uint32_t digit = 0, newrem = 0;
+        uint32_t digit = 0, newrem = 0, hd = 0;
         if (mine) {
             uint32_t acc = above;
 #pragma unroll
             for (int j = 7; j >= 0; --j) {
-                if (acc < (uint32_t)rem && acc + h[j] >= (uint32_t)rem) { digit = lane * 8 + j; newrem = rem - acc; }
+                if (acc < (uint32_t)rem && acc + h[j] >= (uint32_t)rem) {
+                    digit = lane * 8 + j; newrem = rem - acc;
+                    if constexpr (EARLY) hd = h[j];
+                }
                 acc += h[j];
             }
         }
@@ -105,25 +113,32 @@ __device__ __forceinline__ uint64_t radix_kth_largest2(const uint64_t *a, int na
         const int src = __ffs(owner) - 1;
         digit = __shfl_sync(0xffffffffu, digit, src);
         newrem = __shfl_sync(0xffffffffu, newrem, src);
+        if constexpr (EARLY) hd = __shfl_sync(0xffffffffu, hd, src);
         prefix |= (uint64_t)digit << shift;
         mask |= (uint64_t)0xff << shift;
         rem = (int)newrem;
-        group_sync<BLOCK>();  // hist is rewritten next pass
+        group_sync<BLOCK>();  // hist is rewritten next pass (or by the caller)
+        if constexpr (EARLY) {
+            const uint32_t ge = (uint32_t)k - newrem + hd;  // keys >= prefix (low bits cleared); same value in every thread
+            if (ge == (uint32_t)k) break;                   // the whole bucket is inside the top k: decided
+            if (APPROX && ge <= (uint32_t)approx_cap) break;
+        }
     }
     return prefix;
 }
 
 // ---- phase A -> B: called by the whole CTA after a __syncthreads(); cbuf[0, n) holds the sample (zeros = unused
 // slots).  Keeps the k largest in cbuf[0, cnt), publishes tau.
-template <int NT>
-__device__ __forceinline__ void cta_sample_select(uint64_t *cbuf, int n, int k, uint32_t *hist, CtaState *st) {
+template <int NT, bool APPROX = false>
+__device__ __forceinline__ void cta_sample_select(uint64_t *cbuf, int n, int k, uint32_t *hist, CtaState *st,
+                                                  int approx_cap = 0) {
     const int tid = threadIdx.x;
     constexpr int PER = (kCapMax + NT - 1) / NT;
     uint64_t mine[PER];
 #pragma unroll
     for (int j = 0; j < PER; ++j) { const int i = tid + j * NT; mine[j] = (i < n) ? cbuf[i] : 0ull; }
     // zeros rank last, so the k-th largest is exact whenever the sample holds >= k real keys (n >= k by layout)
-    const uint64_t kth = radix_kth_largest2<true>(cbuf, n, tid, NT, cbuf, 0, 0, 1, k, hist, tid, NT);
+    const uint64_t kth = radix_kth_largest2<true, APPROX, APPROX>(cbuf, n, tid, NT, cbuf, 0, 0, 1, k, hist, tid, NT, approx_cap);
     if (tid == 0) st->cnt = 0;
     __syncthreads();
 #pragma unroll
@@ -240,6 +255,65 @@ __device__ __forceinline__ void cta_write_topk(uint64_t *cbuf, int n_priv, int k
     for (int i = lane; i < n_priv; i += 32) {
         const uint64_t x = priv[i];
         if (x >= kth) out[atomicAdd(&st->scratch, 1u)] = x;
+    }
+    __syncthreads();
+    for (int i = (int)st->scratch + tid; i < k; i += NT) out[i] = 0ull;  // fewer than k candidates in this CTA
+}
+
+// ---- K3 (inverted.cu): one CTA-WIDE append region cbuf[kSharedKeys, kCapMax) filled through st->n_app by any thread
+// (the CTA runs in lockstep phases there, so no per-warp regions and no polling are needed).
+constexpr int kAppendCap = kCapMax - kSharedKeys;
+
+// Fold the append region into the shared set, keep the k best, raise tau, empty the region.  Whole CTA.
+template <int NT>
+__device__ __noinline__ void cta_join_flat(uint64_t *cbuf, int k, uint32_t *hist, CtaState *st) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    const int n_sh = (int)st->cnt;
+    const int n_app = min((int)st->n_app, kAppendCap);
+    uint64_t *app = cbuf + kSharedKeys;
+    uint64_t kth = 0;
+    if (n_sh + n_app > k) kth = radix_kth_largest2<true, true>(cbuf, n_sh, tid, NT, app, n_app, tid, NT, k, hist, tid, NT);
+    constexpr int SH_PER = (kSharedKeys + NT - 1) / NT;
+    constexpr int AP_PER = (kAppendCap + NT - 1) / NT;
+    uint64_t keep_sh[SH_PER], keep_ap[AP_PER];
+#pragma unroll
+    for (int j = 0; j < SH_PER; ++j) { const int i = tid + j * NT; keep_sh[j] = (i < n_sh) ? cbuf[i] : 0ull; }
+#pragma unroll
+    for (int j = 0; j < AP_PER; ++j) { const int i = tid + j * NT; keep_ap[j] = (i < n_app) ? app[i] : 0ull; }
+    __syncthreads();
+    if (tid == 0) { st->cnt = 0; st->n_app = 0; }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SH_PER; ++j)
+        if (keep_sh[j] != 0ull && keep_sh[j] >= kth) cbuf[atomicAdd(&st->cnt, 1u)] = keep_sh[j];
+#pragma unroll
+    for (int j = 0; j < AP_PER; ++j)
+        if (keep_ap[j] != 0ull && keep_ap[j] >= kth) cbuf[atomicAdd(&st->cnt, 1u)] = keep_ap[j];
+    if (tid == 0 && kth) publish_tau(st, kth);
+    __syncthreads();
+}
+
+// End of pass: exact top-k of the shared set plus the append region -> out[0..k) (unsorted, zero padded).  Whole CTA.
+template <int NT>
+__device__ __forceinline__ void cta_write_topk_flat(uint64_t *cbuf, int k, uint32_t *hist, CtaState *st, uint64_t *out) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    const int n_sh = (int)st->cnt;
+    const int n_app = min((int)st->n_app, kAppendCap);
+    const uint64_t *app = cbuf + kSharedKeys;
+    uint64_t kth = 0;
+    if (n_sh + n_app > k) kth = radix_kth_largest2<true, true>(cbuf, n_sh, tid, NT, app, n_app, tid, NT, k, hist, tid, NT);
+    __syncthreads();
+    if (tid == 0) st->scratch = 0;
+    __syncthreads();
+    for (int i = tid; i < n_sh; i += NT) {
+        const uint64_t x = cbuf[i];
+        if (x != 0ull && x >= kth) out[atomicAdd(&st->scratch, 1u)] = x;
+    }
+    for (int i = tid; i < n_app; i += NT) {
+        const uint64_t x = app[i];
+        if (x != 0ull && x >= kth) out[atomicAdd(&st->scratch, 1u)] = x;
     }
     __syncthreads();
     for (int i = (int)st->scratch + tid; i < k; i += NT) out[i] = 0ull;  // fewer than k candidates in this CTA
