@@ -88,9 +88,11 @@ static Workspace carve(const vs_index *idx, void *base, int64_t Bc, int k) {
 }
 constexpr int64_t kQueryChunk = 1024;
 // auto-mode cost model; refined from measurements (profiles/)
-constexpr double kScanBytesPerSec = 4.0e12;
-constexpr double kInvPostingsPerSec = 1.5e11;
-constexpr double kInvSelectBytesPerSec = 5.0e12;
+constexpr double kScanBytesPerSecPair = 4.5e12;   // binary / 16-bit values (L1 data-pipe bound)
+constexpr double kScanBytesPerSecF32 = 6.2e12;    // fp32 values (HBM bound)
+constexpr double kInvPostingsPerSec = 3.5e11;     // shared-memory atomics, all SMs
+constexpr double kInvSecPerRow = 1.8e-12;         // zero + select of the block accumulators
+constexpr double kInvFixedSec = 5.0e-6;
 
 }  // namespace vs
 
@@ -282,8 +284,9 @@ static int search_impl(const vs_index *cidx, const void *hd_q, int q_dtype, int6
                 use_inv = true;
             } else {
                 // cost model (seconds per query), constants measured on B200
-                const double t_scan = (double)idx->stream_bytes / kScanBytesPerSec;
-                const double t_inv = mean_post / kInvPostingsPerSec + 8.0 * (double)idx->n_rows / kInvSelectBytesPerSec;
+                const bool f32 = idx->kind == 1 && idx->store_dtype == VS_F32;
+                const double t_scan = (double)idx->stream_bytes / (f32 ? kScanBytesPerSecF32 : kScanBytesPerSecPair);
+                const double t_inv = mean_post / kInvPostingsPerSec + (double)idx->n_rows * kInvSecPerRow + kInvFixedSec;
                 use_inv = usable && t_inv < t_scan;
             }
         }

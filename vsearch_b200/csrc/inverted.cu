@@ -268,6 +268,7 @@ struct InvSearchParams {
     int64_t n_rows;
     uint64_t *cand;      // [B, gridDim.x, k]
     int k, score_round;
+    int flags;           // experiment switches (VSEARCH_B200_K3_FLAGS): 1 = re-select after the first block, 2 = L2 prefetch
 };
 
 __device__ __forceinline__ float posting_value(const void *vals, int kind, uint64_t pos) {
@@ -276,13 +277,22 @@ __device__ __forceinline__ float posting_value(const void *vals, int kind, uint6
     return __bfloat162float(((const __nv_bfloat16 *)vals)[pos]);
 }
 
-// Add w * value at every posting of one list slice: lanes stride the slice, kInvUnroll loads in flight per lane.
-constexpr int kInvUnroll = 8;
+constexpr int kInvUnroll = 8;          // posting loads in flight per lane
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t atom_shared_add(uint32_t *p, uint32_t v) {  // plain ATOMS.ADD (no compiler-made warp aggregation)
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
+}
+
 constexpr uint32_t kLongList = 1024;   // postings; longer (block, token) lists are shared by all warps of the CTA
 
+// Add w * value at every posting of one list slice: offsets begin, begin + stride, ... < end; kInvUnroll loads in
+// flight per lane.  All lanes of a warp work on the SAME list, so their rows are distinct (no intra-warp conflicts)
+// and the token's weight / list start are warp-uniform registers.
 __device__ __forceinline__ void accumulate_slice(float *acc, const uint16_t *rows, const void *vals, int val_kind,
                                                  uint64_t pos0, uint32_t begin, uint32_t end, uint32_t stride, float w) {
-    // offsets begin + lane, begin + lane + stride, ... < end
     for (uint32_t off = begin; off < end; off += stride * kInvUnroll) {
         uint32_t row[kInvUnroll];
         float v[kInvUnroll];
@@ -321,10 +331,14 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     const int R = p.rows_per_block;
     const int blk0 = blockIdx.x * p.blocks_per_cta, blk1 = min(p.n_blocks, blk0 + p.blocks_per_cta);
     const bool cached = cnt <= kTokTile;   // the whole token list stays in shared memory across blocks
+    const int vbytes = p.val_kind == 0 ? 0 : (p.val_kind == 1 ? 4 : 2);
     if (tid == 0) cta_state_reset(&st);
     if (cached && tid < cnt) { s_tok[tid] = tok[tid]; s_w[tid] = w[tid]; }
     __syncthreads();
-    uint32_t np0 = 0, np1 = 0;             // next block's list bounds of token `tid` (prefetched under the select)
+    // list bounds of token `tid` in the NEXT block to score: loaded one block ahead, and the lists themselves are
+    // pulled into L2 while the previous block is being selected
+    uint32_t np0 = 0, np1 = 0;
+    uint64_t nbase = 0;
     if (cached && blk0 < blk1 && tid < cnt) {
         const uint32_t *bp = p.blk_ptr + (size_t)blk0 * (p.V + 1) + s_tok[tid];
         np0 = bp[0]; np1 = bp[1];
@@ -350,14 +364,24 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                     const uint32_t *bp = p.blk_ptr + (size_t)b * (p.V + 1) + t;
                     p0 = bp[0]; p1 = bp[1];
                 }
+            } else if (b + 1 < blk1 && tid < cnt) {  // in flight under this block's accumulate
+                const uint32_t *bp = p.blk_ptr + (size_t)(b + 1) * (p.V + 1) + s_tok[tid];
+                np0 = bp[0]; np1 = bp[1];
+                nbase = p.blk_base[b + 1];
             }
             if (tid < tn) { s_beg[tid] = p0; s_len[tid] = p1 - p0; }
             __syncthreads();  // also orders the zeroing above before the first atomic
-            // short lists: one warp per token, round robin
-            for (int ti = warp; ti < tn; ti += NW) {
+            // short lists: one warp per list piece, round robin; few tokens -> lists are cut in 2 or 4 pieces so that
+            // every warp gets about the same number of postings
+            const int psh = tn >= 2 * NW ? 0 : (tn >= NW ? 1 : 2);   // 1, 2 or 4 pieces per list
+            for (int it = warp; it < (tn << psh); it += NW) {
+                const int ti = it >> psh;
+                const uint32_t pc = (uint32_t)(it & ((1 << psh) - 1));
                 const uint32_t len = s_len[ti];
-                if (len - 1u < kLongList)
-                    accumulate_slice(acc, p.post_row, p.post_val, p.val_kind, base + s_beg[ti], lane, len, 32u, s_w[ti]);
+                if (len - 1u < kLongList) {
+                    const uint32_t lo = (len * pc) >> psh, hi = (len * (pc + 1u)) >> psh;
+                    accumulate_slice(acc, p.post_row, p.post_val, p.val_kind, base + s_beg[ti], lo + lane, hi, 32u, s_w[ti]);
+                }
             }
             // long lists (heavy-tailed token popularity): every warp takes a share
             for (int tb = 0; tb < tn; tb += 32) {
@@ -371,9 +395,15 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
             }
         }
         __syncthreads();
-        if (cached && b + 1 < blk1 && tid < cnt) {
-            const uint32_t *bp = p.blk_ptr + (size_t)(b + 1) * (p.V + 1) + s_tok[tid];
-            np0 = bp[0]; np1 = bp[1];
+        if ((p.flags & 2) && cached && b + 1 < blk1 && tid < cnt) {  // next block's lists -> L2 while this block is selected
+            const uint64_t npos = nbase + np0;
+            const uint32_t nlen = min(np1 - np0, 2048u);
+            const uint8_t *r8 = reinterpret_cast<const uint8_t *>(p.post_row + npos);
+            for (uint32_t o = 0; o < nlen * 2u; o += 128u) prefetch_l2(r8 + o);
+            if (vbytes) {
+                const uint8_t *v8 = reinterpret_cast<const uint8_t *>(p.post_val) + npos * vbytes;
+                for (uint32_t o = 0; o < nlen * (uint32_t)vbytes; o += 128u) prefetch_l2(v8 + o);
+            }
         }
         // ---- select: the block's scores go through the fused top-k
         int i0 = 0;
@@ -388,7 +418,6 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
             }
             __syncthreads();
             cta_sample_select<NT, true>(cbuf, kCapMax, p.k, hist, &st, max(2 * p.k, 512) < kSharedKeys ? max(2 * p.k, 512) : kSharedKeys);
-            sampled = true;
             i0 = kCapMax;
         }
         // phase B.  Optimistic: the whole block in one go, survivors appended through a CTA-wide counter; when the
@@ -397,13 +426,12 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
         const uint32_t app0 = *(volatile uint32_t *)&st.n_app;
         bool stepwise = false;
         for (;;) {
-            const float tau_s0 = gate_tau_score(gate_load(&st));
-            float tau_s = tau_s0;
+            float tau_s = gate_tau_score(gate_load(&st));
             uint64_t tau = *(volatile uint64_t *)&st.tau;
             for (int rb = i0; rb < rows_b; rb += NT * 4) {
                 if (stepwise) {
-                    __syncthreads();
-                    if (*(volatile uint32_t *)&st.n_app + NT * 4 > (uint32_t)kAppendCap) {
+                    // the thread that appended last reads the final count, so the OR is exact
+                    if (__syncthreads_or(*(volatile uint32_t *)&st.n_app + NT * 4 > (uint32_t)kAppendCap)) {
                         cta_join_flat<NT>(cbuf, p.k, hist, &st);
                         tau_s = gate_tau_score(gate_load(&st));
                         tau = *(volatile uint64_t *)&st.tau;
@@ -415,13 +443,22 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                     const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
                     if (round_score(mx, p.score_round) >= tau_s) {   // rounding is monotonic
                         const float s[4] = {v.x, v.y, v.z, v.w};
+                        uint64_t key[4];
+                        uint32_t n = 0;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const uint64_t key = make_key(round_score(s[e], p.score_round), (uint32_t)(row0 + r + e));
-                            if (r + e < rows_b && key > tau) {
-                                const uint32_t slot = atomicAdd(&st.n_app, 1u);
-                                if (slot < (uint32_t)kAppendCap) app[slot] = key;
+                            const float se = round_score(s[e], p.score_round);
+                            key[e] = 0ull;
+                            if (r + e < rows_b && se >= tau_s) {
+                                const uint64_t ke = make_key(se, (uint32_t)(row0 + r + e));
+                                if (ke > tau) { key[e] = ke; ++n; }
                             }
+                        }
+                        if (n) {
+                            uint32_t slot = atom_shared_add(&st.n_app, n);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (key[e] != 0ull) { if (slot < (uint32_t)kAppendCap) app[slot] = key[e]; ++slot; }
                         }
                     }
                 }
@@ -431,10 +468,13 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
             __syncthreads();
             if (tid == 0) st.n_app = app0;   // drop this block's partial appends and replay it safely
             stepwise = true;
-            (void)tau_s0;
+            __syncthreads();
         }
-        // keep room for the next block's optimistic pass and a tight threshold
-        if (*(volatile uint32_t *)&st.n_app > (uint32_t)(kAppendCap / 4)) cta_join_flat<NT>(cbuf, p.k, hist, &st);
+        // tighten the threshold after the CTA's first block (the sample saw kCapMax rows, the block has R), and keep
+        // room for the next block's optimistic pass
+        if (b + 1 < blk1 && ((!sampled && (p.flags & 1)) || *(volatile uint32_t *)&st.n_app > (uint32_t)(kAppendCap / 4)))
+            cta_join_flat<NT>(cbuf, p.k, hist, &st);
+        sampled = true;
         __syncthreads();
     }
     cta_write_topk_flat<NT>(cbuf, p.k, hist, &st, p.cand + ((size_t)q * gridDim.x + blockIdx.x) * (size_t)p.k);
@@ -508,6 +548,8 @@ int launch_inverted(vs_index *idx, int64_t Bc, int k, int score_round, int group
     p.val_kind = idx->kind == 1 ? (idx->store_dtype == VS_F32 ? 1 : (idx->store_dtype == VS_F16 ? 2 : 3)) : 0;
     p.V = (int)idx->n_cols; p.rows_per_block = idx->blk_rows; p.n_blocks = idx->n_blocks; p.blocks_per_cta = idx->blocks_per_cta;
     p.n_rows = idx->n_rows; p.cand = d_cand; p.k = k; p.score_round = score_round;
+    const char *fl = getenv("VSEARCH_B200_K3_FLAGS");
+    p.flags = fl ? atoi(fl) : 3;
     if (ev0) VS_CUDA(cudaEventRecord(ev0, st));
     inv_search_kernel<<<dim3(idx->n_ctas, (unsigned)Bc), kInvThreads, smem, st>>>(p);
     if (ev1) VS_CUDA(cudaEventRecord(ev1, st));
