@@ -262,10 +262,10 @@ def run_gpu(args):
         used = index.last_mode()
         if used == "scan":   # nnz * b_col + (N+1) * b_ptr, binary: b_val = 0; one pass per query (Q_tile = 1)
             bytes_pass = n_loc * TOKENS * 2 + (n_loc + 1) * 4
-            kernel, launches = "vs::scan_topk_kernel<0,4,false,false>", steps * (3 if world == 1 else 4)
-        else:                # K3: postings of the query's tokens (uint32 ids) + accumulator clear and read-back
-            bytes_pass = int(args.qnnz * (n_loc * TOKENS / V)) * 4 + 2 * n_loc * 4
-            kernel, launches = "vs::inv_accum_kernel + vs::inv_select_kernel", steps * ((4 + 2 * B) if world == 1 else (5 + 2 * B))
+            kernel, launches = "vs::scan_topk_kernel<0, 3, 1, 0, 0>", steps * (3 if world == 1 else 4)
+        else:                # K3: postings of the query's tokens (uint16 block-local row ids; binary: no values)
+            bytes_pass = int(args.qnnz * (n_loc * TOKENS / V)) * 2
+            kernel, launches = "vs::inv_search_kernel", steps * (4 if world == 1 else 5)
         achieved = B * bytes_pass / (kern_ms / max(kern_n, 1) * 1e-3) / 1e9 if kern_ms > 0 else None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None,

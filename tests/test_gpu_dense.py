@@ -47,6 +47,8 @@ def test_golden_dense(name, cuda_device):
     (40_000, 128, 33, 1000, torch.float16),   # k = 1000, fp16 storage, D = 128
     (300, 96, 3, 300, torch.bfloat16),        # k == N, D not a multiple of 64
     (1_200_000, 64, 5, 100, torch.bfloat16),  # all three sweeps: sample, 64x sample with tau1, the rest with tau2
+    (300_000, 64, 700, 100, torch.bfloat16),  # CTA-pair kernel (cta_group::2): 3 pair tiles of 256 queries, last one ragged
+    (70_000, 192, 300, 10, torch.float16),    # CTA-pair kernel, odd number of 128-query tiles, 3 k-blocks
 ])
 def test_dense_grid_exact(n, d, B, k, dtype, cuda_device):
     x, q = _grid((n, d), 1), _grid((B, d), 2)

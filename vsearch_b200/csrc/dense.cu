@@ -23,6 +23,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
+
 #include <vector>
 
 #include "index.cuh"
@@ -47,6 +49,7 @@ struct DenseArgs {
     const uint64_t *tau;   // [n_queries] threshold keys (mode 1)
     uint64_t *cand; uint32_t *cand_cnt; int64_t cand_cap;  // [n_queries, cand_cap], [n_queries]
     unsigned long long *work_counter;   // dynamic tile scheduler (zeroed before every launch)
+    int dbg;               // timing experiments only (VSEARCH_B200_DENSE_DBG): 1 skip epilogue, 2 skip MMA, 4 skip TMA
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -97,6 +100,117 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// tcgen05.ld without the wait (the registers must not be read before tc_wait_ld + reg_fence32)
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// ties every later use of r[] to a point after the preceding tc_wait_ld (volatile asms keep their order)
+__device__ __forceinline__ void reg_fence32(uint32_t (&r)[32]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
+    asm volatile("" : "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+    asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]));
+    asm volatile("" : "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
+
+// A tcgen05.ld queues behind every tcgen05.mma already issued on the SM (the MMA warp keeps the ring of k-blocks full:
+// ~1 us of queued tensor work), so the epilogue's cost is the NUMBER of ld -> wait round trips, not the bytes: a serial
+// ld/wait per 32 columns made the epilogue (16 us per tile), not TMA + MMA (6 us), the bottleneck (measured with the
+// epilogue switched off, profiles/README.md).  The filtered sweep therefore pulls 128 columns per wait.
+//
+// The rare 32-column chunk in which some lane of the warp has a candidate (~10 % of the chunks at k = 100) is handled
+// OUT OF LINE and warp-collectively: one more tcgen05.ld of that chunk, count, ONE global atomic per lane with
+// candidates, write.  (Inlined into every batch the epilogue was 6 K instructions and the warps sat in instruction-cache
+// misses; a local-memory copy of the scores is worse still: a CTA that owns 214 KB of shared memory has no L1 left.)
+__device__ __noinline__ void filter32_slow(const uint32_t taddr, const int64_t nb, const int64_t n_rows, const int score_round,
+                                           const float tau_s, const uint64_t tau, uint32_t *cnt_q, uint64_t *dst,
+                                           const uint32_t cap) {
+    uint32_t r[32];
+    tc_ld32(taddr, r);
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float sj = round_score(__uint_as_float(r[j]), score_round);
+        if (sj >= tau_s && nb + j < n_rows && make_key(sj, (uint32_t)(nb + j)) >= tau) m |= 1u << j;
+    }
+    if (m == 0) return;
+    uint32_t pos = atomicAdd(cnt_q, (uint32_t)__popc(m));
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+        if ((m >> j) & 1u) {
+            if (pos < cap) dst[pos] = make_key(round_score(__uint_as_float(r[j]), score_round), (uint32_t)(nb + j));
+            ++pos;
+        }
+}
+
+__device__ __forceinline__ float max32(const uint32_t (&x)[32]) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(x[j]));
+    return mx;
+}
+
+// ---- epilogue of one accumulator tile: thread = query row `q`, columns = passages n0 .. n0 + kBN ----------------
+__device__ __forceinline__ void epilogue_tile(const DenseArgs &a, const uint32_t taddr, const int64_t q, const int64_t n0,
+                                              const float *s_tau) {
+    const bool q_ok = q < a.n_queries;
+    if (a.mode == 0) {
+        // ---- sample sweep: every score of the tile becomes a rank key
+#pragma unroll 1
+        for (int c = 0; c < kBN / 32; ++c) {
+            uint32_t r[32];
+            tc_ld32(taddr + c * 32, r);
+            const int64_t nb = n0 + c * 32;
+            if (q_ok) {
+                uint64_t *dst = a.sample_keys + q * a.sample_ld + (nb - a.row_offset);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int64_t n = nb + j;
+                    const float s = round_score(__uint_as_float(r[j]), a.score_round);
+                    dst[j] = (n < a.n_rows) ? make_key(s, (uint32_t)n) : 0ull;
+                }
+            }
+        }
+    } else {
+        // ---- filtered sweep: 128 accumulator columns per tcgen05.ld round trip; per 32-column chunk a float pre-filter
+        // against the threshold score staged in shared memory, the rare chunk with a candidate goes out of line.
+        const float tau_s = q_ok ? s_tau[q] : INFINITY;
+        const uint64_t tau = q_ok ? a.tau[q] : ~0ull;
+        uint64_t *dst = a.cand + q * a.cand_cap;
+        uint32_t *cnt_q = a.cand_cnt + q;
+        const bool rnd = a.score_round != VS_F32;
+        uint32_t ra[32], rb[32], rc[32], rd[32];
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {   // two batches of 128 columns
+            const uint32_t th = taddr + h * 128;
+            tc_ld32_issue(th, ra); tc_ld32_issue(th + 32, rb); tc_ld32_issue(th + 64, rc); tc_ld32_issue(th + 96, rd);
+            tc_wait_ld(); reg_fence32(ra); reg_fence32(rb); reg_fence32(rc); reg_fence32(rd);
+            float m0 = max32(ra), m1 = max32(rb), m2 = max32(rc), m3 = max32(rd);
+            if (rnd) {
+                m0 = round_score(m0, a.score_round); m1 = round_score(m1, a.score_round);
+                m2 = round_score(m2, a.score_round); m3 = round_score(m3, a.score_round);
+            }
+            const uint32_t hot = __reduce_or_sync(0xffffffffu, (m0 >= tau_s ? 1u : 0u) | (m1 >= tau_s ? 2u : 0u) |
+                                                                   (m2 >= tau_s ? 4u : 0u) | (m3 >= tau_s ? 8u : 0u));
+#pragma unroll 1
+            for (uint32_t hm = hot; hm; hm &= hm - 1) {
+                const int c = __ffs(hm) - 1;
+                filter32_slow(th + c * 32, n0 + h * 128 + c * 32, a.n_rows, a.score_round, tau_s, tau, cnt_q, dst,
+                              (uint32_t)a.cand_cap);
+            }
+        }
+        static_assert(kBN == 256, "the epilogue walks 2 batches of 128 columns");
+    }
 }
 
 __global__ void __launch_bounds__(kDenseThreads, 1)
@@ -222,74 +336,9 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 mbar_wait_u32(bar_tfull + acc * 8, acc_phase);
                 tc_fence_after();
                 const int64_t q = (int64_t)mt * kBM + quarter * 32 + lane;   // this thread's query row
-                const bool q_ok = q < a.n_queries;
                 const int64_t n0 = a.row_offset + (int64_t)nt * kBN;         // first passage of the tile
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kBN;
-                if (a.mode == 0) {
-                    // ---- sample sweep: every score of the tile becomes a rank key
-#pragma unroll 1
-                    for (int c = 0; c < kBN / 32; ++c) {
-                        uint32_t r[32];
-                        tc_ld32(taddr + c * 32, r);
-                        const int64_t nb = n0 + c * 32;
-                        if (q_ok) {
-                            uint64_t *dst = a.sample_keys + q * a.sample_ld + (nb - a.row_offset);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const int64_t n = nb + j;
-                                const float s = round_score(__uint_as_float(r[j]), a.score_round);
-                                dst[j] = (n < a.n_rows) ? make_key(s, (uint32_t)n) : 0ull;
-                            }
-                        }
-                    }
-                } else {
-                    // ---- filtered sweep.  Pass 1 over the accumulator counts this query's survivors (float
-                    // pre-filter against the threshold score staged in shared memory, exact key test for the few that
-                    // pass); ONE global atomic reserves their slots; pass 2 (only for warps that have any) re-reads
-                    // the accumulator from TMEM and writes the keys.
-                    const float tau_s = q_ok ? s_tau[q] : INFINITY;
-                    uint64_t tau = 0;
-                    uint32_t n_surv = 0;
-#pragma unroll 1
-                    for (int c = 0; c < kBN / 32; ++c) {
-                        uint32_t r[32];
-                        tc_ld32(taddr + c * 32, r);
-                        float mx = -INFINITY;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-                        if (a.score_round != VS_F32) mx = round_score(mx, a.score_round);
-                        if (mx >= tau_s) {
-                            if (tau == 0) tau = a.tau[q];
-                            const int64_t nb = n0 + c * 32;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float s = round_score(__uint_as_float(r[j]), a.score_round);
-                                n_surv += (s >= tau_s && nb + j < a.n_rows && make_key(s, (uint32_t)(nb + j)) >= tau) ? 1u : 0u;
-                            }
-                        }
-                    }
-                    if (__any_sync(0xffffffffu, n_surv != 0)) {
-                        uint32_t pos = 0;
-                        if (n_surv) pos = atomicAdd(a.cand_cnt + q, n_surv);
-                        uint64_t *dst = a.cand + q * a.cand_cap;
-#pragma unroll 1
-                        for (int c = 0; c < kBN / 32; ++c) {
-                            uint32_t r[32];
-                            tc_ld32(taddr + c * 32, r);
-                            if (n_surv) {
-                                const int64_t nb = n0 + c * 32;
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    const float s = round_score(__uint_as_float(r[j]), a.score_round);
-                                    if (s >= tau_s && nb + j < a.n_rows) {
-                                        const uint64_t key = make_key(s, (uint32_t)(nb + j));
-                                        if (key >= tau) { if (pos < (uint32_t)a.cand_cap) dst[pos] = key; ++pos; }
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
+                epilogue_tile(a, taddr, q, n0, s_tau);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
@@ -302,6 +351,166 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- CTA-pair variant (cta_group::2): M = 256 queries x N = 256 passages per work item ------------------------
+// Two CTAs of a cluster (one TPC) share one UMMA: each stages ITS 128 queries (A half) and ITS 128 passages (B half)
+// per k-block -- 32 KB instead of 48 KB per CTA per 2 x 128 x 256 x 64 MACs, and a 6-deep ring instead of 4 --
+// the leader's MMA thread issues tcgen05.mma.cta_group::2 (the tensor cores of both SMs read both B halves), each
+// CTA's TMEM gets the accumulator rows of its own 128 queries, and each CTA runs its own epilogue.
+//   full[s]    leader's barrier only: one expect_tx arrival for the 64 KB of BOTH CTAs (the peer's TMA signals it
+//              through the cta_group::2 form with the peer bit of the barrier address cleared)
+//   empty[s], tfull[a]   in both CTAs, signalled by tcgen05.commit ... multicast::cluster (mask 0b11)
+//   tempty[a]  leader's barrier, 8 arrivals: the four epilogue warps of either CTA (remote arrive from the peer)
+// Work items are dealt statically (item = pair + i * n_pairs, query tile fastest): both CTAs of a pair derive the
+// same sequence without talking.  X tiles then come from HBM more than once (the pairs drift apart), which costs
+// < 5 % of the sweep at these arithmetic intensities (measured with the single-CTA kernel, profiles/README.md).
+constexpr int kPairStages = 6;
+constexpr uint32_t kPairStageBytesA = kBM * kBK * 2, kPairStageBytesB = (kBN / 2) * kBK * 2;
+constexpr uint32_t kPairStageBytes = kPairStageBytesA + kPairStageBytesB;   // 32 KB per CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into THIS CTA's shared memory, completion bytes on the LEADER's barrier (same offset, peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on the leader CTA's barrier at this offset
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1)
+dense_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, const DenseArgs a) {
+    extern __shared__ __align__(1024) uint8_t dsmem[];
+    uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)dsmem + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(base);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + kPairStages * kPairStageBytes);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + kPairStages * 8;
+    const uint32_t bar_tfull = bar_empty + kPairStages * 8, bar_tempty = bar_tfull + 2 * 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kPairStages + 4);
+    float *s_tau = reinterpret_cast<float *>(bars + 2 * kPairStages + 6);   // [n_queries <= 4096] threshold scores (mode 1)
+    if (a.mode == 1)
+        for (int64_t i = threadIdx.x; i < a.n_queries; i += kDenseThreads) {
+            const uint64_t t = a.tau[i];
+            s_tau[i] = t ? key_score(t) : -INFINITY;
+        }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_x) : "memory");
+        for (int s = 0; s < kPairStages; ++s) { mbar_init(bars + s, 1); mbar_init(bars + kPairStages + s, 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bars + 2 * kPairStages + i, 1);      // tfull: one multicast commit
+            mbar_init(bars + 2 * kPairStages + 2 + i, 8);  // tempty (leader's is used): epilogue warps of both CTAs
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / peer TMA
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_tiles_m2 = (a.n_tiles_m + 1) / 2;                       // query tiles of 256
+    const long long n_work = (long long)a.n_tiles_n * n_tiles_m2;
+    const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs: own A half, own B half) =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long wk = pair; wk < n_work; wk += n_pairs) {
+                const int nt = (int)(wk / n_tiles_m2), mt2 = (int)(wk % n_tiles_m2);
+                for (int kb = 0; kb < a.k_blocks; ++kb) {
+                    mbar_wait_u32(bar_empty + stage * 8, phase ^ 1u);
+                    if (a.dbg & 4) {
+                        if (leader) mbar_arrive(bar_full + stage * 8);
+                    } else {
+                    if (leader) mbar_expect_tx(bar_full + stage * 8, 2 * kPairStageBytes);
+                    const uint32_t sa = smem_base + stage * kPairStageBytes;
+                    tma_load_2d_pair(sa, &tmap_q, kb * kBK, mt2 * 2 * kBM + (int)rank * kBM, bar_full + stage * 8);
+                    tma_load_2d_pair(sa + kPairStageBytesA, &tmap_x, kb * kBK,
+                                     (int)(a.row_offset) + nt * kBN + (int)rank * (kBN / 2), bar_full + stage * 8);
+                    }
+                    if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (leader && lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (long long wk = pair; wk < n_work; wk += n_pairs) {
+                mbar_wait_u32(bar_tempty + acc * 8, acc_phase ^ 1u);  // both epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)acc * kBN;
+                for (int kb = 0; kb < a.k_blocks; ++kb) {
+                    mbar_wait_u32(bar_full + stage * 8, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * kPairStageBytes;
+                    const uint64_t da = umma_desc(sa), db = umma_desc(sa + kPairStageBytesA);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                        if (!(a.dbg & 2)) tc_mma_f16_pair(d, da + 2 * k, db + 2 * k, a.idesc, (kb | k) != 0);
+                    tc_commit_pair(bar_empty + stage * 8);
+                    if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit_pair(bar_tfull + acc * 8);
+                acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ================= epilogue (each CTA: its own 128 queries; warps 2..5 <-> TMEM lane quarters 2,3,0,1) ======
+        const int quarter = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (long long wk = pair; wk < n_work; wk += n_pairs) {
+            const int nt = (int)(wk / n_tiles_m2), mt2 = (int)(wk % n_tiles_m2);
+            mbar_wait_u32(bar_tfull + acc * 8, acc_phase);
+            tc_fence_after();
+            const int64_t q = (int64_t)mt2 * 2 * kBM + (int64_t)rank * kBM + quarter * 32 + lane;
+            const int64_t n0 = a.row_offset + (int64_t)nt * kBN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kBN;
+            if (!(a.dbg & 1)) epilogue_tile(a, taddr, q, n0, s_tau);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(bar_tempty + acc * 8);
+            acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // the peer's shared memory / barriers stay valid until both CTAs are done
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -406,7 +615,7 @@ static int64_t dense_sample_rows(const vs_index *idx, int k) {
 static DenseWs carve_dense(const vs_index *idx, void *base, int64_t Bc, int k) {
     DenseWs w;
     auto al = [](size_t x) { return (x + 1023) / 1024 * 1024; };
-    const int64_t b_pad = (Bc + kBM - 1) / kBM * kBM;
+    const int64_t b_pad = (Bc + 2 * kBM - 1) / (2 * kBM) * (2 * kBM);   // whole 256-query pair tiles
     size_t o = 0;
     uint8_t *p = (uint8_t *)base;
     w.q16 = (uint16_t *)(p + o); o += al((size_t)b_pad * idx->d_pad * 2);
@@ -425,7 +634,25 @@ size_t dense_workspace_bytes(const vs_index *idx, int64_t B, int k) {
     return carve_dense(idx, nullptr, Bc, k).bytes + 1024;
 }
 
-static int launch_dense(const vs_index *idx, const CUtensorMap &tq, const CUtensorMap &tx, DenseArgs a, cudaStream_t st) {
+static bool dense_use_pair(const DenseArgs &a) {
+    static const bool off = getenv("VSEARCH_B200_DENSE_PAIR") && atoi(getenv("VSEARCH_B200_DENSE_PAIR")) == 0;
+    return !off && a.n_tiles_m >= 2;   // a single 128-query tile would leave the peer CTA's half of the MMA empty
+}
+
+static int launch_dense(const vs_index *idx, const CUtensorMap &tq, const CUtensorMap &tx, const CUtensorMap &tx_half,
+                        DenseArgs a, cudaStream_t st) {
+    if (dense_use_pair(a)) {
+        const size_t smem = (size_t)kPairStages * kPairStageBytes + 256 + (size_t)kDenseQueryChunk * 4 + 1024;
+        VS_CUDA(cudaFuncSetAttribute(dense_topk_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t n_work = (int64_t)a.n_tiles_n * ((a.n_tiles_m + 1) / 2);
+        int64_t pairs = idx->n_ctas / 2;
+        if (pairs > n_work) pairs = n_work;
+        a.idesc = (a.idesc & ~(0x1fu << 24)) | ((uint32_t)((2 * kBM) >> 4) << 24);   // M = 256 across the pair
+        if (getenv("VSEARCH_B200_DEBUG")) fprintf(stderr, "[vsearch_b200] dense pair kernel: %lld pairs, %lld items, idesc %08x\n", (long long)pairs, (long long)n_work, a.idesc);
+        dense_topk_pair_kernel<<<(unsigned)(2 * pairs), kDenseThreads, smem, st>>>(tq, tx_half, a);
+        VS_CUDA(cudaGetLastError());
+        return VS_OK;
+    }
     const size_t smem = (size_t)kStages * kStageBytes + 256 + (size_t)kDenseQueryChunk * 4 + 1024;
     VS_CUDA(cudaFuncSetAttribute(dense_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_work = (int64_t)a.n_tiles_n * a.n_tiles_m;
@@ -440,15 +667,17 @@ static int launch_dense(const vs_index *idx, const CUtensorMap &tq, const CUtens
 int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t ldq, int k, int score_round,
                  int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, void *d_ws, cudaStream_t st) {
     VS_REQUIRE(idx->n_rows + id_offset < 0xffffffffll, VS_ERR_UNSUPPORTED, "global ids must fit 32 bits");
-    CUtensorMap tx;
+    CUtensorMap tx, tx_half;
     int rc = make_tmap(&tx, idx->dense, idx->store_dtype, idx->n_pad, idx->d_pad, kBN);
+    if (rc) return rc;
+    rc = make_tmap(&tx_half, idx->dense, idx->store_dtype, idx->n_pad, idx->d_pad, kBN / 2);   // CTA-pair kernel: B halves
     if (rc) return rc;
     const uint32_t fmt = idx->store_dtype == VS_F16 ? 0u : 1u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     void *ws_base = (void *)(((uintptr_t)d_ws + 1023) / 1024 * 1024);
     for (int64_t b0 = 0; b0 < B; b0 += kDenseQueryChunk) {
         const int64_t Bc = (B - b0) < kDenseQueryChunk ? (B - b0) : kDenseQueryChunk;
-        const int64_t b_pad = (Bc + kBM - 1) / kBM * kBM;
+        const int64_t b_pad = (Bc + 2 * kBM - 1) / (2 * kBM) * (2 * kBM);
         DenseWs w = carve_dense(idx, ws_base, Bc, k);
         const uint8_t *qsrc = (const uint8_t *)d_q + (size_t)b0 * ldq * (q_dtype == VS_F32 ? 4 : 2);
         dense_convert_kernel<<<1024, 256, 0, st>>>(qsrc, q_dtype, Bc, idx->dim, ldq, w.q16, idx->store_dtype, b_pad, idx->d_pad);
@@ -456,19 +685,20 @@ int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t
         rc = make_tmap(&tq, w.q16, idx->store_dtype, b_pad, idx->d_pad, kBM);
         if (rc) return rc;
         DenseArgs a;
-        a.n_tiles_m = (int)(b_pad / kBM);
+        a.n_tiles_m = (int)((Bc + kBM - 1) / kBM);
         a.k_blocks = (int)(idx->d_pad / kBK);
         a.n_rows = idx->n_rows; a.n_queries = Bc; a.row_offset = 0;
         a.score_round = score_round; a.idesc = idesc;
         a.sample_keys = w.sample; a.tau = w.tau; a.cand = w.cand; a.cand_cnt = w.cnt; a.cand_cap = kDenseCandCap;
         a.work_counter = w.work_counter;
+        a.dbg = getenv("VSEARCH_B200_DENSE_DBG") ? atoi(getenv("VSEARCH_B200_DENSE_DBG")) : 0;
 
         // ---- pass 1 (sample sweep): exact top-k of the first S1 rows -> threshold tau1
         const int64_t s1 = dense_sample_rows(idx, k);
         a.mode = 0; a.n_tiles_n = (int)(s1 / kBN); a.sample_ld = s1; a.row_offset = 0;
         const int slot = idx->timer_n < VS_TIMER_SLOTS ? idx->timer_n : -1;
         if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev0[slot], st));
-        rc = launch_dense(idx, tq, tx, a, st);
+        rc = launch_dense(idx, tq, tx, tx_half, a, st);
         if (rc) return rc;
         if (s1 >= idx->n_rows) {
             // the sample IS the index (small index): its top-k is the answer
@@ -492,7 +722,7 @@ int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t
             for (int attempt = 0;; ++attempt) {
                 dense_seed_lists_kernel<<<(unsigned)Bc, 128, 0, st>>>(w.tau_sorted, k, w.cand, kDenseCandCap, w.cnt, w.tau);
                 a.mode = 1; a.row_offset = row; a.n_tiles_n = (int)(rows / kBN);
-                rc = launch_dense(idx, tq, tx, a, st);
+                rc = launch_dense(idx, tq, tx, tx_half, a, st);
                 if (rc) return rc;
                 std::vector<uint32_t> h_cnt((size_t)Bc);
                 VS_CUDA(cudaMemcpyAsync(h_cnt.data(), w.cnt, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
