@@ -82,7 +82,7 @@ def test_dense_heavy_ties_and_edges(cuda_device):
 def test_dense_sorted_index_overflow_retry(cuda_device):
     """Passages sorted by increasing score: the sample prefix gives a useless threshold, every row of the sweep
     survives it, the candidate lists overflow and the kernel must tighten and repeat."""
-    n, d = 200_000, 64
+    n, d = 1_000_000, 64
     x = torch.zeros(n, d)
     x[:, 0] = torch.arange(n).float() / 4.0
     q = torch.zeros(2, d)

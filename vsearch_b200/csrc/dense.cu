@@ -32,7 +32,8 @@
 namespace vs {
 
 constexpr int kBM = 128, kBN = 256, kBK = 64, kStages = 4;
-constexpr int kDenseThreads = 192;
+constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter: each takes half of the tile's 256 columns
+constexpr int kDenseThreads = 64 + kEpiWarps * 32;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr uint32_t kStageBytesA = kBM * kBK * 2, kStageBytesB = kBN * kBK * 2;
 constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;  // 48 KB
 constexpr int kTmemCols = 512;
@@ -49,7 +50,7 @@ struct DenseArgs {
     const uint64_t *tau;   // [n_queries] threshold keys (mode 1)
     uint64_t *cand; uint32_t *cand_cnt; int64_t cand_cap;  // [n_queries, cand_cap], [n_queries]
     unsigned long long *work_counter;   // dynamic tile scheduler (zeroed before every launch)
-    int dbg;               // timing experiments only (VSEARCH_B200_DENSE_DBG): 1 skip epilogue, 2 skip MMA, 4 skip TMA
+    int dbg;               // timing experiments only (VSEARCH_B200_DENSE_DBG): 1 skip epilogue, 2 skip MMA, 4 skip TMA, 8 skip candidate path
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -128,29 +129,38 @@ __device__ __forceinline__ void reg_fence32(uint32_t (&r)[32]) {
 // ld/wait per 32 columns made the epilogue (16 us per tile), not TMA + MMA (6 us), the bottleneck (measured with the
 // epilogue switched off, profiles/README.md).  The filtered sweep therefore pulls 128 columns per wait.
 //
-// The rare 32-column chunk in which some lane of the warp has a candidate (~10 % of the chunks at k = 100) is handled
-// OUT OF LINE and warp-collectively: one more tcgen05.ld of that chunk, count, ONE global atomic per lane with
-// candidates, write.  (Inlined into every batch the epilogue was 6 K instructions and the warps sat in instruction-cache
-// misses; a local-memory copy of the scores is worse still: a CTA that owns 214 KB of shared memory has no L1 left.)
-__device__ __noinline__ void filter32_slow(const uint32_t taddr, const int64_t nb, const int64_t n_rows, const int score_round,
-                                           const float tau_s, const uint64_t tau, uint32_t *cnt_q, uint64_t *dst,
-                                           const uint32_t cap) {
-    uint32_t r[32];
-    tc_ld32(taddr, r);
+// Candidates are rare (k / rows-seen per score), so the filter is two-level and stays in registers: a lane whose
+// 32-column chunk maximum reaches the (conservative, un-rounded) threshold builds the bit mask of its qualifying
+// columns -- one compare per score -- and hands each one to an out-of-line exact test (rounding, key compare, one
+// global atomic, one 8-byte store).  The epilogue has to be SMALL as well as short: every variant that inlined the key
+// handling per column (2-6 K instructions) left the warps waiting on instruction fetch, a local-memory copy of the
+// scores has no L1 to live in next to 214 KB of shared memory, and re-reading a hot chunk from TMEM costs another
+// 1-2 us round trip behind the queued MMAs (all measured, profiles/README.md).
+__device__ __noinline__ void dense_candidate(const float raw, const int64_t row, const int64_t n_rows, const int score_round,
+                                             const uint64_t tau, uint32_t *cnt_q, uint64_t *dst, const uint32_t cap) {
+    if (row >= n_rows) return;
+    const uint64_t key = make_key(round_score(raw, score_round), (uint32_t)row);
+    if (key < tau) return;
+    // Past the end of the list the second half is reused as a ring: after an overflow the list then holds the first AND
+    // the last cap/2 candidates of the sweep, so the retry threshold is tight whichever way the rows are ordered.
+    const uint32_t pos = atomicAdd(cnt_q, 1u);
+    dst[pos < cap ? pos : (cap >> 1) + (pos & ((cap >> 1) - 1u))] = key;
+}
+
+__device__ __forceinline__ void scan32(const uint32_t (&x)[32], const int64_t nb, const DenseArgs &a, const float tau_raw,
+                                       const uint64_t tau, uint32_t *cnt_q, uint64_t *dst) {
     uint32_t m = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const float sj = round_score(__uint_as_float(r[j]), score_round);
-        if (sj >= tau_s && nb + j < n_rows && make_key(sj, (uint32_t)(nb + j)) >= tau) m |= 1u << j;
-    }
-    if (m == 0) return;
-    uint32_t pos = atomicAdd(cnt_q, (uint32_t)__popc(m));
+    for (int j = 0; j < 32; ++j) m |= (__uint_as_float(x[j]) >= tau_raw) ? (1u << j) : 0u;
+#pragma unroll 1
+    while (m) {
+        const uint32_t bit = m & (0u - m);
+        m ^= bit;
+        uint32_t v = x[0];
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-        if ((m >> j) & 1u) {
-            if (pos < cap) dst[pos] = make_key(round_score(__uint_as_float(r[j]), score_round), (uint32_t)(nb + j));
-            ++pos;
-        }
+        for (int j = 1; j < 32; ++j) v = (bit & (1u << j)) ? x[j] : v;   // dynamic register read as a select chain
+        dense_candidate(__uint_as_float(v), nb + (__ffs(bit) - 1), a.n_rows, a.score_round, tau, cnt_q, dst, (uint32_t)a.cand_cap);
+    }
 }
 
 __device__ __forceinline__ float max32(const uint32_t (&x)[32]) {
@@ -161,13 +171,14 @@ __device__ __forceinline__ float max32(const uint32_t (&x)[32]) {
 }
 
 // ---- epilogue of one accumulator tile: thread = query row `q`, columns = passages n0 .. n0 + kBN ----------------
+// `taddr` / `n0` already point at this warp's 128-column half of the tile
 __device__ __forceinline__ void epilogue_tile(const DenseArgs &a, const uint32_t taddr, const int64_t q, const int64_t n0,
                                               const float *s_tau) {
     const bool q_ok = q < a.n_queries;
     if (a.mode == 0) {
         // ---- sample sweep: every score of the tile becomes a rank key
 #pragma unroll 1
-        for (int c = 0; c < kBN / 32; ++c) {
+        for (int c = 0; c < kBN / 64; ++c) {
             uint32_t r[32];
             tc_ld32(taddr + c * 32, r);
             const int64_t nb = n0 + c * 32;
@@ -188,28 +199,23 @@ __device__ __forceinline__ void epilogue_tile(const DenseArgs &a, const uint32_t
         const uint64_t tau = q_ok ? a.tau[q] : ~0ull;
         uint64_t *dst = a.cand + q * a.cand_cap;
         uint32_t *cnt_q = a.cand_cnt + q;
-        const bool rnd = a.score_round != VS_F32;
+        // scores are rounded to the index dtype before they are ranked; raw >= tau_raw is implied by round(raw) >= tau_s
+        // (bf16 / fp16 rounding moves a value by < 2^-8 relative), the exact test happens on the few that pass
+        const float tau_raw = a.score_round != VS_F32 ? tau_s - fabsf(tau_s) * 0.0078125f - 1e-30f : tau_s;
         uint32_t ra[32], rb[32], rc[32], rd[32];
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {   // two batches of 128 columns
-            const uint32_t th = taddr + h * 128;
+        {   // one round trip for the warp's 128 columns
+            const uint32_t th = taddr;
             tc_ld32_issue(th, ra); tc_ld32_issue(th + 32, rb); tc_ld32_issue(th + 64, rc); tc_ld32_issue(th + 96, rd);
             tc_wait_ld(); reg_fence32(ra); reg_fence32(rb); reg_fence32(rc); reg_fence32(rd);
-            float m0 = max32(ra), m1 = max32(rb), m2 = max32(rc), m3 = max32(rd);
-            if (rnd) {
-                m0 = round_score(m0, a.score_round); m1 = round_score(m1, a.score_round);
-                m2 = round_score(m2, a.score_round); m3 = round_score(m3, a.score_round);
-            }
-            const uint32_t hot = __reduce_or_sync(0xffffffffu, (m0 >= tau_s ? 1u : 0u) | (m1 >= tau_s ? 2u : 0u) |
-                                                                   (m2 >= tau_s ? 4u : 0u) | (m3 >= tau_s ? 8u : 0u));
-#pragma unroll 1
-            for (uint32_t hm = hot; hm; hm &= hm - 1) {
-                const int c = __ffs(hm) - 1;
-                filter32_slow(th + c * 32, n0 + h * 128 + c * 32, a.n_rows, a.score_round, tau_s, tau, cnt_q, dst,
-                              (uint32_t)a.cand_cap);
+            const float m0 = max32(ra), m1 = max32(rb), m2 = max32(rc), m3 = max32(rd);
+            if (!(a.dbg & 8)) {
+                if (m0 >= tau_raw) scan32(ra, n0, a, tau_raw, tau, cnt_q, dst);
+                if (m1 >= tau_raw) scan32(rb, n0 + 32, a, tau_raw, tau, cnt_q, dst);
+                if (m2 >= tau_raw) scan32(rc, n0 + 64, a, tau_raw, tau, cnt_q, dst);
+                if (m3 >= tau_raw) scan32(rd, n0 + 96, a, tau_raw, tau, cnt_q, dst);
             }
         }
-        static_assert(kBN == 256, "the epilogue walks 2 batches of 128 columns");
+        static_assert(kBN == 256 && kEpiWarps == 8, "each epilogue warp owns 128 columns");
     }
 }
 
@@ -239,9 +245,9 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int s = 0; s < kStages; ++s) { mbar_init(bars + s, 1); mbar_init(bars + kStages + s, 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bars + 2 * kStages + i, 1);          // tfull: one tcgen05.commit
-            mbar_init(bars + 2 * kStages + 2 + i, 4);      // tempty: the four epilogue warps
+            mbar_init(bars + 2 * kStages + 2 + i, kEpiWarps);      // tempty: the epilogue warps
             mbar_init(bars + 2 * kStages + 4 + i, 1);      // sfull: the scheduler (producer thread)
-            mbar_init(bars + 2 * kStages + 6 + i, 5);      // sempty: MMA thread + four epilogue warps
+            mbar_init(bars + 2 * kStages + 6 + i, 1 + kEpiWarps);      // sempty: MMA thread + the epilogue warps
         }
         fence_mbar_init();
     }
@@ -320,8 +326,8 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
         }
     } else {
-        // ================= epilogue (warps 2..5 <-> TMEM lane quarters 2,3,0,1) =================
-        const int quarter = warp & 3;
+        // ================= epilogue (warp w <-> TMEM lane quarter w % 4; warps 2..5 columns 0..127, 6..9 the rest) ====
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         int ss = 0; uint32_t sphase = 0;
         for (;;) {
@@ -336,8 +342,8 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 mbar_wait_u32(bar_tfull + acc * 8, acc_phase);
                 tc_fence_after();
                 const int64_t q = (int64_t)mt * kBM + quarter * 32 + lane;   // this thread's query row
-                const int64_t n0 = a.row_offset + (int64_t)nt * kBN;         // first passage of the tile
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kBN;
+                const int64_t n0 = a.row_offset + (int64_t)nt * kBN + half * (kBN / 2);   // first passage of this warp's half
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kBN + half * (kBN / 2);
                 epilogue_tile(a, taddr, q, n0, s_tau);
                 tc_fence_before();
                 __syncwarp();
@@ -425,7 +431,7 @@ dense_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         for (int s = 0; s < kPairStages; ++s) { mbar_init(bars + s, 1); mbar_init(bars + kPairStages + s, 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bars + 2 * kPairStages + i, 1);      // tfull: one multicast commit
-            mbar_init(bars + 2 * kPairStages + 2 + i, 8);  // tempty (leader's is used): epilogue warps of both CTAs
+            mbar_init(bars + 2 * kPairStages + 2 + i, 2 * kEpiWarps);  // tempty (leader's is used): epilogue warps of both CTAs
         }
         fence_mbar_init();
     }
@@ -488,16 +494,16 @@ dense_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             }
         }
     } else {
-        // ================= epilogue (each CTA: its own 128 queries; warps 2..5 <-> TMEM lane quarters 2,3,0,1) ======
-        const int quarter = warp & 3;
+        // ================= epilogue (each CTA: its own 128 queries; warp w <-> TMEM lane quarter w % 4, column half) ===
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         for (long long wk = pair; wk < n_work; wk += n_pairs) {
             const int nt = (int)(wk / n_tiles_m2), mt2 = (int)(wk % n_tiles_m2);
             mbar_wait_u32(bar_tfull + acc * 8, acc_phase);
             tc_fence_after();
             const int64_t q = (int64_t)mt2 * 2 * kBM + (int64_t)rank * kBM + quarter * 32 + lane;
-            const int64_t n0 = a.row_offset + (int64_t)nt * kBN;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kBN;
+            const int64_t n0 = a.row_offset + (int64_t)nt * kBN + half * (kBN / 2);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kBN + half * (kBN / 2);
             if (!(a.dbg & 1)) epilogue_tile(a, taddr, q, n0, s_tau);
             tc_fence_before();
             __syncwarp();
@@ -533,11 +539,19 @@ __global__ void dense_convert_kernel(const void *in, int in_dtype, int64_t rows,
 
 // Start of a filtered sweep: every query's candidate list is seeded with its current top-k (sorted keys, one block
 // per query), the threshold is the k-th of them.
+// Every sweep starts from the top-k of the rows BEFORE it (`sorted_keys`) and their k-th key as the threshold.  A retry
+// after an overflow keeps those seeds -- seeding rows of the sweep itself would append them a second time -- and only
+// raises the threshold to the k-th best of what the failed attempt had stored (`retry_keys`).
 __global__ void dense_seed_lists_kernel(const uint64_t *sorted_keys, int k, uint64_t *cand, int64_t cap, uint32_t *cnt,
-                                        uint64_t *tau) {
+                                        uint64_t *tau, const uint64_t *retry_keys) {
     const int64_t q = blockIdx.x;
     for (int i = threadIdx.x; i < k; i += blockDim.x) cand[q * cap + i] = sorted_keys[q * k + i];
-    if (threadIdx.x == 0) { cnt[q] = (uint32_t)k; tau[q] = sorted_keys[q * k + (k - 1)]; }
+    if (threadIdx.x == 0) {
+        cnt[q] = (uint32_t)k;
+        uint64_t t = sorted_keys[q * k + (k - 1)];
+        if (retry_keys && retry_keys[q * k + (k - 1)] > t) t = retry_keys[q * k + (k - 1)];
+        tau[q] = t;
+    }
 }
 
 static PFN_cuTensorMapEncodeTiled get_encode_fn() {
@@ -595,7 +609,8 @@ struct DenseWs {
     uint16_t *q16;        // [b_pad, d_pad]
     uint64_t *sample;     // [Bc, sample_rows]
     uint64_t *tau;        // [Bc]
-    uint64_t *tau_sorted; // [Bc, k]
+    uint64_t *tau_sorted; // [Bc, k]  top-k of the rows before the current sweep
+    uint64_t *tau_retry;  // [Bc, k]  top-k of what an overflowed attempt stored
     uint32_t *cnt;        // [Bc]
     unsigned long long *work_counter;
     uint64_t *cand;       // [Bc, cap]
@@ -622,6 +637,7 @@ static DenseWs carve_dense(const vs_index *idx, void *base, int64_t Bc, int k) {
     w.sample = (uint64_t *)(p + o); o += al((size_t)Bc * dense_sample_rows(idx, k) * 8);
     w.tau = (uint64_t *)(p + o); o += al((size_t)Bc * 8);
     w.tau_sorted = (uint64_t *)(p + o); o += al((size_t)Bc * k * 8);
+    w.tau_retry = (uint64_t *)(p + o); o += al((size_t)Bc * k * 8);
     w.cnt = (uint32_t *)(p + o); o += al((size_t)Bc * 4);
     w.work_counter = (unsigned long long *)(p + o); o += al(8);
     w.cand = (uint64_t *)(p + o); o += al((size_t)Bc * kDenseCandCap * 8);
@@ -720,7 +736,8 @@ int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t
             int64_t rows = (pass == 2) ? 64 * s1 : idx->n_pad - row;
             if (rows > idx->n_pad - row) rows = idx->n_pad - row;
             for (int attempt = 0;; ++attempt) {
-                dense_seed_lists_kernel<<<(unsigned)Bc, 128, 0, st>>>(w.tau_sorted, k, w.cand, kDenseCandCap, w.cnt, w.tau);
+                dense_seed_lists_kernel<<<(unsigned)Bc, 128, 0, st>>>(w.tau_sorted, k, w.cand, kDenseCandCap, w.cnt, w.tau,
+                                                                      attempt ? w.tau_retry : nullptr);
                 a.mode = 1; a.row_offset = row; a.n_tiles_n = (int)(rows / kBN);
                 rc = launch_dense(idx, tq, tx, tx_half, a, st);
                 if (rc) return rc;
@@ -735,7 +752,7 @@ int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t
                 // strictly tighter threshold; redo this sweep with it
                 // (lists that did not overflow keep their own count: only their first cnt[q] entries are valid)
                 rc = launch_merge_counted(w.cand, w.cnt, 1, 0, kDenseCandCap, Bc, (int)kDenseCandCap, k, 0, nullptr, nullptr,
-                                          w.tau_sorted, st);
+                                          w.tau_retry, st);
                 if (rc) return rc;
             }
             row += rows;
