@@ -125,6 +125,25 @@ int vs_index_last_mode(const vs_index *idx, int *mode);
 #define VS_TIMER_SLOTS 256
 int vs_kernel_timer(vs_index *idx, int reset, float *total_ms, int *launches);
 
+/* ---- native .npz shard reader (host only, no CUDA calls) ------------------------------------------------------
+ * Replaces, for the big members of an index shard, scipy.sparse.load_npz + vstack + astype on one Python thread
+ * (reference src/ir/retriever/index.py:172-176).  A shard is a zip of .npy members written by
+ * scipy.sparse.save_npz (index.py:195-197): indices / indptr (int32 | int64), data (float32 | float16), plus the
+ * small format / shape / _is_array members.  Calls on one handle may run concurrently from several threads (each
+ * opens its own file descriptor), which is how the loader inflates every member of every shard in parallel. */
+typedef struct vs_npz vs_npz;
+int vs_npz_open(const char *path, vs_npz **out);
+int vs_npz_close(vs_npz *z);
+/* name without ".npy".  dtype = VS_* code (VS_NONE for dtypes the search path does not use); shape4 gets up to
+ * four extents (0-filled); n_elems = product of the extents. */
+int vs_npz_member_info(vs_npz *z, const char *name, int *dtype, int *ndim, int64_t *shape4, int64_t *n_elems);
+/* Inflate elements [skip_elems, skip_elems + n_elems) of member `name` straight into dst (host memory), converted
+ * to dst_dtype (integer -> VS_I32 | VS_I64 | VS_U32 | VS_U16 with add_offset added: the row-pointer offset of a
+ * shard when shards are concatenated by rows; float -> VS_F32 | VS_F16: the reference's fp16=True astype).
+ * Streaming: 2 MB of scratch per call, no inflated copy of the member. */
+int vs_npz_read(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t skip_elems, int64_t n_elems,
+                int64_t add_offset);
+
 #ifdef __cplusplus
 }
 #endif

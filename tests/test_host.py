@@ -138,3 +138,39 @@ def test_row_partition_covers_rows():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
     assert vs.row_partition(21015324, 8, 0) == (0, 2626916)
+
+
+def test_native_npz_reader_matches_numpy_reader(tmp_path):
+    """csrc/npz.cu (zip central directory, .npy headers, streaming inflate with on-the-fly int64 -> int32, row-pointer
+    offsets and astype(float16)) against the numpy member reader, on files written by scipy (deflate), by numpy
+    (stored) and by our saver (fp16 data), int32 and int64 index members, an empty-row and a one-row shard."""
+    rng = np.random.default_rng(0)
+    files = []
+    for i, (n, idt) in enumerate([(3000, np.int32), (2000, np.int64), (1, np.int32), (2500, np.int32)]):
+        m = sp.random(n, 29523, density=0.003, format="csr", random_state=i, dtype=np.float32)
+        m.indices, m.indptr = m.indices.astype(idt), m.indptr.astype(idt)
+        f = str(tmp_path / f"index{i}.npz")
+        sp.save_npz(f, m)
+        files.append(f)
+    a = npz_io.load_csr_shards(files)
+    b = npz_io.load_csr_shards_native(files, threads=3)
+    assert a[3] == b[3]
+    for x, y in zip(a[:3], b[:3]):
+        assert x.dtype == y.dtype and np.array_equal(x, y)
+    c = npz_io.load_csr_shards_native(files, fp16=True)
+    assert c[2].dtype == np.float16 and np.array_equal(c[2], a[2].astype(np.float16))
+    stored = str(tmp_path / "stored.npz")
+    np.savez(stored, indices=a[1], indptr=a[0], format=np.array(b"csr"), shape=np.asarray(a[3], dtype=np.int64),
+             data=a[2], _is_array=np.array(True))
+    d = npz_io.load_csr_shards_native([stored])
+    assert np.array_equal(d[0], a[0]) and np.array_equal(d[1], a[1]) and np.array_equal(d[2], a[2])
+    half = str(tmp_path / "half.npz")
+    npz_io.save_csr_npz(half, a[0], a[1], a[2].astype(np.float16), a[3])
+    e = npz_io.load_csr_shards_native([half])
+    assert e[2].dtype == np.float16 and np.array_equal(e[1], a[1])
+    with pytest.raises(ValueError):
+        npz_io.load_csr_shards_native([str(tmp_path / "missing.npz")])
+    bad = tmp_path / "bad.npz"
+    bad.write_bytes(b"not a zip archive at all" * 10)
+    with pytest.raises(ValueError):
+        npz_io.load_csr_shards_native([str(bad)])

@@ -4,22 +4,24 @@
 //
 //   S[b, n] = sum_d Q[b, d] * X[n, d]      A = Q tile [128 queries, 64] , B = X tile [256 passages, 64], both K-major
 //
-// One persistent CTA per SM, warp-specialised (192 threads):
+// Persistent, warp-specialised (320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the A / B k-blocks (128-byte swizzle) into a
-//               4-stage shared-memory ring, completion on mbarriers
-//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) x4
-//               per k-block into one of two 256-column TMEM accumulators; tcgen05.commit frees the smem stage /
-//               signals the epilogue
-//   warps 2-5   epilogue: tcgen05.ld the accumulator (thread = query row, 32 columns at a time), never write S:
+//               shared-memory ring, completion on mbarriers
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.kind::f16 (K = 16, x4 per k-block) into one of two
+//               256-column TMEM accumulators; tcgen05.commit frees the smem stage / signals the epilogue
+//   warps 2-9   epilogue: warp w reads TMEM lane quarter w % 4 (thread = query row), columns 0..127 (warps 2-5) or
+//               128..255 (warps 6-9), in ONE tcgen05.ld round trip per tile; S is never written:
 //               mode 0 (sample)    emit every score of the tile as a rank key (small sample prefix of the index)
-//               mode 1 (filter)    compare against the per-query threshold; survivors are appended to the
-//                                  query's candidate list with one global atomic
-// Work items (passage tile, query tile) are dealt round-robin with the query tile fastest, so the CTAs that run
-// concurrently share a handful of passage tiles: X is read from HBM once and re-read from L2.
+//               mode 1 (filter)    compare against the per-query threshold; candidates are appended to the
+//                                  query's list (one global atomic each; they are rare)
+// Two variants: dense_topk_pair_kernel (default; cta_group::2, a cluster of two CTAs shares one M=256 x N=256 UMMA,
+// static item order) and dense_topk_kernel (cta_group::1, M=128 x N=256, dynamic tile scheduler; used when there
+// is a single 128-query tile).  DESIGN.md section 4 records what bounds the kernel and how that was measured.
 //
-// Host side (search_dense): threshold from an exact top-k of a sample prefix -> one filtered sweep over the whole
-// index -> exact top-k of the survivors with the K6 merge kernel.  If a candidate list overflows (adversarial
-// ordering) the threshold is tightened from the stored candidates and the sweep repeated.
+// Host side (search_dense): threshold from an exact top-k of a sample prefix -> filtered sweeps over the rest of the
+// index (the threshold is tightened once after the first ~1M rows) -> exact top-k of the survivors with the K6 merge
+// kernel.  If a candidate list overflows (adversarial ordering) the threshold is tightened from the stored candidates
+// and the sweep repeated.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 

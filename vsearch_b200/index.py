@@ -406,15 +406,20 @@ class SparseIndex(Index):
         """glob -> sorted -> load_npz -> ``[:, shift:]`` -> vstack -> optional fp16 (upstream index.py:163-179)."""
         if not index_file:
             return
-        from .npz_io import load_csr_shards
+        from .npz_io import load_csr_shards, load_csr_shards_native
 
         files = sorted(glob.glob(index_file))
         if not files:
             raise FileNotFoundError(f"no index files match {index_file!r}")
         logger.info("***** Loading %s Index from %d files *****", self.index_type.value, len(files))
-        indptr, indices, data, shape = load_csr_shards(files, self.shift)
-        if fp16:
-            data = data.astype(np.float16)
+        if self.shift <= 0:
+            # native reader (csrc/npz.cu): all members of all shards inflated in parallel into the final arrays,
+            # int64 -> int32 narrowing and astype(float16) on the fly
+            indptr, indices, data, shape = load_csr_shards_native(files, fp16=fp16)
+        else:  # the column slice changes the row pointers: numpy path
+            indptr, indices, data, shape = load_csr_shards(files, self.shift)
+            if fp16:
+                data = data.astype(np.float16)
         import warnings
 
         with warnings.catch_warnings():

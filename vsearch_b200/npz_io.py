@@ -11,6 +11,9 @@ index.py:174) and so that no scipy matrix copy of a 21M-row index is ever made.
 """
 from __future__ import annotations
 
+import ctypes
+import os
+from concurrent.futures import ThreadPoolExecutor
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -60,6 +63,100 @@ def load_csr_shards(files: Sequence[str], shift: int = 0) -> Tuple[np.ndarray, n
     indices = np.concatenate(idxs).astype(idx_dtype)
     data = np.concatenate(vals)
     return indptr, indices, data, (n_rows, int(n_cols or 0))
+
+
+# ---- native loader (csrc/npz.cu through the C ABI) ---------------------------------------------------------------
+_NP2VS = {np.dtype(np.int32): 3, np.dtype(np.int64): 4, np.dtype(np.float32): 0, np.dtype(np.float16): 1}
+_VS2NP = {0: np.float32, 1: np.float16, 3: np.int32, 4: np.int64, 5: np.uint16, 6: np.uint32}
+
+
+class _NativeShard:
+    """One open shard file: member table from the zip central directory + .npy headers (no data read yet)."""
+
+    def __init__(self, path: str):
+        from . import _native as nat
+
+        self.nat, self.path = nat, path
+        self.h = ctypes.c_void_p()
+        nat.check(nat.LIB.vs_npz_open(os.fsencode(path), ctypes.byref(self.h)))
+
+    def info(self, name: str):
+        dt, nd, n = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+        shape = (ctypes.c_int64 * 4)()
+        self.nat.check(self.nat.LIB.vs_npz_member_info(self.h, name.encode(), dt, nd, shape, n))
+        return dt.value, tuple(shape[i] for i in range(nd.value)), int(n.value)
+
+    def read_into(self, name: str, out: np.ndarray, skip: int = 0, add: int = 0) -> None:
+        assert out.flags.c_contiguous
+        self.nat.check(self.nat.LIB.vs_npz_read(self.h, name.encode(), out.ctypes.data_as(ctypes.c_void_p),
+                                                _NP2VS[out.dtype], skip, out.size, add))
+
+    def small(self, name: str) -> np.ndarray:
+        dt, shape, n = self.info(name)
+        out = np.empty(n, dtype=_VS2NP[dt])
+        self.read_into(name, out)
+        return out.reshape(shape)
+
+    def close(self):
+        if self.h:
+            self.nat.LIB.vs_npz_close(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
+def load_csr_shards_native(files: Sequence[str], fp16: bool = False, threads: int | None = None):
+    """Row-concatenation of shard files like :func:`load_csr_shards` (``shift == 0``), but every big member of every
+    shard is inflated by its own thread straight into its slice of the final arrays (ctypes releases the GIL), with
+    the int64 -> int32 narrowing, the row-pointer offset of the shard and the optional ``astype(float16)`` of the
+    reference loader (index.py:176) applied on the fly.  Peak host memory = the final arrays.
+    Returns (indptr, indices, data, shape) as numpy arrays."""
+    shards = [_NativeShard(f) for f in files]
+    try:
+        metas = []
+        n_rows, n_cols, nnz = 0, None, 0
+        data_np = None
+        for sh, f in zip(shards, files):
+            with np.load(f, allow_pickle=False) as z:   # the three tiny members: numpy is fine
+                fmt = z["format"].item()
+                shape = tuple(int(x) for x in z["shape"])
+            fmt = fmt.decode("ascii") if isinstance(fmt, bytes) else str(fmt)
+            if fmt != "csr":
+                raise ValueError(f"{f}: expected a CSR .npz, found format {fmt!r}")
+            (_, _, n_ptr), (_, _, n_idx), (ddt, _, n_dat) = sh.info("indptr"), sh.info("indices"), sh.info("data")
+            if n_ptr != shape[0] + 1 or n_idx != n_dat:
+                raise ValueError(f"{f}: inconsistent CSR members")
+            if n_cols is None:
+                n_cols = shape[1]
+            elif shape[1] != n_cols:
+                raise ValueError(f"{f}: column count {shape[1]} differs from previous shards ({n_cols})")
+            if ddt not in (0, 1):
+                raise ValueError(f"{f}: data must be float32 or float16")
+            data_np = _VS2NP[ddt] if data_np is None else np.result_type(data_np, _VS2NP[ddt])
+            metas.append((n_rows, nnz, shape[0], n_idx))
+            n_rows += shape[0]
+            nnz += n_idx
+        idx_dtype = np.int32 if max(nnz, n_cols or 0) < 2**31 - 1 else np.int64
+        indptr = np.empty(n_rows + 1, dtype=idx_dtype)
+        indices = np.empty(nnz, dtype=idx_dtype)
+        data = np.empty(nnz, dtype=np.float16 if fp16 else (data_np or np.float32))
+        indptr[0] = 0
+        jobs = []
+        for sh, (r0, z0, rows, cnt) in zip(shards, metas):
+            jobs.append((sh, "indices", indices[z0:z0 + cnt], 0, 0))
+            jobs.append((sh, "data", data[z0:z0 + cnt], 0, 0))
+            jobs.append((sh, "indptr", indptr[r0 + 1:r0 + 1 + rows], 1, z0))   # drop each shard's leading 0, add its offset
+        jobs.sort(key=lambda j: -j[2].size)
+        with ThreadPoolExecutor(max_workers=threads or min(len(jobs), os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda j: j[0].read_into(j[1], j[2], skip=j[3], add=j[4]), jobs))
+        return indptr, indices, data, (n_rows, int(n_cols or 0))
+    finally:
+        for sh in shards:
+            sh.close()
 
 
 def save_csr_npz(path: str, indptr: np.ndarray, indices: np.ndarray, data: np.ndarray, shape) -> None:
