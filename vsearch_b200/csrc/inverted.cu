@@ -1,7 +1,7 @@
 // inverted.cu -- K3: token-major inverted-list scoring for sparse queries, sm_100a.
 // Same contract as the scan (replaces upstream index.py:91-92) but touches only the posting lists of the query's
-// non-zero tokens.  The lists are BLOCK-PARTITIONED: the rows are cut into blocks of R <= 36,864 consecutive rows
-// (a multiple of the SM count of them when the index is large), and every block keeps its own token-major posting
+// non-zero tokens.  The lists are BLOCK-PARTITIONED: the rows are cut into blocks of R = 36,864 consecutive rows
+// (fewer for a smaller index), and every block keeps its own token-major posting
 // lists with 16-bit block-local row ids.  A block's fp32 score accumulator (R x 4 B <= 144 KB) lives in SHARED
 // memory, so scoring one query against one block is
 //   zero the accumulator -> add w_t (x value) at every posting of the query's tokens (shared-memory atomics)
@@ -30,7 +30,6 @@ constexpr int kInvWarps = kInvThreads / 32;
 constexpr int kInvBuildThreads = 1024;
 constexpr int kMaxQueryNnz = 4096;    // queries denser than this are served by the scan kernels
 constexpr int kBlockRowsMax = 36864;  // accumulator rows per block: 144 KB of the 227 KB
-constexpr int kBlockRowsMin = 8192;   // small indices: fewer, longer lists rather than one tiny block per SM
 constexpr int kTokTile = 512;         // query tokens staged per pass over a block
 
 struct BlockLists {
@@ -124,16 +123,17 @@ __global__ void __launch_bounds__(kInvBuildThreads, 1) inv_build_kernel(const Ws
     }
 }
 
+// Blocks are as large as the shared-memory accumulator allows: the per-(query, block) fixed costs (threshold sample,
+// final select, list-pointer fetches) are what a small shard pays for, so fewer and longer blocks win; a query then
+// occupies ceil(N / R) CTAs and the grid's query dimension fills the remaining SMs.
 static void block_geometry(const vs_index *idx, int *rows_per_block, int *n_blocks, int *blocks_per_cta) {
     const int64_t N = idx->n_rows > 0 ? idx->n_rows : 1;
-    const int64_t per_cta = (N + idx->n_ctas - 1) / idx->n_ctas;
-    int64_t R, bpc = 1;
-    if (per_cta <= kBlockRowsMax) R = per_cta < kBlockRowsMin ? kBlockRowsMin : per_cta;
-    else { bpc = (per_cta + kBlockRowsMax - 1) / kBlockRowsMax; R = (N + idx->n_ctas * bpc - 1) / (idx->n_ctas * bpc); }
+    int64_t R = N < kBlockRowsMax ? N : kBlockRowsMax;
     R = (R + 3) / 4 * 4;
+    const int64_t nb = (N + R - 1) / R;
     *rows_per_block = (int)R;
-    *n_blocks = (int)((N + R - 1) / R);
-    *blocks_per_cta = (int)bpc;
+    *n_blocks = (int)nb;
+    *blocks_per_cta = (int)((nb + idx->n_ctas - 1) / idx->n_ctas);
 }
 
 int build_inverted(vs_index *idx, cudaStream_t st) {
