@@ -125,6 +125,20 @@ int vs_index_last_mode(const vs_index *idx, int *mode);
 #define VS_TIMER_SLOTS 256
 int vs_kernel_timer(vs_index *idx, int reset, float *total_ms, int *launches);
 
+/* ---- bag-of-token rows from token-id batches, on the GPU -----------------------------------------------------------
+ * Replaces Retriever._build_bot_vectors (reference src/ir/retriever/retriever.py:208-253: dense [batch, vocab]
+ * scatter of ones, `[:, num_shift:]`, to_sparse_coo / cat / to_sparse_csr).  Row r of the result = the distinct
+ * token ids of passage r (all of them, or the first `max_token` distinct ones in sequence order when max_token > 0,
+ * reference get_first_unique_n), minus ids < num_shift, renumbered id - num_shift, ascending.
+ *   d_token_ids  device [n_rows, ld] int32 | int64 (ids outside [0, vocab_size) are ignored)
+ *   d_lengths    device int32 [n_rows] valid ids per row, or NULL (all ld)
+ * Two calls: d_col == NULL writes the row lengths into d_row_nnz_or_crow[n_rows]; the caller scans them into row
+ * pointers and calls again with d_row_nnz_or_crow = crow (int64 [n_rows + 1]) and d_col (int32 [nnz]) to fill.
+ * Enqueues on `stream`, does not synchronise. */
+int vs_bot_from_tokens(int device, const void *d_token_ids, int ids_dtype, int64_t n_rows, int64_t ld,
+                       const int32_t *d_lengths, int vocab_size, int num_shift, int max_token,
+                       int64_t *d_row_nnz_or_crow, int32_t *d_col, void *stream);
+
 /* ---- native .npz shard reader (host only, no CUDA calls) ------------------------------------------------------
  * Replaces, for the big members of an index shard, scipy.sparse.load_npz + vstack + astype on one Python thread
  * (reference src/ir/retriever/index.py:172-176).  A shard is a zip of .npy members written by

@@ -195,3 +195,28 @@ def merge_keys_oracle(gathered: torch.Tensor, k: int):
     top = np.take_along_axis(u, order, axis=1)
     ids, sc = unpack_keys(torch.from_numpy(top.view(np.int64).copy()))
     return ids, sc
+
+
+def ref_bot_rows(token_lists, vocab_size=30522, num_shift=999, max_token=None):
+    """Restates upstream Retriever._build_bot_vectors (src/ir/retriever/retriever.py:232-251) for ONE batch: dense
+    zeros [n, vocab], ``emb[i, token_ids] = 1`` (first ``max_token`` distinct ids in order when given,
+    index_utils.py:11-21), the ``[:, num_shift:]`` slice, ``to_sparse_coo`` -> ``to_sparse_csr``.
+    Returns (crow int64, col int64, shape)."""
+    n = len(token_lists)
+    emb = torch.zeros([n, vocab_size], dtype=torch.float32)
+    for i, ids in enumerate(token_lists):
+        ids = list(ids)
+        if max_token:
+            seen, first = set(), []
+            for e in ids:
+                if e in seen:
+                    continue
+                seen.add(e)
+                first.append(e)
+                if len(seen) == max_token:
+                    break
+            ids = first
+        if ids:
+            emb[i, ids] = 1
+    csr = emb[:, num_shift:].to_sparse_coo().to_sparse_csr()
+    return csr.crow_indices().to(torch.int64), csr.col_indices().to(torch.int64), (n, vocab_size - num_shift)

@@ -102,3 +102,44 @@ def test_dense_build_save_load(tmp_path, cuda_device):
     assert torch.equal(res2.ids.cpu(), canon16.ids)
     r2.save_index(str(tmp_path / "all.pt"))
     assert torch.equal(torch.load(str(tmp_path / "all.pt")), x.to(torch.float16))
+
+
+class _WordTokenizer:
+    """Stand-in for the BERT tokenizer of upstream's encoder_p: [CLS] words... [SEP], ids from a fixed vocabulary."""
+
+    def __init__(self, vocab_size=3000):
+        self.vocab = {f"w{i}": i for i in range(vocab_size)}
+
+    def __call__(self, texts, max_length=128, truncation=True):
+        out = []
+        for t in texts:
+            ids = [101] + [self.vocab[w] for w in t.split() if w in self.vocab]
+            out.append((ids[:max_length - 1] if truncation else ids) + [102])
+        return {"input_ids": out}
+
+
+class _TokEncoder:
+    def __init__(self):
+        self.tokenizer = _WordTokenizer()
+
+
+def test_bag_of_token_build_from_texts(cuda_device):
+    """build_index(texts, bag_of_token) with a tokenizer-bearing encoder: upstream retriever.py:208-253, 307-312."""
+    import vsearch_b200 as vs
+
+    g = torch.Generator().manual_seed(2)
+    texts = [" ".join(f"w{int(j)}" for j in torch.randint(900, 3000, (int(torch.randint(1, 200, (1,), generator=g)),),
+                                                          generator=g)) for _ in range(500)]
+    r = vs.Retriever(encoder_p=_TokEncoder(), device="cuda:0")
+    r.build_index(texts, index_type="bag_of_token")
+    assert isinstance(r.index, vs.BoTIndex) and r.index.data is texts
+    rows = _WordTokenizer()(texts)["input_ids"]
+    crow, col, shape = ref_search.ref_bot_rows(rows, vocab_size=3000, num_shift=999)
+    got = r.index.vector.cpu()
+    assert tuple(got.shape) == shape and got.values().dtype == torch.float16
+    assert torch.equal(got.crow_indices().to(torch.int64), crow) and torch.equal(got.col_indices().to(torch.int64), col)
+    q = sparse_queries(3, shape[1], 30, seed=4)
+    X = ref_search.torch_csr(crow, col, torch.ones(col.numel()), shape)
+    res = r.retrieve(q, k=5)
+    assert ref_search.compare_results(ref_search.SearchResults(res.ids, res.scores.float()), ref_search.ref_scores(q, X), 5,
+                                      exact=True) is None

@@ -376,3 +376,31 @@ def test_auto_mode_crossover(cuda_device):
     idx.search_mode = "inverted"
     with pytest.raises(NotImplementedError):  # > 4096 non-zeros per query: inverted lists refuse, auto falls back
         idx.search(sparse_queries(1, V, 6000, seed=1), 5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_token", [None, 20])
+def test_bot_index_from_token_ids(max_token, cuda_device):
+    """GPU bag-of-token construction (vs_bot_from_tokens) against the restated reference builder, then a search on it."""
+    import vsearch_b200 as vs
+
+    g = torch.Generator().manual_seed(11)
+    n, max_len, vocab, shift = 3000, 128, 30522, 999
+    lens = torch.randint(0, max_len + 1, (n,), generator=g, dtype=torch.int32)
+    lens[0], lens[1] = 0, max_len
+    ids = torch.randint(0, vocab, (n, max_len), generator=g, dtype=torch.int64)
+    ids[:, :60] = torch.randint(900, 1400, (n, 60), generator=g)      # many duplicates and ids around the shift
+    ids[:, 0], ids[2, :] = 101, 102                                    # [CLS]; a row of nothing but [SEP]
+    rows = [ids[i, :int(lens[i])].tolist() for i in range(n)]
+    crow, col, shape = ref_search.ref_bot_rows(rows, vocab, shift, max_token)
+    idx = vs.BoTIndex.from_token_ids(ids, lens, vocab_size=vocab, num_shift=shift, max_token=max_token, dtype=torch.float32)
+    assert tuple(idx.vector.shape) == shape
+    got = idx.vector.cpu()
+    assert torch.equal(got.crow_indices().to(torch.int64), crow)
+    assert torch.equal(got.col_indices().to(torch.int64), col)
+    X = ref_search.torch_csr(crow, col, torch.ones(col.numel()), shape)
+    q = sparse_queries(4, shape[1], 64, seed=5)
+    assert ref_search.compare_results(idx.search(q, 10), ref_search.ref_scores(q, X), 10, exact=True) is None
+    ids32 = vs.BoTIndex.from_token_ids(ids.to(torch.int32), None, vocab_size=vocab, num_shift=shift, max_token=max_token)
+    full, _, _ = ref_search.ref_bot_rows(ids.tolist(), vocab, shift, max_token)
+    assert torch.equal(ids32.vector.cpu().crow_indices().to(torch.int64), full)

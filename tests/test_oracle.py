@@ -114,3 +114,16 @@ def test_one_d_query_shape():
     res = ref_search.oracle_search(torch.from_numpy(z["q"]), X, z["k"])
     assert tuple(res.ids.shape) == (7,) and tuple(z["ref_topk_ids"].shape) == (7,)
     assert torch.equal(res.scores, torch.from_numpy(z["ref_topk_scores"]))
+
+
+def test_ref_bot_rows_matches_reference_semantics():
+    """hand-checked case of the bag-of-token construction (retriever.py:232-251): duplicates collapse, ids below the
+    shift vanish, columns are renumbered and ascending, max_token keeps the first distinct ids in order."""
+    rows = [[101, 2054, 2003, 2054, 1996, 102], [101, 102], [5000, 999, 998, 5000]]
+    crow, col, shape = ref_search.ref_bot_rows(rows, vocab_size=30522, num_shift=999)
+    assert shape == (3, 29523)
+    assert crow.tolist() == [0, 3, 3, 5]
+    assert col.tolist() == [1996 - 999, 2003 - 999, 2054 - 999, 0, 5000 - 999]
+    crow, col, _ = ref_search.ref_bot_rows(rows, vocab_size=30522, num_shift=999, max_token=3)
+    assert crow.tolist() == [0, 2, 2, 4]          # row 0 keeps {101, 2054, 2003}; row 2 keeps {5000, 999, 998}
+    assert col.tolist() == [2003 - 999, 2054 - 999, 0, 5000 - 999]

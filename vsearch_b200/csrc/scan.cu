@@ -10,10 +10,10 @@
 //      ring) -- loads never depend on row pointers, the row-end ("tail") flag of a chunk rides in
 //      bit 15 of its first entry; each lane gathers q[col] for its 16 entries from shared memory;
 //   3. ONE segmented warp scan per 64 chunks (6 shuffles) turns lane partials into row scores;
-//   4. rows whose rank key beats the CTA threshold go to a per-warp staging buffer, which is
-//      flushed under a shared-memory lock into the CTA candidate buffer; when that fills, the
-//      flushing warp alone radix-selects it down to k and raises the threshold while the other
-//      31 warps keep streaming;
+//   4. the first rows of a pass are sampled into shared memory and ONE CTA-wide radix select sets the threshold;
+//      afterwards a float pre-filter rejects almost every row, rows whose rank key beats the threshold are appended
+//      to the warp's PRIVATE region with plain stores, and a warp whose region runs low raises a join epoch that all
+//      warps poll: one CTA-wide re-selection, no locks, no per-row atomics (topk.cuh);
 //   5. at the end of the pass the CTA selects its exact top-k and writes k keys to HBM.
 // The [B, N] score matrix is never written.  A second tiny kernel (merge.cu) merges the
 // per-CTA lists.

@@ -475,6 +475,39 @@ class BoTIndex(SparseIndex):
         self._logical_dtype = dtype
         return self
 
+    @classmethod
+    def from_token_ids(cls, token_ids: torch.Tensor, lengths: Optional[torch.Tensor] = None, vocab_size: int = 30522,
+                       num_shift: int = 999, max_token: Optional[int] = None, device="cuda", dtype=torch.float16):
+        """Bag-of-token index straight from tokenizer output (upstream ``Retriever._build_bot_vectors``,
+        retriever.py:208-253): ``token_ids`` ``[N, max_len]`` int32/int64 (padded; ``lengths`` = valid ids per row),
+        row = the distinct ids of the passage (the first ``max_token`` distinct ones when given), ids below
+        ``num_shift`` dropped, the rest renumbered ``id - num_shift``.  Built on the GPU (``vs_bot_from_tokens``):
+        no dense ``[batch, vocab]`` matrix, no COO concatenation."""
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("vsearch_b200 builds and searches on CUDA devices only (no CPU fallback)")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        ids = token_ids.to(dev)
+        if ids.dtype not in (torch.int32, torch.int64):
+            ids = ids.to(torch.int64)
+        ids = ids.contiguous()
+        if ids.dim() != 2:
+            raise ValueError("token_ids must be [N, max_len]")
+        n, ld = ids.shape
+        lens = None if lengths is None else lengths.to(dev, torch.int32).contiguous()
+        crow = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        _sp = _stream_ptr
+        args = (dev.index, ids.data_ptr(), _TORCH2VS[ids.dtype], n, ld, None if lens is None else lens.data_ptr(),
+                int(vocab_size), int(num_shift), int(max_token or 0))
+        with torch.cuda.device(dev):
+            nat.check(nat.LIB.vs_bot_from_tokens(*args, crow[1:].data_ptr() if n else None, None, _sp(dev)))
+            torch.cumsum(crow[1:], 0, out=crow[1:])
+            col = torch.empty(int(crow[-1]) if n else 0, dtype=torch.int32, device=dev)
+            if n:
+                nat.check(nat.LIB.vs_bot_from_tokens(*args, crow.data_ptr(), col.data_ptr(), _sp(dev)))
+        return cls.from_token_csr(crow, col, (n, int(vocab_size) - int(num_shift)), device=dev, dtype=dtype)
+
     def _value_dtype(self):
         if self._vector is None and getattr(self, "_logical_dtype", None) is not None:
             return self._logical_dtype

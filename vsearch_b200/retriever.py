@@ -81,6 +81,12 @@ class Retriever:
         elif not isinstance(index_type, IndexType):
             raise TypeError("index_type must be an instance of IndexType, int, or str.")
         self.index_type = index_type
+        if vectors is None and index_type == IndexType.BAG_OF_TOKEN and getattr(self.encoder_p, "tokenizer", None) is not None:
+            # upstream _build_bot_vectors (retriever.py:208-253): tokenize (max_length 128, truncation), set of token
+            # ids per passage, drop ids < 999.  The tokenizer runs on the host; the rows are built on the GPU.
+            self.index = self._build_bot_index(list(texts), batch_size=batch_size)
+            self.index.data = texts
+            return
         if vectors is None:
             if self.encoder_p is None:
                 raise NotImplementedError("build_index from texts needs an encoder_p; pass vectors= instead")
@@ -100,6 +106,19 @@ class Retriever:
             raise NotImplementedError
         self.index.data = texts
         self.index.move_to_device(self.device)
+
+    def _build_bot_index(self, texts, batch_size: int = 32, max_len: int = 128, max_token=None, num_shift: int = 999):
+        tok = self.encoder_p.tokenizer
+        vocab_size = len(tok.vocab)
+        ids = torch.zeros((len(texts), max_len), dtype=torch.int32)
+        lens = torch.zeros(len(texts), dtype=torch.int32)
+        for b0 in range(0, len(texts), batch_size):
+            for i, row in enumerate(tok(texts[b0:b0 + batch_size], max_length=max_len, truncation=True)["input_ids"]):
+                row = row[:max_len]
+                ids[b0 + i, :len(row)] = torch.as_tensor(row, dtype=torch.int32)
+                lens[b0 + i] = len(row)
+        return BoTIndex.from_token_ids(ids, lens, vocab_size=vocab_size, num_shift=num_shift, max_token=max_token,
+                                       device=self.device, dtype=torch.float16)
 
     def save_index(self, path):
         self.index.save(path)
