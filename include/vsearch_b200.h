@@ -115,6 +115,14 @@ int vs_scores(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int
 int vs_merge_keys(int device, const uint64_t *d_keys_in, int64_t P, int64_t stride_p, int64_t stride_b,
                   int64_t B, int k_in, int k_out, int64_t *d_ids, float *d_scores, void *stream);
 
+/* Rerank stage: scores of GIVEN rows, d_scores[b, j] = <q_b, row d_ids[b, j]> (ids outside [0, N) -> -inf).
+ * Replaces the re-embedding + bmm of the reference's `retrieve(rerank=True)` (src/ir/retriever/retriever.py:137-141)
+ * when the candidates' parametric vectors already sit in a device-resident sparse index: B*k row gathers instead of
+ * an encoder pass.  Sparse / bag-of-token indices.  Workspace >= B * vpad * 4 + 256 bytes (vs_search_workspace_bytes
+ * covers it). */
+int vs_score_rows(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, const int64_t *d_ids, int k,
+                  int score_round, float *d_scores, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* which kernel family (VS_MODE_SCAN | VS_MODE_INVERTED) served the last search on this handle */
 int vs_index_last_mode(const vs_index *idx, int *mode);
 

@@ -143,3 +143,35 @@ def test_bag_of_token_build_from_texts(cuda_device):
     res = r.retrieve(q, k=5)
     assert ref_search.compare_results(ref_search.SearchResults(res.ids, res.scores.float()), ref_search.ref_scores(q, X), 5,
                                       exact=True) is None
+
+
+def test_rerank_with_precomputed_vectors(cuda_device):
+    """First stage on the bag-of-token index, second stage = gather the candidates' parametric rows (vs_score_rows):
+    the same ids/scores as upstream's rerank (retriever.py:137-147) with the re-embedding replaced by row lookups."""
+    import vsearch_b200 as vs
+
+    n, k = 20_000, 50
+    crow, col, val = stratified_csr(n, V, 30, seed=4, grid=True, jitter=10)
+    Xp = ref_search.torch_csr(crow, col, val, (n, V))                      # parametric vectors (valued)
+    Xb = ref_search.torch_csr(crow, col, torch.ones_like(val), (n, V))     # their bag-of-token support
+    r = vs.Retriever(device="cuda:0")
+    r.build_index([f"p{i}" for i in range(n)], index_type="bag_of_token", vectors=Xb)
+    par = vs.SparseIndex()
+    par.vector = Xp
+    par.move_to_device("cuda:0")
+    q = sparse_queries(6, V, 40, seed=8)
+    first = r.retrieve(q, k=k)
+    res = r.retrieve(q, k=k, rerank=True, rerank_index=par)
+    # restated upstream rerank on the same candidates: p_emb = Xp[ids]; bmm with q; sort (ties keep first-stage order)
+    dense_p = Xp.to_dense()
+    cand = first.ids.cpu()
+    sc = torch.einsum("bkv,bv->bk", dense_p[cand], q)
+    order = torch.sort(sc, dim=-1, descending=True, stable=True)
+    assert torch.equal(res.ids.cpu(), torch.gather(cand, 1, order.indices))
+    assert torch.equal(res.scores.float().cpu(), order.values)
+    # ids outside the index score -inf; 1-D query / 1-D ids round-trip
+    bad = par.score_rows(q[:1], torch.tensor([[0, -1, n, 5]]))
+    assert torch.isinf(bad[0, 1]) and torch.isinf(bad[0, 2]) and bad[0, 0] == (dense_p[0] * q[0]).sum()
+    assert par.score_rows(q[0], torch.tensor([3, 4])).shape == (2,)
+    bot_scores = r.index.score_rows(q, first.ids)                          # binary index: recovers the first-stage scores
+    assert torch.equal(bot_scores.float(), first.scores.float())

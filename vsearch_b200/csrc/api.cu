@@ -94,6 +94,44 @@ constexpr double kInvPostingsPerSec = 3.5e11;     // shared-memory atomics, all 
 constexpr double kInvSecPerRow = 1.8e-12;         // zero + select of the block accumulators
 constexpr double kInvFixedSec = 5.0e-6;
 
+
+// ---- score given rows (rerank stage) ---------------------------------------------------------
+// One warp per (query, candidate): the candidate's run of 16-byte chunks in the WS stream (row_chunk[]), lanes stride
+// the chunks, q[col] gathered from the prepared query in global memory (L2-resident), fp32 accumulate.
+__global__ void __launch_bounds__(256) score_rows_kernel(const WsView idx, const float *qprep, int vpad, const int64_t *ids,
+                                                         int64_t n_pairs, int k, int score_round, float *out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t pair = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pair >= n_pairs) return;
+    const int64_t id = ids[pair];
+    if (id < 0 || id >= idx.n_rows) {
+        if (lane == 0) out[pair] = -INFINITY;
+        return;
+    }
+    const float *q = qprep + (pair / k) * (int64_t)vpad;
+    const uint32_t c0 = idx.row_chunk[id], c1 = idx.row_chunk[id + 1];
+    float s = 0.f;
+    for (uint32_t c = c0 + lane; c < c1; c += 32) {
+        const uint4 u = idx.cols[c];
+        const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t col = ((e & 1) ? (wv[e >> 1] >> 16) : (wv[e >> 1] & 0xffffu)) & 0x7fffu;   // bit 15 = row-end flag
+            float v = 1.f;   // binary index; padding entries point at the query's zero slot
+            if (idx.kind == 1) {
+                const uint64_t at = (uint64_t)c * 8ull + e;
+                if (idx.store_dtype == VS_F32) v = ((const float *)idx.vals)[at];
+                else if (idx.store_dtype == VS_F16) v = __half2float(((const __half *)idx.vals)[at]);
+                else v = __bfloat162float(((const __nv_bfloat16 *)idx.vals)[at]);
+            }
+            s += q[col] * v;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) out[pair] = round_score(s, score_round);
+}
+
 }  // namespace vs
 
 using namespace vs;
@@ -334,6 +372,32 @@ int vs_scores(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int
     VS_REQUIRE(d_scores_full != nullptr, VS_ERR_INVALID, "output pointer is NULL");
     return search_impl(idx, hd_q, q_dtype, B, ldq, 1, VS_MODE_SCAN, score_round, 0, nullptr, nullptr, nullptr,
                        d_scores_full, d_workspace, workspace_bytes, stream);
+}
+
+int vs_score_rows(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, const int64_t *d_ids, int k,
+                  int score_round, float *d_scores, void *d_workspace, size_t workspace_bytes, void *stream) {
+    VS_REQUIRE(idx != nullptr && hd_q != nullptr && d_ids != nullptr && d_scores != nullptr, VS_ERR_INVALID, "NULL pointer");
+    VS_REQUIRE(idx->kind != 0, VS_ERR_UNSUPPORTED, "vs_score_rows serves sparse and bag-of-token indices");
+    VS_REQUIRE(B >= 0 && k >= 1 && ldq >= idx->n_cols, VS_ERR_INVALID, "bad query / candidate shape");
+    VS_REQUIRE(q_dtype == VS_F32 || q_dtype == VS_F16 || q_dtype == VS_BF16, VS_ERR_INVALID, "queries must be f32 / f16 / bf16");
+    if (B == 0) return VS_OK;
+    VS_CUDA(cudaSetDevice(idx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vpad = vpad_for(idx->n_cols);
+    void *ws = (void *)(((uintptr_t)d_workspace + 255) / 256 * 256);
+    VS_REQUIRE(d_workspace != nullptr && workspace_bytes >= (size_t)B * vpad * 4 + 256, VS_ERR_INVALID,
+               "workspace too small: vs_score_rows needs B * %d * 4 + 256 bytes", vpad);
+    Staged sq;
+    int rc = sq.init(hd_q, (size_t)B * ldq * dtype_size(q_dtype), st);
+    if (rc) return rc;
+    rc = launch_prep_query(sq.ptr, q_dtype, B, ldq, idx->n_cols, vpad, score_round, (float *)ws, st);
+    if (rc) return rc;
+    const int64_t n_pairs = B * (int64_t)k;
+    score_rows_kernel<<<(unsigned)((n_pairs + 7) / 8), 256, 0, st>>>(ws_view(idx), (const float *)ws, vpad, d_ids, n_pairs, k,
+                                                                    score_round, d_scores);
+    VS_CUDA(cudaGetLastError());
+    if (sq.owned) VS_CUDA(cudaStreamSynchronize(st));   // staging buffer is freed at scope exit
+    return VS_OK;
 }
 
 int vs_merge_keys(int device, const uint64_t *d_keys_in, int64_t P, int64_t stride_p, int64_t stride_b, int64_t B,

@@ -171,6 +171,21 @@ class _Engine:
         nat.check(rc)
         return out
 
+    def score_rows(self, q: torch.Tensor, ids: torch.Tensor, score_round: int = nat.VS_F32) -> torch.Tensor:
+        """scores[b, j] = <q_b, row ids[b, j]> (rerank stage, upstream retriever.py:137-141)."""
+        q = self._prep_q(q)
+        ids = ids.to(self.device, torch.int64).contiguous()
+        if ids.dim() != 2 or ids.shape[0] != q.shape[0]:
+            raise ValueError("ids must be [B, k] with one row per query")
+        B, k = ids.shape
+        out = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            ws = self.workspace(B, 1)
+            rc = nat.LIB.vs_score_rows(self.handle, q.data_ptr(), _TORCH2VS[q.dtype], B, q.stride(0), ids.data_ptr(), k,
+                                       score_round, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
+        nat.check(rc)
+        return out
+
     def export_csr(self):
         crow = torch.empty(self.n_rows + 1, dtype=torch.int64, device=self.device)
         col = torch.empty(self.nnz, dtype=torch.int64, device=self.device)
@@ -340,6 +355,14 @@ class Index:
         m = ctypes.c_int()
         nat.check(nat.LIB.vs_index_last_mode(self._require_engine().handle, m))
         return "inverted" if m.value == nat.VS_MODE_INVERTED else "scan"
+
+    def score_rows(self, q_embs: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+        """``scores[b, j] = <q_b, vector[ids[b, j]]>`` in the index dtype: the re-scoring half of upstream's
+        ``retrieve(rerank=True)`` (retriever.py:137-141) for candidates whose vectors live in this index."""
+        eng = self._require_engine()
+        q = q_embs.unsqueeze(0) if q_embs.dim() == 1 else q_embs
+        ids2 = ids.reshape(q.shape[0], -1)
+        return eng.score_rows(q, ids2, score_round=self._score_round()).to(self._value_dtype()).reshape(ids.shape)
 
     def search_keys(self, q_embs: torch.Tensor, k: int, id_offset: int = 0) -> torch.Tensor:
         """Packed rank keys ``[B, k]`` of this shard with global ids (row-sharded path, sharded.py)."""

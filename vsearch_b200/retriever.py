@@ -47,17 +47,34 @@ class Retriever:
         return q_emb
 
     def retrieve(self, queries, k: int = 5, dropout: float = 0, a: Optional[int] = None,
-                 index: Optional[Index] = None, rerank: bool = False, batch_size: int = 32) -> SearchResults:
+                 index: Optional[Index] = None, rerank: bool = False, batch_size: int = 32,
+                 rerank_index: Optional[Index] = None) -> SearchResults:
+        """``rerank_index`` (extension): a device-resident sparse index holding the passages' parametric vectors, row
+        for row with the bag-of-token index.  With it the rerank stage re-scores the k candidates by gathering their
+        rows on the GPU instead of re-embedding their texts (upstream retriever.py:137-147)."""
         index = index if index is not None else self.index  # upstream resolves this, then ignores it (:133,136)
         if index is None:
             raise RuntimeError("no index: call build_index() or load_index() first")
         q_emb = self.process_query(queries, dropout, a, batch_size=batch_size)
         results = index.search(q_emb, k=k)
         if rerank and index.index_type == IndexType.BAG_OF_TOKEN:
-            if self.encoder_p is None:
-                raise NotImplementedError("rerank needs an encoder_p to re-embed the retrieved passages")
-            results = self._rerank(index, q_emb, results, k, batch_size)
+            if rerank_index is not None:
+                results = self._rerank_rows(rerank_index, q_emb, results)
+            elif self.encoder_p is None:
+                raise NotImplementedError("rerank needs an encoder_p to re-embed the retrieved passages, or a rerank_index")
+            else:
+                results = self._rerank(index, q_emb, results, k, batch_size)
         return results
+
+    @staticmethod
+    def _rerank_rows(rerank_index, q_emb, results):
+        """Re-score the candidates against their precomputed vectors (``vs_score_rows``), re-sort (stable: equal scores
+        keep the first-stage order)."""
+        ids = results.ids.reshape(-1, results.ids.shape[-1])
+        sc = rerank_index.score_rows(q_emb.reshape(ids.shape[0], -1), ids)
+        order = torch.sort(sc.float(), dim=-1, descending=True, stable=True)
+        new_ids = torch.gather(ids, 1, order.indices).reshape(results.ids.shape)
+        return SearchResults(new_ids, torch.gather(sc, 1, order.indices).reshape(results.ids.shape))
 
     def _rerank(self, index, q_emb, results, k, batch_size):
         """upstream retriever.py:137-147: re-embed the k texts, dot with the query, re-sort."""
