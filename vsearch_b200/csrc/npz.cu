@@ -13,6 +13,7 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <new>
 #include <string>
 #include <vector>
 
@@ -189,9 +190,9 @@ bool convert_run_half(const __half *src, size_t n, void *dst, int dd, size_t at)
 
 }  // namespace
 
-extern "C" {
+namespace {
 
-int vs_npz_open(const char *path, vs_npz **out) {
+int npz_open_impl(const char *path, vs_npz **out) {
     NPZ_REQUIRE(path && out, VS_ERR_INVALID, "vs_npz_open: NULL argument");
     File fh;
     fh.f = fopen(path, "rb");
@@ -250,12 +251,7 @@ int vs_npz_open(const char *path, vs_npz **out) {
     return VS_OK;
 }
 
-int vs_npz_close(vs_npz *z) {
-    delete z;
-    return VS_OK;
-}
-
-int vs_npz_member_info(vs_npz *z, const char *name, int *dtype, int *ndim, int64_t *shape4, int64_t *n_elems) {
+int npz_member_info_impl(vs_npz *z, const char *name, int *dtype, int *ndim, int64_t *shape4, int64_t *n_elems) {
     NPZ_REQUIRE(z && name, VS_ERR_INVALID, "vs_npz_member_info: NULL argument");
     NpzMember *m = find_member(z, name);
     NPZ_REQUIRE(m, VS_ERR_INVALID, "%s: no member %s", z->path.c_str(), name);
@@ -270,7 +266,7 @@ int vs_npz_member_info(vs_npz *z, const char *name, int *dtype, int *ndim, int64
     return VS_OK;
 }
 
-int vs_npz_read(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t skip_elems, int64_t n_elems, int64_t add_offset) {
+int npz_read_impl(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t skip_elems, int64_t n_elems, int64_t add_offset) {
     NPZ_REQUIRE(z && name && (dst || n_elems == 0), VS_ERR_INVALID, "vs_npz_read: NULL argument");
     NpzMember *m = find_member(z, name);
     NPZ_REQUIRE(m, VS_ERR_INVALID, "%s: no member %s", z->path.c_str(), name);
@@ -341,6 +337,37 @@ int vs_npz_read(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t s
     NPZ_REQUIRE((int64_t)written == n_elems, VS_ERR_INVALID, "%s: member %s ended after %lld of %lld elements", z->path.c_str(), name,
                 (long long)written, (long long)n_elems);
     return VS_OK;
+}
+
+}  // namespace
+
+// The ABI never throws: allocation failures inside the readers come back as VS_ERR_NOMEM.
+#define NPZ_NOTHROW(expr)                                                    \
+    try {                                                                    \
+        return (expr);                                                       \
+    } catch (const std::bad_alloc &) {                                       \
+        vs::set_error("out of host memory in the .npz reader");              \
+        return VS_ERR_NOMEM;                                                 \
+    } catch (...) {                                                          \
+        vs::set_error("unexpected C++ exception in the .npz reader");        \
+        return VS_ERR_INVALID;                                               \
+    }
+
+extern "C" {
+
+int vs_npz_open(const char *path, vs_npz **out) { NPZ_NOTHROW(npz_open_impl(path, out)) }
+
+int vs_npz_close(vs_npz *z) {
+    delete z;
+    return VS_OK;
+}
+
+int vs_npz_member_info(vs_npz *z, const char *name, int *dtype, int *ndim, int64_t *shape4, int64_t *n_elems) {
+    NPZ_NOTHROW(npz_member_info_impl(z, name, dtype, ndim, shape4, n_elems))
+}
+
+int vs_npz_read(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t skip_elems, int64_t n_elems, int64_t add_offset) {
+    NPZ_NOTHROW(npz_read_impl(z, name, dst, dst_dtype, skip_elems, n_elems, add_offset))
 }
 
 }  // extern "C"
