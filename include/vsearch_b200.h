@@ -166,6 +166,17 @@ int vs_npz_member_info(vs_npz *z, const char *name, int *dtype, int *ndim, int64
 int vs_npz_read(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t skip_elems, int64_t n_elems,
                 int64_t add_offset);
 
+/* Writer: a zip of deflated .npy members, byte-compatible with scipy.sparse.save_npz / numpy.savez_compressed
+ * (reference SparseIndex.save, index.py:195-197), compressed by `threads` threads (independent 4 MB deflate blocks
+ * concatenated into one valid stream).  The caller supplies each member's .npy header bytes (numpy.lib.format) and
+ * its raw C-order data; members are written in the order given.  ZIP64 when a member or offset needs it. */
+typedef struct vs_npz_member_in {
+    const char *name;            /* without ".npy" */
+    const void *header; int64_t header_bytes;
+    const void *data; int64_t data_bytes;
+} vs_npz_member_in;
+int vs_npz_write(const char *path, const vs_npz_member_in *members, int n_members, int level, int threads);
+
 #ifdef __cplusplus
 }
 #endif

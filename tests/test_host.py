@@ -174,3 +174,30 @@ def test_native_npz_reader_matches_numpy_reader(tmp_path):
     bad.write_bytes(b"not a zip archive at all" * 10)
     with pytest.raises(ValueError):
         npz_io.load_csr_shards_native([str(bad)])
+
+
+def test_native_npz_writer_is_scipy_loadable(tmp_path):
+    """vs_npz_write (parallel block deflate, csrc/npz.cu): same members, order, dtypes and contents as
+    scipy.sparse.save_npz; zipfile's CRC check passes; scipy, numpy and the native reader load it; multi-block members."""
+    rng = np.random.default_rng(1)
+    n, m = 60_000, 40                                   # data member = 9.6 MB -> three 4 MB deflate blocks
+    cols = (np.arange(m) * 29523 // m)[None, :] + rng.integers(0, 29523 // m, (n, m))
+    M = sp.csr_array((rng.random(n * m, dtype=np.float32), cols.reshape(-1).astype(np.int32),
+                      np.arange(n + 1, dtype=np.int32) * m), shape=(n, 29523))
+    ref, mine = str(tmp_path / "ref.npz"), str(tmp_path / "mine.npz")
+    sp.save_npz(ref, M)
+    npz_io.save_csr_npz_native(mine, M.indptr, M.indices, M.data, M.shape, threads=3)
+    with zipfile.ZipFile(ref) as a, zipfile.ZipFile(mine) as b:
+        assert [i.filename for i in a.infolist()] == [i.filename for i in b.infolist()]
+        assert all(i.compress_type == zipfile.ZIP_DEFLATED for i in b.infolist())
+        assert b.testzip() is None
+    za, zb = np.load(ref), np.load(mine)
+    for k in za.files:
+        assert za[k].dtype == zb[k].dtype and np.array_equal(za[k], zb[k]), k
+    assert (sp.load_npz(mine) != M).nnz == 0
+    back = npz_io.load_csr_shards_native([mine])
+    assert np.array_equal(back[1], M.indices) and np.array_equal(back[2], M.data)
+    tiny = str(tmp_path / "tiny")                       # suffix appended like numpy; empty matrix; fp16 / int64
+    npz_io.save_csr_npz_native(tiny, np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float16), (0, 7))
+    z = np.load(tiny + ".npz")
+    assert z["indices"].size == 0 and z["data"].dtype == np.float16 and z["shape"].tolist() == [0, 7]

@@ -24,8 +24,13 @@ SYMBOLS = [
     "vs_last_error", "vs_abi_version", "vs_index_create_csr", "vs_index_create_dense", "vs_index_destroy",
     "vs_index_info", "vs_index_export_csr", "vs_search_workspace_bytes", "vs_search", "vs_search_keys",
     "vs_scores", "vs_merge_keys", "vs_kernel_timer", "vs_index_last_mode",
-    "vs_npz_open", "vs_npz_close", "vs_npz_member_info", "vs_npz_read", "vs_bot_from_tokens", "vs_score_rows",
+    "vs_npz_open", "vs_npz_close", "vs_npz_member_info", "vs_npz_read", "vs_bot_from_tokens", "vs_score_rows", "vs_npz_write",
 ]
+
+
+class NpzMemberIn(ctypes.Structure):
+    _fields_ = [("name", c_char_p), ("header", c_void_p), ("header_bytes", c_int64), ("data", c_void_p),
+                ("data_bytes", c_int64)]
 
 
 class NativeLibraryMissing(ImportError):
@@ -65,6 +70,7 @@ def _load() -> ctypes.CDLL:
                                   c_size_t, c_void_p]
     lib.vs_bot_from_tokens.argtypes = [c_int, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p]
+    lib.vs_npz_write.argtypes = [c_char_p, c_void_p, c_int, c_int, c_int]
     lib.vs_npz_open.argtypes = [c_char_p, POINTER(c_void_p)]
     lib.vs_npz_close.argtypes = [c_void_p]
     lib.vs_npz_member_info.argtypes = [c_void_p, c_char_p, POINTER(c_int), POINTER(c_int), POINTER(c_int64), POINTER(c_int64)]

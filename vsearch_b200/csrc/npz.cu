@@ -371,3 +371,194 @@ int vs_npz_read(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t s
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Writer: a zip of deflated `.npy` members (what scipy.sparse.save_npz / numpy.savez_compressed produce,
+// reference index.py:195-197), compressed by a thread pool.  A member's bytes (the .npy header the caller built +
+// the array data) are cut into 4 MB blocks; every block is deflated independently (raw deflate, Z_SYNC_FLUSH, the
+// last one Z_FINISH) and the pieces are concatenated in order: sync-flushed deflate blocks end byte-aligned without
+// the final bit, so the concatenation is ONE valid deflate stream that zipfile / scipy / upstream's loader inflate as
+// usual (the pigz construction).  CRC-32 per block, combined in order.  ZIP64 records for members or offsets >= 4 GB.
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+namespace {
+
+constexpr size_t kWriteBlock = 4u << 20;
+
+struct OutBlock {
+    std::vector<uint8_t> comp;
+    uint32_t crc = 0;
+    size_t raw = 0;
+    bool done = false;
+};
+
+void put16(std::vector<uint8_t> &v, uint16_t x) { v.push_back((uint8_t)x); v.push_back((uint8_t)(x >> 8)); }
+void put32(std::vector<uint8_t> &v, uint32_t x) { for (int i = 0; i < 4; ++i) v.push_back((uint8_t)(x >> (8 * i))); }
+void put64(std::vector<uint8_t> &v, uint64_t x) { for (int i = 0; i < 8; ++i) v.push_back((uint8_t)(x >> (8 * i))); }
+
+// byte `at` of the member = header bytes followed by data bytes
+void copy_span(const vs_npz_member_in &m, uint64_t at, size_t n, uint8_t *dst) {
+    size_t done = 0;
+    if (at < (uint64_t)m.header_bytes) {
+        const size_t h = (size_t)std::min<uint64_t>(n, (uint64_t)m.header_bytes - at);
+        memcpy(dst, (const uint8_t *)m.header + at, h);
+        done = h;
+    }
+    if (done < n) memcpy(dst + done, (const uint8_t *)m.data + (at + done - (uint64_t)m.header_bytes), n - done);
+}
+
+bool deflate_block(const uint8_t *src, size_t n, bool last, int level, std::vector<uint8_t> &out) {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (deflateInit2(&zs, level, Z_DEFLATED, -MAX_WBITS, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    out.resize(deflateBound(&zs, (uLong)n) + 16);
+    zs.next_in = const_cast<uint8_t *>(src);
+    zs.avail_in = (uInt)n;
+    zs.next_out = out.data();
+    zs.avail_out = (uInt)out.size();
+    const int rc = deflate(&zs, last ? Z_FINISH : Z_SYNC_FLUSH);
+    const bool ok = last ? rc == Z_STREAM_END : (rc == Z_OK && zs.avail_in == 0);
+    out.resize(out.size() - zs.avail_out);
+    deflateEnd(&zs);
+    return ok;
+}
+
+int npz_write_impl(const char *path, const vs_npz_member_in *members, int n_members, int level, int threads) {
+    NPZ_REQUIRE(path && members && n_members > 0, VS_ERR_INVALID, "vs_npz_write: bad argument");
+    if (threads < 1) threads = 1;
+    if (level < 0 || level > 9) level = 6;
+    File fh;
+    fh.f = fopen(path, "wb");
+    NPZ_REQUIRE(fh.f, VS_ERR_INVALID, "%s: cannot create", path);
+    struct Entry { std::string name; uint32_t crc; uint64_t comp, raw, off; bool z64; };
+    std::vector<Entry> dir;
+    for (int mi = 0; mi < n_members; ++mi) {
+        const vs_npz_member_in &m = members[mi];
+        NPZ_REQUIRE(m.name && m.header_bytes >= 0 && m.data_bytes >= 0 && (m.header || m.header_bytes == 0) && (m.data || m.data_bytes == 0),
+                    VS_ERR_INVALID, "vs_npz_write: bad member %d", mi);
+        Entry e;
+        e.name = std::string(m.name) + ".npy";
+        e.raw = (uint64_t)m.header_bytes + (uint64_t)m.data_bytes;
+        e.off = (uint64_t)ftello(fh.f);
+        e.z64 = e.raw >= 0x7fffffffull || e.off >= 0x7fffffffull;
+        e.crc = 0; e.comp = 0;
+        // local header (sizes patched after the data is written)
+        std::vector<uint8_t> lh;
+        put32(lh, 0x04034b50u); put16(lh, e.z64 ? 45 : 20); put16(lh, 0); put16(lh, 8); put16(lh, 0); put16(lh, 0x21);
+        put32(lh, 0); put32(lh, 0); put32(lh, 0);
+        put16(lh, (uint16_t)e.name.size()); put16(lh, e.z64 ? 20 : 0);
+        lh.insert(lh.end(), e.name.begin(), e.name.end());
+        if (e.z64) { put16(lh, 1); put16(lh, 16); put64(lh, 0); put64(lh, 0); }
+        NPZ_REQUIRE(fwrite(lh.data(), 1, lh.size(), fh.f) == lh.size(), VS_ERR_INVALID, "%s: write failed", path);
+        // parallel deflate, in-order write
+        const uint64_t n_blocks = e.raw == 0 ? 1 : (e.raw + kWriteBlock - 1) / kWriteBlock;
+        const uint64_t window = (uint64_t)threads * 2;
+        std::vector<OutBlock> ring((size_t)window);
+        std::mutex mu;
+        std::condition_variable cv;
+        uint64_t next_claim = 0, next_write = 0;
+        bool failed = false;
+        auto worker = [&]() {
+            std::vector<uint8_t> raw(kWriteBlock);
+            for (;;) {
+                uint64_t b;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return failed || next_claim >= n_blocks || next_claim < next_write + window; });
+                    if (failed || next_claim >= n_blocks) return;
+                    b = next_claim++;
+                }
+                const uint64_t at = b * kWriteBlock;
+                const size_t n = (size_t)std::min<uint64_t>(kWriteBlock, e.raw - at);
+                copy_span(m, at, n, raw.data());
+                OutBlock ob;
+                ob.raw = n;
+                ob.crc = (uint32_t)crc32(0L, raw.data(), (uInt)n);
+                const bool ok = deflate_block(raw.data(), n, b + 1 == n_blocks, level, ob.comp);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (!ok) failed = true;
+                    ob.done = true;
+                    ring[(size_t)(b % window)] = std::move(ob);
+                }
+                cv.notify_all();
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+        bool io_ok = true;
+        while (next_write < n_blocks) {
+            OutBlock ob;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return failed || ring[(size_t)(next_write % window)].done; });
+                if (failed) break;
+                ob = std::move(ring[(size_t)(next_write % window)]);
+                ring[(size_t)(next_write % window)] = OutBlock();
+            }
+            if (fwrite(ob.comp.data(), 1, ob.comp.size(), fh.f) != ob.comp.size()) io_ok = false;
+            e.crc = next_write == 0 ? ob.crc : (uint32_t)crc32_combine(e.crc, ob.crc, (z_off_t)ob.raw);
+            e.comp += ob.comp.size();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ++next_write;
+                if (!io_ok) failed = true;
+            }
+            cv.notify_all();
+            if (!io_ok) break;
+        }
+        { std::lock_guard<std::mutex> lk(mu); if (next_write < n_blocks) failed = true; }
+        cv.notify_all();
+        for (auto &t : pool) t.join();
+        NPZ_REQUIRE(!failed, VS_ERR_INVALID, "%s: compressing or writing member %s failed", path, m.name);
+        // patch the local header
+        const uint64_t end = (uint64_t)ftello(fh.f);
+        std::vector<uint8_t> fix;
+        put32(fix, e.crc);
+        if (e.z64) { put32(fix, 0xffffffffu); put32(fix, 0xffffffffu); } else { put32(fix, (uint32_t)e.comp); put32(fix, (uint32_t)e.raw); }
+        NPZ_REQUIRE(fseeko(fh.f, (off_t)(e.off + 14), SEEK_SET) == 0 && fwrite(fix.data(), 1, fix.size(), fh.f) == fix.size(), VS_ERR_INVALID,
+                    "%s: write failed", path);
+        if (e.z64) {
+            std::vector<uint8_t> x;
+            put64(x, e.raw); put64(x, e.comp);
+            NPZ_REQUIRE(fseeko(fh.f, (off_t)(e.off + 30 + e.name.size() + 4), SEEK_SET) == 0 && fwrite(x.data(), 1, 16, fh.f) == 16, VS_ERR_INVALID,
+                        "%s: write failed", path);
+        }
+        NPZ_REQUIRE(fseeko(fh.f, (off_t)end, SEEK_SET) == 0, VS_ERR_INVALID, "%s: seek failed", path);
+        dir.push_back(e);
+    }
+    // central directory
+    const uint64_t cd_off = (uint64_t)ftello(fh.f);
+    std::vector<uint8_t> cd;
+    for (const Entry &e : dir) {
+        const bool z64 = e.z64 || e.comp >= 0xffffffffull;
+        put32(cd, 0x02014b50u); put16(cd, 45); put16(cd, z64 ? 45 : 20); put16(cd, 0); put16(cd, 8); put16(cd, 0); put16(cd, 0x21);
+        put32(cd, e.crc);
+        put32(cd, z64 ? 0xffffffffu : (uint32_t)e.comp); put32(cd, z64 ? 0xffffffffu : (uint32_t)e.raw);
+        put16(cd, (uint16_t)e.name.size()); put16(cd, z64 ? 28 : 0); put16(cd, 0); put16(cd, 0); put16(cd, 0);
+        put32(cd, 0x01800000u);   // external attributes: regular file 0600, like numpy
+        put32(cd, z64 ? 0xffffffffu : (uint32_t)e.off);
+        cd.insert(cd.end(), e.name.begin(), e.name.end());
+        if (z64) { put16(cd, 1); put16(cd, 24); put64(cd, e.raw); put64(cd, e.comp); put64(cd, e.off); }
+    }
+    const uint64_t cd_size = cd.size();
+    const bool big = cd_off >= 0xffffffffull || dir.size() >= 0xffff;
+    if (big) {
+        put32(cd, 0x06064b50u); put64(cd, 44); put16(cd, 45); put16(cd, 45); put32(cd, 0); put32(cd, 0);
+        put64(cd, dir.size()); put64(cd, dir.size()); put64(cd, cd_size); put64(cd, cd_off);
+        put32(cd, 0x07064b50u); put32(cd, 0); put64(cd, cd_off + cd_size); put32(cd, 1);
+    }
+    put32(cd, 0x06054b50u); put16(cd, 0); put16(cd, 0);
+    put16(cd, big ? 0xffff : (uint16_t)dir.size()); put16(cd, big ? 0xffff : (uint16_t)dir.size());
+    put32(cd, big ? 0xffffffffu : (uint32_t)cd_size); put32(cd, big ? 0xffffffffu : (uint32_t)cd_off); put16(cd, 0);
+    NPZ_REQUIRE(fwrite(cd.data(), 1, cd.size(), fh.f) == cd.size() && fflush(fh.f) == 0, VS_ERR_INVALID, "%s: write failed", path);
+    return VS_OK;
+}
+
+}  // namespace
+
+extern "C" int vs_npz_write(const char *path, const vs_npz_member_in *members, int n_members, int level, int threads) {
+    NPZ_NOTHROW(npz_write_impl(path, members, n_members, level, threads))
+}

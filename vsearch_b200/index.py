@@ -465,12 +465,13 @@ class SparseIndex(Index):
     def save(self, path):
         """scipy-loadable ``.npz`` (upstream index.py:181-202)."""
         try:
-            from .npz_io import save_csr_npz
+            from .npz_io import save_csr_npz_native
 
             crow, col, val, shape = self._csr_parts() if self._vector is not None else (*self._engine.export_csr(), self._shape())
             if val.dtype == torch.bfloat16:
                 val = val.to(torch.float32)  # numpy has no bfloat16
-            save_csr_npz(path, crow.cpu().numpy(), col.cpu().numpy(), val.cpu().numpy(), tuple(shape))
+            # same members / order / dtypes as scipy.sparse.save_npz, deflated by a thread pool (csrc/npz.cu)
+            save_csr_npz_native(path, crow.cpu().numpy(), col.cpu().numpy(), val.cpu().numpy(), tuple(shape))
             logger.info("Index successfully saved to %s", path)
         except Exception as e:  # noqa: BLE001
             logger.error("Failed to save index to %s: %s", path, e)

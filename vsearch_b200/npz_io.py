@@ -159,6 +159,34 @@ def load_csr_shards_native(files: Sequence[str], fp16: bool = False, threads: in
             sh.close()
 
 
+def save_csr_npz_native(path: str, indptr: np.ndarray, indices: np.ndarray, data: np.ndarray, shape,
+                        threads: int | None = None, level: int = 6) -> None:
+    """Same file as :func:`save_csr_npz` (members, order, dtypes, deflate), written by ``vs_npz_write``: every member
+    is deflated by a thread pool (independent 4 MB blocks concatenated into one valid stream), so saving a 21M-row
+    index is no longer one zlib thread."""
+    import io
+
+    from . import _native as nat
+
+    if not path.endswith(".npz"):
+        path += ".npz"   # numpy / scipy append the suffix too
+    arrays = [("indices", np.ascontiguousarray(indices)), ("indptr", np.ascontiguousarray(indptr)),
+              ("format", np.array(b"csr")), ("shape", np.asarray(shape, dtype=np.int64)),
+              ("data", np.ascontiguousarray(data)), ("_is_array", np.array(True))]
+    keep, members = [], (nat.NpzMemberIn * len(arrays))()
+    for i, (name, arr) in enumerate(arrays):
+        buf = io.BytesIO()
+        np.lib.format.write_array_header_1_0(buf, np.lib.format.header_data_from_array_1_0(arr))
+        hdr = buf.getvalue()
+        keep.append((hdr, arr))
+        members[i].name = name.encode()
+        members[i].header = ctypes.cast(ctypes.c_char_p(hdr), ctypes.c_void_p)
+        members[i].header_bytes = len(hdr)
+        members[i].data = arr.ctypes.data_as(ctypes.c_void_p) if arr.nbytes else None
+        members[i].data_bytes = arr.nbytes
+    nat.check(nat.LIB.vs_npz_write(os.fsencode(path), members, len(arrays), level, threads or min(16, os.cpu_count() or 1)))
+
+
 def save_csr_npz(path: str, indptr: np.ndarray, indices: np.ndarray, data: np.ndarray, shape) -> None:
     """Write what ``scipy.sparse.save_npz(path, csr_array(...))`` writes (compressed)."""
     np.savez_compressed(
