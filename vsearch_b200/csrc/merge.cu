@@ -34,7 +34,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
     __shared__ uint32_t sel_cnt;
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t b = blockIdx.x;
-    const int64_t n = p.P * p.k_in;
+    // a single counted list (the dense path's candidate lists: capacity 65,536, a few thousand valid): walk only the
+    // valid prefix -- the capacity-sized loop was 11 of the 25 ms of a dense call on a 2.6M-row shard
+    const int64_t n = (p.P == 1 && p.counts != nullptr) ? min((int64_t)p.counts[b], (int64_t)p.k_in) : p.P * p.k_in;
 
     // ---- radix-select the k_out-th largest key, streaming the lists from L2/HBM
     uint64_t prefix = 0, mask = 0;
