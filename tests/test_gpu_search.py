@@ -404,3 +404,47 @@ def test_bot_index_from_token_ids(max_token, cuda_device):
     ids32 = vs.BoTIndex.from_token_ids(ids.to(torch.int32), None, vocab_size=vocab, num_shift=shift, max_token=max_token)
     full, _, _ = ref_search.ref_bot_rows(ids.tolist(), vocab, shift, max_token)
     assert torch.equal(ids32.vector.cpu().crow_indices().to(torch.int64), full)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_pathological_rows_for_the_bank_placement(dtype, cuda_device):
+    """Rows the build-time bank placement cannot balance, mixed with ordinary ones: a 20,000-entry row (spans ~40
+    steps), rows whose columns all fall in ONE shared-memory bank (multiples of 32), duplicate columns inside a row,
+    empty rows, a single-entry row -- through the scan and the inverted lists, fp32 (one chunk per lane) and fp16
+    (two chunks per lane) value layouts, against the reference."""
+    g = torch.Generator().manual_seed(21)
+    rows = []
+    for i in range(400):
+        kind = i % 8
+        if i == 7:
+            c = torch.randperm(V, generator=g)[:20_000].sort().values          # very long row
+        elif kind == 1:
+            c = (torch.randperm(V // 32, generator=g)[:150] * 32).sort().values  # one bank
+        elif kind == 2:
+            c = torch.randint(0, 40, (60,), generator=g).sort().values          # duplicates (CSR sums them)
+        elif kind == 3:
+            c = torch.zeros(0, dtype=torch.int64)                               # empty
+        elif kind == 4:
+            c = torch.randint(0, V, (1,), generator=g)
+        else:
+            c = torch.randperm(V, generator=g)[:int(torch.randint(1, 300, (1,), generator=g))].sort().values
+        rows.append(c)
+    lens = torch.tensor([r.numel() for r in rows])
+    crow = torch.zeros(len(rows) + 1, dtype=torch.int64)
+    crow[1:] = torch.cumsum(lens, 0)
+    col = torch.cat(rows)
+    val = torch.randint(1, 64, (col.numel(),), generator=g).float() / 16.0     # exact in fp16
+    X = ref_search.torch_csr(crow, col, val, (len(rows), V))
+    idx = _mk("SparseIndex", crow, col, val, (len(rows), V), dtype=dtype)
+    q = sparse_queries(5, V, 400, seed=12)
+    q[1, ::32] = 0.5                                                            # hits the one-bank rows hard
+    q[2, :40] = 1.0
+    ref = ref_search.ref_scores(q, X)
+    for mode in ("scan", "inverted"):
+        idx.search_mode = mode
+        res = idx.search(q, 50)
+        assert idx.last_mode() == mode
+        msg = ref_search.compare_results(ref_search.SearchResults(res.ids, res.scores.float()),
+                                         ref_search.quantize_like(ref, dtype), 50, exact=True)
+        assert msg is None, f"{mode}: {msg}"
