@@ -133,6 +133,15 @@ int vs_index_last_mode(const vs_index *idx, int *mode);
 #define VS_TIMER_SLOTS 256
 int vs_kernel_timer(vs_index *idx, int reset, float *total_ms, int *launches);
 
+/* ---- query sparsifier ---------------------------------------------------------------------------------------------
+ * In place on a device fp32 batch d_q [B, ld]: keep the k largest of the first n_cols entries of every row (ties ->
+ * lower column) and zero the rest -- upstream utils/sparse.py:8-19 (build_topk_mask / topk_sparsify), the `a=768`
+ * activation budget of retrieve (retriever.py:134).  d_bow_ids (optional, int32 [B, bow_ld], values id - bow_shift
+ * outside [0, n_cols) ignored): the row's own token columns survive as well, the logical_or(bow_mask, topk_mask) of
+ * encoder/vdr.py:159-169.  k = 0 keeps only those; k >= n_cols keeps everything. */
+int vs_sparsify_topk(int device, float *d_q, int64_t B, int64_t ld, int n_cols, int k, const int32_t *d_bow_ids, int bow_ld,
+                     int bow_shift, void *stream);
+
 /* ---- bag-of-token rows from token-id batches, on the GPU -----------------------------------------------------------
  * Replaces Retriever._build_bot_vectors (reference src/ir/retriever/retriever.py:208-253: dense [batch, vocab]
  * scatter of ones, `[:, num_shift:]`, to_sparse_coo / cat / to_sparse_csr).  Row r of the result = the distinct

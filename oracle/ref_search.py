@@ -220,3 +220,23 @@ def ref_bot_rows(token_lists, vocab_size=30522, num_shift=999, max_token=None):
             emb[i, ids] = 1
     csr = emb[:, num_shift:].to_sparse_coo().to_sparse_csr()
     return csr.crow_indices().to(torch.int64), csr.col_indices().to(torch.int64), (n, vocab_size - num_shift)
+
+
+def ref_topk_sparsify(emb: torch.Tensor, k: int, bow_ids=None, shift: int = 0) -> torch.Tensor:
+    """Restates upstream utils/sparse.py:8-19 (topk -> scatter a bool mask -> multiply) with the logical_or of the
+    row's own token columns (encoder/vdr.py:159-169); ties at the k-th value go to the lower column (upstream's
+    torch.topk leaves them arbitrary)."""
+    emb = emb.to(torch.float32)
+    B, V = emb.shape
+    mask = torch.zeros_like(emb, dtype=torch.bool)
+    if k >= V:
+        mask[:] = True
+    elif k > 0:
+        order = torch.sort(emb + 0.0, dim=-1, descending=True, stable=True).indices[:, :k]   # stable: lower column first
+        mask.scatter_(-1, order, True)
+    if bow_ids is not None:
+        for b in range(B):
+            for t in bow_ids[b].tolist():
+                if 0 <= t - shift < V:
+                    mask[b, t - shift] = True
+    return emb * mask

@@ -448,3 +448,32 @@ def test_pathological_rows_for_the_bank_placement(dtype, cuda_device):
         msg = ref_search.compare_results(ref_search.SearchResults(res.ids, res.scores.float()),
                                          ref_search.quantize_like(ref, dtype), 50, exact=True)
         assert msg is None, f"{mode}: {msg}"
+
+
+@pytest.mark.gpu
+def test_topk_sparsify_matches_reference(cuda_device):
+    """vs_sparsify_topk against the restated upstream sparsifier (utils/sparse.py:8-19, vdr.py:159-169): continuous
+    activations, heavy ties at the k-th value, k = 0 / k >= V, the lexical OR, then a search with the sparse queries."""
+    import vsearch_b200 as vs
+
+    g = torch.Generator().manual_seed(3)
+    emb = torch.rand(6, V, generator=g) * 3
+    emb[1] = torch.randint(0, 4, (V,), generator=g).float()          # thousands of ties at the threshold
+    emb[2, 100:] = 0                                                  # fewer non-zeros than k
+    emb[3] = -emb[3]                                                  # negative activations
+    bow = torch.randint(0, V + 999, (6, 40), generator=g, dtype=torch.int32)
+    for k in (768, 1, 0, V, V + 5):
+        got = vs.topk_sparsify(emb.cuda(), k).cpu()
+        assert torch.equal(got, ref_search.ref_topk_sparsify(emb, k)), k
+        assert int((got[0] != 0).sum()) == min(k, V)
+        got = vs.topk_sparsify(emb.cuda(), k, bow_ids=bow, shift=999).cpu()
+        assert torch.equal(got, ref_search.ref_topk_sparsify(emb, k, bow, 999)), k
+    assert vs.topk_sparsify(emb[0].cuda(), 10).shape == (V,)
+    crow, col, val = stratified_csr(20_000, V, 40, seed=6, grid=True, binary=True)
+    idx = _mk("BoTIndex", crow, col, val, (20_000, V))
+    q = vs.topk_sparsify(emb.cuda(), 768)
+    idx.search_mode = "inverted"                                     # 768 non-zeros per query: inverted lists apply
+    res = idx.search(q, 20)
+    assert idx.last_mode() == "inverted"
+    X = ref_search.torch_csr(crow, col, val, (20_000, V))
+    assert ref_search.compare_results(res, ref_search.ref_scores(q.cpu(), X), 20, rtol=1e-5, exact=False) is None

@@ -1,8 +1,8 @@
 """vsearch_b200 -- B200-native engine for vsearch's index-scoring hot path
 (``Retriever.retrieve`` -> ``Index.search`` -> top-k).  See DESIGN.md."""
-from .index import BoTIndex, Index, IndexType, SearchResults, SparseIndex, merge_keys  # noqa: F401
+from .index import BoTIndex, Index, IndexType, SearchResults, SparseIndex, merge_keys, topk_sparsify  # noqa: F401
 from .retriever import Retriever  # noqa: F401
 from .sharded import ShardedIndex, row_partition  # noqa: F401
 
-__all__ = ["Retriever", "Index", "SparseIndex", "BoTIndex", "IndexType", "SearchResults", "ShardedIndex",
+__all__ = ["topk_sparsify", "Retriever", "Index", "SparseIndex", "BoTIndex", "IndexType", "SearchResults", "ShardedIndex",
            "row_partition", "merge_keys"]

@@ -24,7 +24,7 @@ SYMBOLS = [
     "vs_last_error", "vs_abi_version", "vs_index_create_csr", "vs_index_create_dense", "vs_index_destroy",
     "vs_index_info", "vs_index_export_csr", "vs_search_workspace_bytes", "vs_search", "vs_search_keys",
     "vs_scores", "vs_merge_keys", "vs_kernel_timer", "vs_index_last_mode",
-    "vs_npz_open", "vs_npz_close", "vs_npz_member_info", "vs_npz_read", "vs_bot_from_tokens", "vs_score_rows", "vs_npz_write",
+    "vs_npz_open", "vs_npz_close", "vs_npz_member_info", "vs_npz_read", "vs_bot_from_tokens", "vs_score_rows", "vs_npz_write", "vs_sparsify_topk",
 ]
 
 
@@ -70,6 +70,7 @@ def _load() -> ctypes.CDLL:
                                   c_size_t, c_void_p]
     lib.vs_bot_from_tokens.argtypes = [c_int, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p]
+    lib.vs_sparsify_topk.argtypes = [c_int, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
     lib.vs_npz_write.argtypes = [c_char_p, c_void_p, c_int, c_int, c_int]
     lib.vs_npz_open.argtypes = [c_char_p, POINTER(c_void_p)]
     lib.vs_npz_close.argtypes = [c_void_p]

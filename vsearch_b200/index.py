@@ -202,6 +202,26 @@ class _Engine:
         return float(ms.value), int(n.value)
 
 
+def topk_sparsify(emb_dense: torch.Tensor, k: int, bow_ids: Optional[torch.Tensor] = None, shift: int = 0) -> torch.Tensor:
+    """Keep the ``k`` largest activations of every row of ``emb_dense`` ``[B, V]`` (ties -> lower column), zero the
+    rest; with ``bow_ids`` ``[B, L]`` the columns ``id - shift`` of the row's own tokens survive too.  Upstream
+    ``utils/sparse.py:8-19`` (``topk_sparsify`` / ``build_topk_mask``) and the ``logical_or(bow_mask, topk_mask)`` of
+    ``encoder/vdr.py:159-169``; returns a new fp32 tensor on the embedding's CUDA device."""
+    if emb_dense.device.type != "cuda":
+        raise RuntimeError("vsearch_b200.topk_sparsify runs on CUDA tensors only (no CPU fallback)")
+    one_d = emb_dense.dim() == 1
+    out = (emb_dense.unsqueeze(0) if one_d else emb_dense).to(torch.float32).clone().contiguous()
+    B, V = out.shape
+    ids = None
+    if bow_ids is not None:
+        ids = bow_ids.to(out.device, torch.int32).reshape(B, -1).contiguous()
+    with torch.cuda.device(out.device):
+        nat.check(nat.LIB.vs_sparsify_topk(out.device.index, out.data_ptr(), B, out.stride(0), V, int(k),
+                                           None if ids is None else ids.data_ptr(), 0 if ids is None else ids.shape[1],
+                                           int(shift), _stream_ptr(out.device)))
+    return out[0] if one_d else out
+
+
 def merge_keys(keys: torch.Tensor, k_out: int):
     """Merge gathered rank keys ``[P, B, k_in]`` (int64 bit patterns) into ``(ids, scores)`` ``[B, k_out]``."""
     if not keys.is_cuda:
