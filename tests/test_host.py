@@ -230,3 +230,36 @@ def test_retireve_negatives_filters_answers_and_pads(monkeypatch):
     assert set(out[1]) <= set(texts[:3])
     out = r.retireve_negatives(torch.zeros(1, 4), [["paris", "berlin", "rome", "platz"]], ret_neg_num=3, ret_topk=5)
     assert len(out[0]) == 3                                                       # empty pool -> padded with random passages
+
+
+def test_native_npz_reader_rejects_corrupt_files(tmp_path):
+    """truncations, byte flips and overwritten spans of a valid shard: the native reader reports an error (bad zip
+    structure, corrupt deflate stream, short member, size / CRC-32 mismatch) -- never a crash, never wrong data."""
+    import random
+
+    m = sp.random(1500, 29523, density=0.003, format="csr", random_state=1, dtype=np.float32)
+    good = str(tmp_path / "good.npz")
+    sp.save_npz(good, m)
+    truth = npz_io.load_csr_shards_native([good])
+    raw = open(good, "rb").read()
+    rnd = random.Random(0)
+    bad = str(tmp_path / "bad.npz")
+    for t in range(90):
+        b = bytearray(raw)
+        if t % 3 == 0:
+            b = b[:rnd.randrange(1, len(b))]
+        elif t % 3 == 1:
+            for _ in range(rnd.randrange(1, 20)):
+                b[rnd.randrange(len(b))] = rnd.randrange(256)
+        else:
+            i = rnd.randrange(len(b) - 64)
+            b[i:i + 32] = bytes(rnd.randrange(256) for _ in range(32))
+        if bytes(b) == raw:
+            continue
+        with open(bad, "wb") as f:
+            f.write(bytes(b))
+        try:
+            got = npz_io.load_csr_shards_native([bad])
+        except Exception:  # noqa: BLE001  (ValueError from the ABI, or numpy/zipfile on the tiny members)
+            continue
+        assert all(np.array_equal(x, y) for x, y in zip(got[:3], truth[:3])), f"case {t}: corrupt file loaded as different data"

@@ -35,6 +35,7 @@ struct NpzMember {
     std::string name;        // without ".npy"
     uint16_t method = 0;     // 0 stored, 8 deflate
     uint64_t comp_size = 0, raw_size = 0, local_off = 0;
+    uint32_t crc = 0;        // CRC-32 of the inflated member (central directory)
     // filled lazily by parse_npy_header
     bool parsed = false;
     int dtype = VS_NONE;     // VS_* code, or VS_NONE for dtypes the search path does not use
@@ -62,8 +63,11 @@ struct File {
 };
 
 // Streams the raw (inflated) bytes of a member through `sink(ptr, n)`; stops early when sink returns false.
+// A member that was streamed to its end is checked against the CRC-32 of the central directory.
 template <typename Sink>
 int stream_member(const vs_npz *z, const NpzMember &m, Sink &&sink) {
+    uint32_t crc = (uint32_t)crc32(0L, Z_NULL, 0);
+    uint64_t total = 0;
     File fh;
     fh.f = fopen(z->path.c_str(), "rb");
     NPZ_REQUIRE(fh.f, VS_ERR_INVALID, "%s: cannot open", z->path.c_str());
@@ -80,8 +84,11 @@ int stream_member(const vs_npz *z, const NpzMember &m, Sink &&sink) {
             const size_t n = (size_t)(left < kBuf ? left : kBuf);
             NPZ_REQUIRE(fread(in.data(), 1, n, fh.f) == n, VS_ERR_INVALID, "%s: truncated member %s", z->path.c_str(), m.name.c_str());
             left -= n;
-            if (!sink(in.data(), n)) return VS_OK;
+            crc = (uint32_t)crc32(crc, in.data(), (uInt)n);
+            total += n;
+            if (!sink(in.data(), n) && total < m.raw_size) return VS_OK;
         }
+        NPZ_REQUIRE(total == m.raw_size && crc == m.crc, VS_ERR_INVALID, "%s: size / CRC mismatch in member %s", z->path.c_str(), m.name.c_str());
         return VS_OK;
     }
     NPZ_REQUIRE(m.method == 8, VS_ERR_UNSUPPORTED, "%s: member %s uses zip method %d (only stored / deflate)", z->path.c_str(),
@@ -105,9 +112,13 @@ int stream_member(const vs_npz *z, const NpzMember &m, Sink &&sink) {
         zrc = inflate(&zs, Z_NO_FLUSH);
         if (zrc != Z_OK && zrc != Z_STREAM_END) { inflateEnd(&zs); NPZ_REQUIRE(false, VS_ERR_INVALID, "%s: corrupt deflate stream in member %s (zlib %d)", z->path.c_str(), m.name.c_str(), zrc); }
         const size_t produced = kBuf - zs.avail_out;
-        if (produced && !sink(out.data(), produced)) stop = true;
+        crc = (uint32_t)crc32(crc, out.data(), (uInt)produced);
+        total += produced;
+        if (produced && !sink(out.data(), produced) && total < m.raw_size) stop = true;
     }
     inflateEnd(&zs);
+    NPZ_REQUIRE(stop || (total == m.raw_size && crc == m.crc), VS_ERR_INVALID, "%s: size / CRC mismatch in member %s", z->path.c_str(),
+                m.name.c_str());
     return VS_OK;
 }
 
@@ -226,6 +237,7 @@ int npz_open_impl(const char *path, vs_npz **out) {
         if (p + 46 > cd.size() || rd32(&cd[p]) != 0x02014b50u) { delete z; NPZ_REQUIRE(false, VS_ERR_INVALID, "%s: corrupt central directory", path); }
         NpzMember m;
         m.method = rd16(&cd[p + 10]);
+        m.crc = rd32(&cd[p + 16]);
         m.comp_size = rd32(&cd[p + 20]); m.raw_size = rd32(&cd[p + 24]);
         const uint16_t nl = rd16(&cd[p + 28]), xl = rd16(&cd[p + 30]), cl = rd16(&cd[p + 32]);
         m.local_off = rd32(&cd[p + 42]);
