@@ -477,3 +477,22 @@ def test_topk_sparsify_matches_reference(cuda_device):
     assert idx.last_mode() == "inverted"
     X = ref_search.torch_csr(crow, col, val, (20_000, V))
     assert ref_search.compare_results(res, ref_search.ref_scores(q.cpu(), X), 20, rtol=1e-5, exact=False) is None
+
+
+@pytest.mark.gpu
+def test_malformed_csr_is_rejected_not_read_out_of_bounds(cuda_device):
+    """vs_index_create_csr validates what torch.sparse_csr_tensor validates: row pointers start at 0, never decrease and
+    stay within nnz; columns lie in [0, n_cols).  Errors come back as ValueError, nothing is read or written out of range."""
+    from vsearch_b200.index import _Engine
+
+    dev = torch.device("cuda:0")
+    col = torch.tensor([1, 5, 2, 7], dtype=torch.int64, device=dev)
+    val = torch.ones(4, device=dev)
+    good = torch.tensor([0, 2, 2, 4], dtype=torch.int64, device=dev)
+    _Engine.from_csr(good, col, val, (3, 10), dev)
+    for bad_crow in ([0, 3, 2, 4], [1, 2, 2, 4], [0, 2, 2, 4000], [0, -2, 2, 4]):
+        with pytest.raises(ValueError):
+            _Engine.from_csr(torch.tensor(bad_crow, dtype=torch.int64, device=dev), col, val, (3, 10), dev)
+    for bad_col in ([1, 5, 2, 10], [1, -1, 2, 7]):
+        with pytest.raises(ValueError):
+            _Engine.from_csr(good, torch.tensor(bad_col, dtype=torch.int64, device=dev), val, (3, 10), dev)

@@ -20,11 +20,12 @@ __device__ __forceinline__ float load_value(const void *p, int dtype, int64_t i)
 }
 
 // chunks per row (>= 1 so that every row, even an empty one, owns a tail bit)
-__global__ void row_chunks_kernel(const void *crow, int crow_dtype, int64_t n_rows, uint64_t *rc, int *err) {
+__global__ void row_chunks_kernel(const void *crow, int crow_dtype, int64_t n_rows, int64_t nnz, uint64_t *rc, int *err) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n_rows) return;
     if (r == n_rows) { rc[r] = 0; return; }
     int64_t a = load_index(crow, crow_dtype, r), e = load_index(crow, crow_dtype, r + 1);
+    if (a < 0 || e > nnz || (r == 0 && a != 0)) { atomicExch(err, 3); a = e = 0; }   // row pointers must stay inside col / val
     if (e < a) { atomicExch(err, 1); e = a; }
     uint64_t len = (uint64_t)(e - a);
     rc[r] = len == 0 ? 1 : (len + 7) / 8;
@@ -67,7 +68,7 @@ __global__ void fill_u32_kernel(uint32_t *p, uint64_t n, uint32_t v) {
 // one warp per row: scatter the row's entries into its chunks, set the tail bit, record row_chunk
 template <typename VT>
 __global__ void fill_rows_kernel(const void *crow, int crow_dtype, const void *col, int col_dtype, const void *val,
-                                 int val_dtype, int64_t n_rows, int64_t n_cols, const uint64_t *cptr,
+                                 int val_dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, const uint64_t *cptr,
                                  const uint32_t *part_row_begin, const uint32_t *part_win_begin, int n_parts,
                                  uint16_t *cols16, VT *vals, uint32_t *tails, uint32_t *row_chunk, int *err) {
     int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -83,6 +84,7 @@ __global__ void fill_rows_kernel(const void *crow, int crow_dtype, const void *c
     uint64_t dst = (uint64_t)part_win_begin[p] * 32ull + (cptr[r] - cptr[part_row_begin[p]]);
     uint64_t nchunks = cptr[r + 1] - cptr[r];
     int64_t a = load_index(crow, crow_dtype, r), e = load_index(crow, crow_dtype, r + 1);
+    if (a < 0 || e > nnz || (r == 0 && a != 0)) a = e = 0;   // same clamps as row_chunks_kernel (which raised the error)
     if (e < a) e = a;
     for (int64_t j = a + lane; j < e; j += 32) {
         int64_t c = load_index(col, col_dtype, j);
@@ -314,7 +316,7 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
     VS_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
     {
         int64_t n = N + 1;
-        row_chunks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_crow, crow_dtype, N, d_cptr, d_err);
+        row_chunks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_crow, crow_dtype, N, idx->nnz, d_cptr, d_err);
     }
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cptr, d_cptr, (int64_t)(N + 1), st);
     VS_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16));
@@ -349,7 +351,8 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
         unsigned blocks = (unsigned)((N * 32 + 255) / 256);
 #define VS_FILL(VT)                                                                                              \
     fill_rows_kernel<VT><<<blocks, 256, 0, st>>>(d_crow, crow_dtype, d_col, col_dtype, d_val, val_dtype, N,      \
-                                                 idx->n_cols, d_cptr, idx->part_row_begin, idx->part_win_begin,  \
+                                                 idx->n_cols, idx->nnz, d_cptr, idx->part_row_begin,             \
+                                                 idx->part_win_begin,                                           \
                                                  P, (uint16_t *)idx->cols, (VT *)idx->vals, idx->tails,          \
                                                  idx->row_chunk, d_err)
         if (idx->kind == 2) VS_FILL(NoVal);
@@ -376,6 +379,7 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
     VS_CUDA(cudaGetLastError());
     cleanup();
     VS_REQUIRE(h_err != 1, VS_ERR_INVALID, "crow_indices are not non-decreasing");
+    VS_REQUIRE(h_err != 3, VS_ERR_INVALID, "crow_indices must start at 0 and stay within [0, nnz]");
     VS_REQUIRE(h_err != 2, VS_ERR_INVALID, "col_indices outside [0, n_cols)");
 
     idx->stream_bytes = (int64_t)(n_windows * 32ull * (16 + 8 * val_elem) + n_windows * 4);
