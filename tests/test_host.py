@@ -263,3 +263,18 @@ def test_native_npz_reader_rejects_corrupt_files(tmp_path):
         except Exception:  # noqa: BLE001  (ValueError from the ABI, or numpy/zipfile on the tiny members)
             continue
         assert all(np.array_equal(x, y) for x, y in zip(got[:3], truth[:3])), f"case {t}: corrupt file loaded as different data"
+
+
+def test_native_npz_writer_zip64_records(tmp_path, monkeypatch):
+    """A 21M-row index has members beyond 4 GB, i.e. ZIP64 records in the local headers, the central directory and the
+    end-of-directory locator.  VSEARCH_B200_NPZ_FORCE_ZIP64 takes that path with a small matrix: zipfile (CRC check),
+    scipy and the native reader must all read the file."""
+    monkeypatch.setenv("VSEARCH_B200_NPZ_FORCE_ZIP64", "1")
+    m = sp.random(3000, 29523, density=0.003, format="csr", random_state=1, dtype=np.float32)
+    f = str(tmp_path / "z64.npz")
+    npz_io.save_csr_npz_native(f, m.indptr, m.indices, m.data, m.shape, threads=2)
+    with zipfile.ZipFile(f) as z:
+        assert all(i.extract_version == 45 for i in z.infolist()) and z.testzip() is None
+    assert (sp.load_npz(f) != m).nnz == 0
+    r = npz_io.load_csr_shards_native([f])
+    assert np.array_equal(r[0], m.indptr) and np.array_equal(r[1], m.indices) and np.array_equal(r[2], m.data)

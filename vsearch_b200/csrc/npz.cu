@@ -441,6 +441,8 @@ int npz_write_impl(const char *path, const vs_npz_member_in *members, int n_memb
     NPZ_REQUIRE(path && members && n_members > 0, VS_ERR_INVALID, "vs_npz_write: bad argument");
     if (threads < 1) threads = 1;
     if (level < 0 || level > 9) level = 6;
+    // test hook: write ZIP64 records for every member (the path a 21M-row index takes: its members exceed 4 GB)
+    const bool force_z64 = getenv("VSEARCH_B200_NPZ_FORCE_ZIP64") != nullptr;
     File fh;
     fh.f = fopen(path, "wb");
     NPZ_REQUIRE(fh.f, VS_ERR_INVALID, "%s: cannot create", path);
@@ -454,7 +456,7 @@ int npz_write_impl(const char *path, const vs_npz_member_in *members, int n_memb
         e.name = std::string(m.name) + ".npy";
         e.raw = (uint64_t)m.header_bytes + (uint64_t)m.data_bytes;
         e.off = (uint64_t)ftello(fh.f);
-        e.z64 = e.raw >= 0x7fffffffull || e.off >= 0x7fffffffull;
+        e.z64 = force_z64 || e.raw >= 0x7fffffffull || e.off >= 0x7fffffffull;
         e.crc = 0; e.comp = 0;
         // local header (sizes patched after the data is written)
         std::vector<uint8_t> lh;
@@ -556,7 +558,7 @@ int npz_write_impl(const char *path, const vs_npz_member_in *members, int n_memb
         if (z64) { put16(cd, 1); put16(cd, 24); put64(cd, e.raw); put64(cd, e.comp); put64(cd, e.off); }
     }
     const uint64_t cd_size = cd.size();
-    const bool big = cd_off >= 0xffffffffull || dir.size() >= 0xffff;
+    const bool big = force_z64 || cd_off >= 0xffffffffull || dir.size() >= 0xffff;
     if (big) {
         put32(cd, 0x06064b50u); put64(cd, 44); put16(cd, 45); put16(cd, 45); put32(cd, 0); put32(cd, 0);
         put64(cd, dir.size()); put64(cd, dir.size()); put64(cd, cd_size); put64(cd, cd_off);
