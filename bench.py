@@ -14,6 +14,8 @@ value  = queries/sec with the query batch already resident in HBM;
 e2e    = the same through the public call with HOST (pinned) queries and a device->host read of ids+scores;
 roofline = achieved HBM GB/s of the scan kernel on ALGORITHMIC bytes (nnz*2 + (N+1)*4 per pass, one pass per
            query), CUDA events around each launch, vs the measured copy peak in MEASURED_PEAKS.json;
+auto_mode = the same step through the default `auto` mode a user gets (for these 64-nnz queries the engine picks
+           the K3 inverted lists): value / e2e / roofline of that run, reported next to the headline scan;
 cpu_baseline / --impl reference = the reference's own CPU path (torch CSR matmul + topk, restated in
            oracle/ref_search.py because the reference package cannot be imported/installed -- DESIGN.md) on a
            bounded row sample, linearly extrapolated in N.
