@@ -52,6 +52,12 @@ def timed(fn, reps=5, warm=2):
     return e0.elapsed_time(e1) / reps
 
 
+def torch_path(q, X, k):
+    """The reference's own two calls (upstream index.py:89-92) through stock torch: the 'beat that' baseline."""
+    with torch.no_grad():
+        return torch.matmul(q.to(X.device).type(X.dtype), X.t()).topk(k)
+
+
 def emit(**kw):
     print(json.dumps(kw), flush=True)
 
@@ -91,20 +97,19 @@ def cfg1():
     n, m = 100_000, 256
     cols, vals, crow = sparse_case("cfg1", n, m, [64], 100)
     # reference torch path on the same data: GPU (B2 baseline) and CPU (B1 baseline)
-    from oracle import ref_search
     q = queries(64, 64)
     X = torch.sparse_csr_tensor(crow, cols.reshape(-1).to(torch.int64), vals, size=(n, V))
     try:
-        ms = timed(lambda: ref_search.ref_search(q, X, 100), reps=5)
+        ms = timed(lambda: torch_path(q, X, 100), reps=5)
         emit(config="cfg1", impl="reference torch CSR matmul+topk on the SAME B200 (cuSPARSE)", B=64, ms_per_call=ms, qps=64 / ms * 1e3)
     except Exception as e:  # noqa: BLE001
         emit(config="cfg1", impl="reference torch GPU", error=str(e)[:300])
     Xc, qc = X.cpu(), q.cpu()
     torch.set_num_threads(os.cpu_count())
-    ref_search.ref_search(qc, Xc, 100)
+    torch_path(qc, Xc, 100)
     t0 = time.perf_counter()
     for _ in range(3):
-        ref_search.ref_search(qc, Xc, 100)
+        torch_path(qc, Xc, 100)
     dt = (time.perf_counter() - t0) / 3
     emit(config="cfg1", impl=f"reference torch CSR matmul+topk on CPU ({os.cpu_count()} threads)", B=64, ms_per_call=dt * 1e3, qps=64 / dt)
 
@@ -148,7 +153,6 @@ def cfg4():
 def cfg2_torch():
     """B2 baseline of BASELINE.md: the reference's own torch path (cuSPARSE SpMM + topk) on the SAME B200 for the
     headline config (21M x 120 binary).  The [B, N] score matrix limits the batch (B=64 -> 5.4 GB)."""
-    from oracle import ref_search
     n, m = 21_015_324, 120
     cols = strat_cols(n, m, 1234).reshape(-1).to(torch.int64)
     crow = torch.arange(n + 1, device=dev, dtype=torch.int64) * m
@@ -158,7 +162,7 @@ def cfg2_torch():
             X = torch.sparse_csr_tensor(crow, cols, vals, size=(n, V))
             for B in (1, 64):
                 q = queries(B, 64)
-                ms = timed(lambda: ref_search.ref_search(q, X, 100), reps=3, warm=1)
+                ms = timed(lambda: torch_path(q, X, 100), reps=3, warm=1)
                 emit(config="cfg2", impl=f"reference torch CSR matmul+topk on the SAME B200 (cuSPARSE), values {dtype}", B=B,
                      ms_per_call=ms, qps=B / ms * 1e3, peak_mem_GB=torch.cuda.max_memory_allocated() / 1e9)
             del X, vals

@@ -2,7 +2,7 @@
 """Multi-GPU parity of the row-sharded path over NCCL (run under torchrun, one rank per GPU):
 every rank builds its contiguous shard of the same seeded index, ShardedIndex.search does local fused top-k ->
 ONE all-gather of rank keys -> merge, and rank 0 checks ids/scores bit-exactly against the oracle on the full index.
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 scripts/nccl_parity.py"""
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/nccl_parity.py"""
 import os
 import sys
 
