@@ -278,3 +278,45 @@ def test_native_npz_writer_zip64_records(tmp_path, monkeypatch):
     assert (sp.load_npz(f) != m).nnz == 0
     r = npz_io.load_csr_shards_native([f])
     assert np.array_equal(r[0], m.indptr) and np.array_equal(r[1], m.indices) and np.array_equal(r[2], m.data)
+
+
+def test_native_npz_roundtrip_property(tmp_path):
+    """hypothesis: random CSR shapes / dtypes / thread counts through vs_npz_write then vs_npz_read, with every
+    supported conversion (index narrowing and widening, float16 <-> float32) and partial reads."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st_
+
+    counter = [0]
+
+    @settings(max_examples=25, deadline=None)
+    @given(n=st_.integers(0, 300), width=st_.integers(1, 40), idt=st_.sampled_from([np.int32, np.int64]),
+           fdt=st_.sampled_from([np.float32, np.float16]), threads=st_.integers(1, 4), seed=st_.integers(0, 10**6))
+    def run(n, width, idt, fdt, threads, seed):
+        rng = np.random.default_rng(seed)
+        lens = rng.integers(0, width + 1, n)
+        indptr = np.concatenate(([0], np.cumsum(lens))).astype(idt)
+        nnz = int(indptr[-1])
+        indices = rng.integers(0, 29523, nnz).astype(idt)
+        data = (rng.integers(-64, 64, nnz) / 8).astype(fdt)          # exact in fp16
+        counter[0] += 1
+        f = str(tmp_path / f"p{counter[0]}.npz")
+        npz_io.save_csr_npz_native(f, indptr, indices, data, (n, 29523), threads=threads)
+        z = np.load(f)
+        assert np.array_equal(z["indptr"], indptr) and np.array_equal(z["indices"], indices) and np.array_equal(z["data"], data)
+        sh = npz_io._NativeShard(f)
+        try:
+            for dst in (np.int32, np.int64):
+                out = np.empty(nnz, dtype=dst)
+                sh.read_into("indices", out)
+                assert np.array_equal(out, indices.astype(dst))
+            for dst in (np.float32, np.float16):
+                out = np.empty(nnz, dtype=dst)
+                sh.read_into("data", out)
+                assert np.array_equal(out, data.astype(dst))
+            out = np.empty(n, dtype=np.int64)                           # row pointers: skip the leading 0, add an offset
+            sh.read_into("indptr", out, skip=1, add=1000)
+            assert np.array_equal(out, indptr[1:].astype(np.int64) + 1000)
+        finally:
+            sh.close()
+
+    run()
