@@ -5,15 +5,17 @@
 //     ceil(len/8) chunks (>= 1), padded with the sentinel column V whose query slot is 0;
 //   * 32 consecutive chunks form a WINDOW = one coalesced 512-byte warp load;
 //   * the stream is cut into n_parts contiguous PARTS (one per resident warp of the
-//     persistent scan grid: #SMs x 32), each a whole number of windows holding whole rows,
-//     balanced by chunk count;
-//   * tails[w] has bit i set when chunk i of window w is the LAST chunk of its row: the
-//     scan kernel turns per-lane partial dot products into row scores with one segmented
-//     warp scan and no row-pointer lookups;
+//     persistent scan grid: #SMs x 24), each a whole number of 64-chunk steps holding whole
+//     rows, balanced by chunk count;
+//   * bit 15 of a chunk's FIRST entry is set when the chunk is the LAST chunk of its row (so
+//     n_cols <= 32,767): the scan kernel turns per-lane partial dot products into row scores
+//     with one segmented warp scan and reads no side stream and no row pointers;
+//   * tails[w] keeps the same flags as one bit per chunk of window w for the builders (bank
+//     placement, inverted lists); the scan does not read it;
 //   * values (fp32 / fp16 / bf16) sit in a parallel array with the same chunk geometry;
 //     the binary bag-of-token index has none.
 // Algorithmic bytes of a pass: nnz*(2+b_val) + (N+1)*4.  The format streams
-// n_windows*32*(16 + 8*b_val) + n_windows*4 bytes; the overhead is the row padding (<= 7
+// n_windows*32*(16 + 8*b_val) bytes; the overhead is the row padding (<= 7
 // entries per row) and is reported by vs_index_info(stream_bytes).
 #pragma once
 #include "common.cuh"
