@@ -5,7 +5,9 @@ import pytest
 import torch
 
 from oracle import c_oracle, ref_search
-from tests.util import golden_search_cases, load_golden
+import os
+
+from tests.util import GOLDEN, golden_search_cases, load_golden
 
 
 @pytest.mark.parametrize("name", golden_search_cases("csr"))
@@ -127,3 +129,27 @@ def test_ref_bot_rows_matches_reference_semantics():
     crow, col, _ = ref_search.ref_bot_rows(rows, vocab_size=30522, num_shift=999, max_token=3)
     assert crow.tolist() == [0, 2, 2, 4]          # row 0 keeps {101, 2054, 2003}; row 2 keeps {5000, 999, 998}
     assert col.tolist() == [2003 - 999, 2054 - 999, 0, 5000 - 999]
+
+
+@pytest.mark.parametrize("tag", ["all", "first20"])
+def test_ref_bot_rows_matches_reference_output(tag):
+    """oracle restatement of the bag-of-token builder vs the output of the reference's own _build_bot_vectors
+    (tests/golden/make_golden_neighbours.py executes the unmodified function body)."""
+    z = np.load(os.path.join(GOLDEN, f"bot_rows_{tag}.npz"))
+    # the tokenizer truncates to max_len (retriever.py:238) before the builder sees the ids
+    rows = [z["token_ids"][i, :min(int(z["lengths"][i]), int(z["max_len"]))].tolist() for i in range(z["token_ids"].shape[0])]
+    crow, col, shape = ref_search.ref_bot_rows(rows, int(z["vocab"]), int(z["shift"]), int(z["max_token"]) or None)
+    assert shape == tuple(z["shape"])
+    assert np.array_equal(crow.numpy(), z["crow"]) and np.array_equal(col.numpy(), z["col"])
+    assert str(z["val_dtype"]) == "torch.float16" and bool((z["val"] == 1).all())
+
+
+def test_ref_topk_sparsify_matches_reference_output():
+    """oracle restatement of the sparsifier vs the reference's topk_sparsify / build_topk_mask / build_bow_mask
+    (utils/sparse.py) combined as in encoder/vdr.py:159-169."""
+    z = np.load(os.path.join(GOLDEN, "sparsify_k768.npz"))
+    emb, ids = torch.from_numpy(z["emb"]), torch.from_numpy(z["token_ids"])
+    for name, out in (("plain", ref_search.ref_topk_sparsify(emb, int(z["k"]))),
+                      ("lexical", ref_search.ref_topk_sparsify(emb, int(z["k"]), ids, int(z["shift"])))):
+        assert np.array_equal(out.nonzero().numpy(), z[f"{name}_idx"]), name
+        assert np.array_equal(out[out != 0].numpy(), z[f"{name}_val"]), name
