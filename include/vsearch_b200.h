@@ -133,6 +133,17 @@ int vs_index_last_mode(const vs_index *idx, int *mode);
 #define VS_TIMER_SLOTS 256
 int vs_kernel_timer(vs_index *idx, int reset, float *total_ms, int *launches);
 
+/* Diagnostic: while d_buf != NULL the binary scan kernel (K2) stores %globaltimer at its phase boundaries,
+ * d_buf[(cta * B + query) * 8 + slot] (slots: 0 pass start, 1 query vector staged, 2 sampling streamed, 3 threshold
+ * selected, 4 warp 0 finished streaming, 5 all warps finished, 6 top-k written); the buffer must hold
+ * n_ctas * B * 8 entries for every search issued while it is set.  NULL switches it off. */
+int vs_debug_scan_profile(vs_index *idx, unsigned long long *d_buf);
+
+/* Diagnostic: what the bank-aware entry placement achieved on this sparse / binary index.  d_out2[0] = shared-memory
+ * wavefronts the scan's query gathers cost per pass (largest number of distinct addresses on one bank, summed over the
+ * gather instructions), d_out2[1] = gather instructions per pass (device uint64[2]).  1.0 per gather is conflict-free. */
+int vs_debug_gather_wavefronts(const vs_index *idx, unsigned long long *d_out2, void *stream);
+
 /* ---- query sparsifier ---------------------------------------------------------------------------------------------
  * In place on a device fp32 batch d_q [B, ld]: keep the k largest of the first n_cols entries of every row (ties ->
  * lower column) and zero the rest -- upstream utils/sparse.py:8-19 (build_topk_mask / topk_sparsify), the `a=768`

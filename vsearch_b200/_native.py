@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvsearch_b200.so")
+# VSEARCH_B200_LIB: an experiment build of the same library (csrc/Makefile: BUILD= OUT= EXTRA=); never a different backend
+LIB_PATH = os.environ.get("VSEARCH_B200_LIB") or os.path.join(_HERE, "lib", "libvsearch_b200.so")
 
 VS_OK, VS_ERR_INVALID, VS_ERR_UNSUPPORTED, VS_ERR_CUDA, VS_ERR_NOMEM = 0, 1, 2, 3, 4
 VS_F32, VS_F16, VS_BF16, VS_I32, VS_I64, VS_U16, VS_U32, VS_NONE = range(8)
@@ -25,6 +26,7 @@ SYMBOLS = [
     "vs_index_info", "vs_index_export_csr", "vs_search_workspace_bytes", "vs_search", "vs_search_keys",
     "vs_scores", "vs_merge_keys", "vs_kernel_timer", "vs_index_last_mode",
     "vs_npz_open", "vs_npz_close", "vs_npz_member_info", "vs_npz_read", "vs_bot_from_tokens", "vs_score_rows", "vs_npz_write", "vs_sparsify_topk",
+    "vs_debug_scan_profile", "vs_debug_gather_wavefronts",
 ]
 
 
@@ -65,6 +67,8 @@ def _load() -> ctypes.CDLL:
     lib.vs_merge_keys.argtypes = [c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p]
     lib.vs_index_last_mode.argtypes = [c_void_p, POINTER(c_int)]
+    lib.vs_debug_scan_profile.argtypes = [c_void_p, c_void_p]
+    lib.vs_debug_gather_wavefronts.argtypes = [c_void_p, c_void_p, c_void_p]
     lib.vs_kernel_timer.argtypes = [c_void_p, c_int, POINTER(c_float), POINTER(c_int)]
     lib.vs_score_rows.argtypes = [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                   c_size_t, c_void_p]

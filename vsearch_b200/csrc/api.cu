@@ -20,6 +20,7 @@ void set_error(const char *fmt, ...) {
 // scan.cu / merge.cu
 size_t scan_smem_bytes(int vpad, int cap);
 int scan_cap_for_k(int k);
+int scan_kout(const vs_index *idx, int k);
 int launch_prep_query(const void *d_q, int q_dtype, int64_t B, int64_t ldq, int64_t n_cols, int vpad, int round_mode,
                       float *d_out, cudaStream_t st);
 int launch_scan(const vs_index *idx, const float *d_qprep, int vpad, int64_t B, int k, int score_round,
@@ -79,7 +80,7 @@ static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 static Workspace carve(const vs_index *idx, void *base, int64_t Bc, int k) {
     Workspace w;
     size_t q_bytes = align256((size_t)Bc * vpad_for(idx->n_cols) * 4);
-    size_t c_bytes = align256((size_t)Bc * idx->n_ctas * (size_t)k * 8);
+    size_t c_bytes = align256((size_t)Bc * idx->n_ctas * (size_t)scan_kout(idx, k) * 8);   // scan lists are the longer ones
     w.qprep = (float *)base;
     w.cand = (uint64_t *)((uint8_t *)base + q_bytes);
     w.inv = (uint8_t *)base + q_bytes + c_bytes;
@@ -87,6 +88,13 @@ static Workspace carve(const vs_index *idx, void *base, int64_t Bc, int k) {
     return w;
 }
 constexpr int64_t kQueryChunk = 1024;
+// queries per launch: at most kQueryChunk, fewer when the per-CTA candidate lists of a chunk would pass 512 MB (large k)
+static int64_t query_chunk(const vs_index *idx, int64_t B, int k) {
+    const int64_t per_query = (int64_t)idx->n_ctas * scan_kout(idx, k) * 8;
+    int64_t c = (512ll << 20) / (per_query > 0 ? per_query : 1);
+    c = c < 16 ? 16 : (c > kQueryChunk ? kQueryChunk : c);
+    return B < c ? B : c;
+}
 // auto-mode cost model; refined from measurements (profiles/)
 constexpr double kScanBytesPerSecPair = 4.5e12;   // binary / 16-bit values (L1 data-pipe bound)
 constexpr double kScanBytesPerSecF32 = 6.2e12;    // fp32 values (HBM bound)
@@ -112,14 +120,15 @@ __global__ void __launch_bounds__(256) score_rows_kernel(const WsView idx, const
     const uint32_t c0 = idx.row_chunk[id], c1 = idx.row_chunk[id + 1];
     float s = 0.f;
     for (uint32_t c = c0 + lane; c < c1; c += 32) {
-        const uint4 u = idx.cols[c];
+        const uint64_t pc = ws_phys_chunk(c, idx.cpl_shift);   // c runs over the row's LOGICAL chunks
+        const uint4 u = idx.cols[pc];
         const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const uint32_t col = ((e & 1) ? (wv[e >> 1] >> 16) : (wv[e >> 1] & 0xffffu)) & 0x7fffu;   // bit 15 = row-end flag
             float v = 1.f;   // binary index; padding entries point at the query's zero slot
             if (idx.kind == 1) {
-                const uint64_t at = (uint64_t)c * 8ull + e;
+                const uint64_t at = pc * 8ull + e;
                 if (idx.store_dtype == VS_F32) v = ((const float *)idx.vals)[at];
                 else if (idx.store_dtype == VS_F16) v = __half2float(((const __half *)idx.vals)[at]);
                 else v = __bfloat162float(((const __nv_bfloat16 *)idx.vals)[at]);
@@ -260,8 +269,7 @@ int vs_index_export_csr(const vs_index *idx, int64_t *d_crow, int64_t *d_col, fl
 size_t vs_search_workspace_bytes(const vs_index *idx, int64_t B, int k) {
     if (!idx || B <= 0 || k <= 0) return 256;
     if (idx->kind == 0) return dense_workspace_bytes(idx, B, k) + 256;
-    int64_t Bc = B < kQueryChunk ? B : kQueryChunk;
-    return carve(idx, nullptr, Bc, k).bytes + 256;
+    return carve(idx, nullptr, query_chunk(idx, B, k), k).bytes + 256;
 }
 
 static int search_impl(const vs_index *cidx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int k, int mode,
@@ -297,8 +305,9 @@ static int search_impl(const vs_index *cidx, const void *hd_q, int q_dtype, int6
         if (rc == VS_OK && sq.owned) VS_CUDA(cudaStreamSynchronize(st));
         return rc;
     }
-    for (int64_t b0 = 0; b0 < B; b0 += kQueryChunk) {
-        const int64_t Bc = (B - b0) < kQueryChunk ? (B - b0) : kQueryChunk;
+    const int64_t chunk = query_chunk(idx, B, k);
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int64_t Bc = (B - b0) < chunk ? (B - b0) : chunk;
         Workspace w = carve(idx, ws_base, Bc, k);
         const uint8_t *qsrc = (const uint8_t *)hd_q + (size_t)b0 * ldq * dtype_size(q_dtype);
         Staged sq;
@@ -342,7 +351,8 @@ static int search_impl(const vs_index *cidx, const void *hd_q, int q_dtype, int6
             if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
         }
         idx->timer_n += 1;
-        rc = launch_merge(w.cand, idx->n_ctas, k, (int64_t)idx->n_ctas * k, Bc, k, k, id_offset,
+        const int k_in = use_inv ? k : scan_kout(idx, k);   // length of the per-CTA lists
+        rc = launch_merge(w.cand, idx->n_ctas, k_in, (int64_t)idx->n_ctas * k_in, Bc, k_in, k, id_offset,
                           d_ids ? d_ids + b0 * k : nullptr, d_scores ? d_scores + b0 * k : nullptr,
                           d_keys ? d_keys + b0 * k : nullptr, st);
         if (rc) return rc;
@@ -412,6 +422,18 @@ int vs_merge_keys(int device, const uint64_t *d_keys_in, int64_t P, int64_t stri
 int vs_index_last_mode(const vs_index *idx, int *mode) {
     VS_REQUIRE(idx != nullptr && mode != nullptr, VS_ERR_INVALID, "NULL pointer");
     *mode = idx->last_mode;
+    return VS_OK;
+}
+
+int vs_debug_gather_wavefronts(const vs_index *idx, unsigned long long *d_out2, void *stream) {
+    VS_REQUIRE(idx != nullptr && idx->kind != 0 && d_out2 != nullptr, VS_ERR_INVALID, "needs a sparse / binary index");
+    VS_CUDA(cudaSetDevice(idx->device));
+    return debug_gather_wavefronts(idx, d_out2, (cudaStream_t)stream);
+}
+
+int vs_debug_scan_profile(vs_index *idx, unsigned long long *d_buf) {
+    VS_REQUIRE(idx != nullptr, VS_ERR_INVALID, "NULL pointer");
+    idx->scan_prof = d_buf;
     return VS_OK;
 }
 

@@ -46,14 +46,15 @@ __global__ void part_rows_kernel(const uint64_t *cptr, int64_t n_rows, int n_par
     part_row_begin[p] = (uint32_t)lo;
 }
 
-__global__ void part_windows_kernel(const uint64_t *cptr, const uint32_t *part_row_begin, int n_parts,
+__global__ void part_windows_kernel(const uint64_t *cptr, const uint32_t *part_row_begin, int n_parts, int cpl_shift,
                                     uint32_t *part_win_begin, uint64_t *n_windows_out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     uint64_t w = 0;
+    const uint64_t sc = 32ull << cpl_shift;   // chunks per scan step
     for (int p = 0; p < n_parts; ++p) {
         part_win_begin[p] = (uint32_t)w;
         uint64_t chunks = cptr[part_row_begin[p + 1]] - cptr[part_row_begin[p]];
-        w += (chunks + 63) / 64 * 2;   // whole 64-chunk steps: the scan kernel takes two chunks per lane per step
+        w += ((chunks + sc - 1) / sc) << cpl_shift;   // whole steps (32 << cpl_shift chunks each)
     }
     part_win_begin[n_parts] = (uint32_t)w;
     *n_windows_out = w;
@@ -69,7 +70,7 @@ __global__ void fill_u32_kernel(uint32_t *p, uint64_t n, uint32_t v) {
 template <typename VT>
 __global__ void fill_rows_kernel(const void *crow, int crow_dtype, const void *col, int col_dtype, const void *val,
                                  int val_dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, const uint64_t *cptr,
-                                 const uint32_t *part_row_begin, const uint32_t *part_win_begin, int n_parts,
+                                 const uint32_t *part_row_begin, const uint32_t *part_win_begin, int n_parts, int cpl_shift,
                                  uint16_t *cols16, VT *vals, uint32_t *tails, uint32_t *row_chunk, int *err) {
     int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -89,7 +90,8 @@ __global__ void fill_rows_kernel(const void *crow, int crow_dtype, const void *c
     for (int64_t j = a + lane; j < e; j += 32) {
         int64_t c = load_index(col, col_dtype, j);
         if (c < 0 || c >= n_cols) { atomicExch(err, 2); continue; }  // leaves the sentinel in place
-        uint64_t o = dst * 8ull + (uint64_t)(j - a);
+        const uint64_t ent = (uint64_t)(j - a);
+        const uint64_t o = ws_phys_chunk(dst + (ent >> 3), cpl_shift) * 8ull + (ent & 7ull);
         cols16[o] = (uint16_t)c;
         if constexpr (sizeof(VT) == 4) {
             vals[o] = load_value(val, val_dtype, j);
@@ -110,18 +112,22 @@ __global__ void fill_rows_kernel(const void *crow, int crow_dtype, const void *c
 struct NoVal { char c; };  // sizeof == 1: "no values" marker type
 
 // ---- bank-aware entry placement ---------------------------------------------------------------------------
-// A scan step covers 32*CPL chunks (CPL = chunks per lane: 2 for the binary / 16-bit-value kernels, 1 for fp32 values).
-// Gather #j of sub-chunk q reads slot j of the 32 chunks {CPL*l + q} of the step at once; the shared-memory cost of
-// that instruction is the largest number of lanes hitting one bank (bank = column mod 32).  A dot product does not
-// care about the order of a row's entries, so inside every step each row's entries are re-dealt over the row's
-// (chunk, slot) positions of that step: for every gather group (slot, sub-chunk) a maximum bipartite matching
+// A scan step covers 32*CPL chunks (CPL = chunks per lane: 8 for the binary kernel, 2 for 16-bit values, 1 for fp32
+// values).  Gather #j of sub-chunk q reads slot j of the 32 chunks {CPL*l + q} of the step at once; the shared-memory
+// cost of that instruction is the largest number of lanes hitting one bank (bank = column mod 32).  A dot product
+// does not care about the order of a row's entries, so inside every step each row's entries are re-dealt over the
+// row's (chunk, slot) positions of that step: for every gather group (slot, sub-chunk) a maximum bipartite matching
 // lanes -> banks (edge = the lane's row still has an entry in that bank; banks tried in order of the row's remaining
 // supply; Kuhn's augmenting paths) gives every lane a DISTINCT bank whenever one exists; unmatched lanes collide on
 // the emptiest bank their row can still supply.
-// Random order costs 3.5 wavefronts per gather, a greedy deal 2.0-2.1, the matching 1.83 = the bound set by the
-// per-step bank imbalance of random columns (simulated; measured numbers in profiles/README.md).
+// The bound is the per-step bank imbalance of the columns: a step of 8*CPL gathers cannot cost fewer wavefronts than
+// its most loaded bank holds entries.  Random columns: 3.5 wavefronts per gather in input order, 1.83 after the
+// matching with CPL = 2 (64-chunk steps), lower with CPL = 8 (256-chunk steps: the imbalance averages out over 64
+// gathers; measured numbers in profiles/README.md).
 // One warp per step (steps are independent: entries never leave their step), state in shared memory; the search
 // itself is sequential but every inner loop over banks is one ballot / redux.  One-off work at index build.
+// Positions inside the scratch are LOGICAL (chunk c = CPL*lane + q); the global arrays are addressed physically
+// (chunk c of the step sits at q*32 + lane, index.cuh).
 template <typename VT, int CPL>
 struct alignas(16) PlaceScratch {
     static constexpr int SC = 32 * CPL;   // chunks per step
@@ -131,18 +137,19 @@ struct alignas(16) PlaceScratch {
     uint16_t ocol[NP];                    // ... and as re-dealt
     VT eval[NV];
     VT oval[NV];
+    static constexpr int MS = SC < 64 ? SC : 64;   // segments a step may hold and still be re-dealt (see below)
     int16_t nxt[NP];                      // per (segment, bank) linked lists of unused entries
-    int16_t head[SC][32];
-    uint16_t sup[SC][32];                 // remaining entries per (segment, bank); segment = piece of a row in the step
-    int16_t rem[SC];                      // remaining entries per segment
+    int16_t head[MS][32];
+    uint16_t sup[MS][32];                 // remaining entries per (segment, bank); segment = piece of a row in the step
+    int16_t rem[MS];                      // remaining entries per segment
     uint8_t chunk_seg[SC];
+    uint32_t tw[CPL];                     // row-end flags of the step's chunks (logical order)
+    uint32_t tpre[CPL + 1];               // exclusive prefix of their popcounts
 };
 
-constexpr int kPlaceWarps = 8;
-
-template <typename VT, int CPL>
-__global__ void __launch_bounds__(kPlaceWarps * 32) place_step_kernel(uint16_t *cols16, VT *vals, const uint32_t *tails,
-                                                                      uint64_t n_steps, int n_cols) {
+template <typename VT, int CPL, int PW>
+__global__ void __launch_bounds__(PW * 32) place_step_kernel(uint16_t *cols16, VT *vals, const uint32_t *tails,
+                                                             uint64_t n_steps, int n_cols) {
     using S = PlaceScratch<VT, CPL>;
     constexpr int SC = S::SC, NP = S::NP;
     constexpr unsigned FULL = 0xffffffffu;
@@ -152,25 +159,35 @@ __global__ void __launch_bounds__(kPlaceWarps * 32) place_step_kernel(uint16_t *
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const uint16_t sent = (uint16_t)n_cols;
-    const uint64_t n_warps = (uint64_t)gridDim.x * kPlaceWarps;
+    const uint64_t n_warps = (uint64_t)gridDim.x * PW;
 
-    for (uint64_t step = (uint64_t)blockIdx.x * kPlaceWarps + (threadIdx.x >> 5); step < n_steps; step += n_warps) {
+    for (uint64_t step = (uint64_t)blockIdx.x * PW + (threadIdx.x >> 5); step < n_steps; step += n_warps) {
         const uint64_t c0 = step * SC;
-        uint64_t T;  // row-end flags of the step's chunks
-        if constexpr (CPL == 2) T = (uint64_t)tails[2 * step] | ((uint64_t)tails[2 * step + 1] << 32);
-        else T = tails[step];
-        const int n_seg = __popcll(T & ((1ull << (SC - 1)) - 1ull)) + 1;
+        if (lane < CPL) s.tw[lane] = tails[step * CPL + lane];
+        __syncwarp();
+        if (lane == 0) {
+            uint32_t run = 0;
+            for (int w = 0; w < CPL; ++w) { s.tpre[w] = run; run += __popc(s.tw[w]); }
+            s.tpre[CPL] = run;
+        }
+        __syncwarp();
+        // segments = pieces of rows inside the step: one more than the row ends among the first SC-1 chunks
+        const int n_seg = (int)s.tpre[CPL] - (int)((s.tw[CPL - 1] >> 31) & 1u) + 1;
+        // a step of more than MS row pieces (rows of < 4 chunks on average) keeps its input order: such rows have few
+        // entries to re-deal, and the per-segment tables stay small enough for 8 warps per SM
+        if (n_seg > S::MS) { __syncwarp(); continue; }
 #pragma unroll
         for (int q = 0; q < CPL; ++q) {
             const int c = CPL * lane + q;
-            *reinterpret_cast<uint4 *>(&s.ecol[c * 8]) = *reinterpret_cast<const uint4 *>(cols16 + (c0 + c) * 8);
+            const uint64_t pc = c0 + (uint64_t)q * 32 + lane;   // physical chunk
+            *reinterpret_cast<uint4 *>(&s.ecol[c * 8]) = *reinterpret_cast<const uint4 *>(cols16 + pc * 8);
             if constexpr (kVals) {
                 constexpr int kVec = (int)sizeof(VT) * 8 / 16;
 #pragma unroll
                 for (int t = 0; t < kVec; ++t)
-                    reinterpret_cast<uint4 *>(&s.eval[c * 8])[t] = reinterpret_cast<const uint4 *>(vals + (c0 + c) * 8)[t];
+                    reinterpret_cast<uint4 *>(&s.eval[c * 8])[t] = reinterpret_cast<const uint4 *>(vals + pc * 8)[t];
             }
-            s.chunk_seg[c] = (uint8_t)__popcll(T & ((1ull << c) - 1ull));
+            s.chunk_seg[c] = (uint8_t)(s.tpre[c >> 5] + __popc(s.tw[c >> 5] & ((1u << (c & 31)) - 1u)));
         }
         for (int r = 0; r < n_seg; ++r) { s.head[r][lane] = -1; s.sup[r][lane] = 0; }
         __syncwarp();
@@ -262,12 +279,13 @@ __global__ void __launch_bounds__(kPlaceWarps * 32) place_step_kernel(uint16_t *
 #pragma unroll
         for (int q = 0; q < CPL; ++q) {
             const int c = CPL * lane + q;
-            *reinterpret_cast<uint4 *>(cols16 + (c0 + c) * 8) = *reinterpret_cast<const uint4 *>(&s.ocol[c * 8]);
+            const uint64_t pc = c0 + (uint64_t)q * 32 + lane;
+            *reinterpret_cast<uint4 *>(cols16 + pc * 8) = *reinterpret_cast<const uint4 *>(&s.ocol[c * 8]);
             if constexpr (kVals) {
                 constexpr int kVec = (int)sizeof(VT) * 8 / 16;
 #pragma unroll
                 for (int t = 0; t < kVec; ++t)
-                    reinterpret_cast<uint4 *>(vals + (c0 + c) * 8)[t] = reinterpret_cast<const uint4 *>(&s.oval[c * 8])[t];
+                    reinterpret_cast<uint4 *>(vals + pc * 8)[t] = reinterpret_cast<const uint4 *>(&s.oval[c * 8])[t];
             }
         }
         __syncwarp();
@@ -276,21 +294,24 @@ __global__ void __launch_bounds__(kPlaceWarps * 32) place_step_kernel(uint16_t *
 
 template <typename VT, int CPL>
 static int launch_place(uint16_t *cols16, VT *vals, const uint32_t *tails, uint64_t n_steps, int n_cols, int sms, cudaStream_t st) {
-    const size_t smem = sizeof(PlaceScratch<VT, CPL>) * kPlaceWarps;
-    VS_CUDA(cudaFuncSetAttribute(place_step_kernel<VT, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned blocks = (unsigned)std::min<uint64_t>((n_steps + kPlaceWarps - 1) / kPlaceWarps, (uint64_t)sms * 2);
-    place_step_kernel<VT, CPL><<<blocks, kPlaceWarps * 32, smem, st>>>(cols16, vals, tails, n_steps, n_cols);
+    constexpr int PW = 8;   // warps per CTA (the scratch of a 256-chunk step is 21 KB)
+    const size_t smem = sizeof(PlaceScratch<VT, CPL>) * PW;
+    auto kern = place_step_kernel<VT, CPL, PW>;
+    VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n_steps + PW - 1) / PW, (uint64_t)sms * (CPL >= 8 ? 1 : 2));
+    VS_REQUIRE(smem <= 227 * 1024, VS_ERR_UNSUPPORTED, "placement scratch does not fit shared memory");
+    kern<<<blocks, PW * 32, smem, st>>>(cols16, vals, tails, n_steps, n_cols);
     VS_CUDA(cudaGetLastError());
     return VS_OK;
 }
 
 // The scan kernel reads a chunk's "last chunk of its row" flag from bit 15 of the chunk's first entry
 // (columns are < 32768), so it needs no row pointers and no separate mask stream.
-__global__ void mark_tails_kernel(uint16_t *cols16, const uint32_t *tails, uint64_t n_chunks) {
-    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void mark_tails_kernel(uint16_t *cols16, const uint32_t *tails, uint64_t n_chunks, int cpl_shift) {
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // logical chunk
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; c < n_chunks; c += stride)
-        if ((tails[c >> 5] >> (c & 31)) & 1u) cols16[c * 8] |= 0x8000u;
+        if ((tails[c >> 5] >> (c & 31)) & 1u) cols16[ws_phys_chunk(c, cpl_shift) * 8] |= 0x8000u;
 }
 
 
@@ -325,7 +346,10 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
     VS_CUDA(cudaMalloc(&idx->part_row_begin, sizeof(uint32_t) * (size_t)(P + 1)));
     VS_CUDA(cudaMalloc(&idx->part_win_begin, sizeof(uint32_t) * (size_t)(P + 1)));
     part_rows_kernel<<<(P + 1 + 255) / 256, 256, 0, st>>>(d_cptr, N, P, idx->part_row_begin);
-    part_windows_kernel<<<1, 32, 0, st>>>(d_cptr, idx->part_row_begin, P, idx->part_win_begin, d_nwin);
+    // chunks per lane per scan step (scan.cu): 8 binary, 2 fp16/bf16 values, 1 fp32 values
+    idx->cpl_shift = idx->kind == 2 ? 3 : (idx->store_dtype == VS_F32 ? 0 : 1);
+    const int cpl_shift = idx->cpl_shift;
+    part_windows_kernel<<<1, 32, 0, st>>>(d_cptr, idx->part_row_begin, P, cpl_shift, idx->part_win_begin, d_nwin);
     uint64_t n_windows = 0;
     VS_CUDA(cudaMemcpyAsync(&n_windows, d_nwin, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     VS_CUDA(cudaStreamSynchronize(st));
@@ -353,7 +377,7 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
     fill_rows_kernel<VT><<<blocks, 256, 0, st>>>(d_crow, crow_dtype, d_col, col_dtype, d_val, val_dtype, N,      \
                                                  idx->n_cols, idx->nnz, d_cptr, idx->part_row_begin,             \
                                                  idx->part_win_begin,                                           \
-                                                 P, (uint16_t *)idx->cols, (VT *)idx->vals, idx->tails,          \
+                                                 P, cpl_shift, (uint16_t *)idx->cols, (VT *)idx->vals, idx->tails, \
                                                  idx->row_chunk, d_err)
         if (idx->kind == 2) VS_FILL(NoVal);
         else if (idx->store_dtype == VS_F32) VS_FILL(float);
@@ -362,17 +386,15 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
 #undef VS_FILL
     }
     if (N > 0 && idx->bank_aware && n_windows) {
-        // scan.cu: fp32 values keep one chunk per lane (32-chunk steps), everything else two (64-chunk steps)
-        const bool pair = !(idx->kind == 1 && idx->store_dtype == VS_F32);
-        const uint64_t n_steps = pair ? n_windows / 2 : n_windows;
+        const uint64_t n_steps = n_windows >> cpl_shift;
         int rc;
-        if (idx->kind == 2) rc = launch_place<NoVal, 2>((uint16_t *)idx->cols, (NoVal *)nullptr, idx->tails, n_steps, (int)idx->n_cols, idx->n_ctas, st);
+        if (idx->kind == 2) rc = launch_place<NoVal, 8>((uint16_t *)idx->cols, (NoVal *)nullptr, idx->tails, n_steps, (int)idx->n_cols, idx->n_ctas, st);
         else if (idx->store_dtype == VS_F32) rc = launch_place<float, 1>((uint16_t *)idx->cols, (float *)idx->vals, idx->tails, n_steps, (int)idx->n_cols, idx->n_ctas, st);
         else if (idx->store_dtype == VS_F16) rc = launch_place<__half, 2>((uint16_t *)idx->cols, (__half *)idx->vals, idx->tails, n_steps, (int)idx->n_cols, idx->n_ctas, st);
         else rc = launch_place<__nv_bfloat16, 2>((uint16_t *)idx->cols, (__nv_bfloat16 *)idx->vals, idx->tails, n_steps, (int)idx->n_cols, idx->n_ctas, st);
         if (rc != VS_OK) return rc;
     }
-    if (n_windows) mark_tails_kernel<<<2048, 256, 0, st>>>((uint16_t *)idx->cols, idx->tails, n_windows * 32ull);
+    if (n_windows) mark_tails_kernel<<<2048, 256, 0, st>>>((uint16_t *)idx->cols, idx->tails, n_windows * 32ull, cpl_shift);
     int h_err = 0;
     VS_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     VS_CUDA(cudaStreamSynchronize(st));
@@ -387,19 +409,49 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
     return VS_OK;
 }
 
+// ---- diagnostic: shared-memory wavefronts the scan's gathers cost on this index (distinct addresses per bank; equal
+// columns broadcast).  One warp per step; out[0] += wavefronts, out[1] += gather instructions.
+__global__ void gather_wavefronts_kernel(const uint16_t *cols16, uint64_t n_steps, int cpl, unsigned long long *out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long wf = 0, ng = 0;
+    for (uint64_t step = warp; step < n_steps; step += n_warps)
+        for (int i = 0; i < cpl; ++i) {
+            const uint16_t *ch = cols16 + ((step * cpl + i) * 32 + lane) * 8;
+            for (int j = 0; j < 8; ++j) {
+                const unsigned col = ch[j] & (j == 0 ? 0x7fffu : 0xffffu);
+                const unsigned same_col = __match_any_sync(0xffffffffu, col);
+                const bool leader = (__ffs(same_col) - 1) == lane;   // one access per distinct address
+                const unsigned same_bank = __match_any_sync(0xffffffffu, leader ? (col & 31u) : 0xffffu + lane);
+                const int m = leader ? __popc(same_bank) : 1;
+                wf += __reduce_max_sync(0xffffffffu, (unsigned)m);
+                ng += 1;
+            }
+        }
+    if (lane == 0) { atomicAdd(&out[0], wf); atomicAdd(&out[1], ng); }
+}
+
+int debug_gather_wavefronts(const vs_index *idx, unsigned long long *d_out2, cudaStream_t st) {
+    VS_CUDA(cudaMemsetAsync(d_out2, 0, 16, st));
+    const uint64_t n_steps = idx->n_windows >> idx->cpl_shift;
+    if (n_steps) gather_wavefronts_kernel<<<1024, 256, 0, st>>>((const uint16_t *)idx->cols, n_steps, 1 << idx->cpl_shift, d_out2);
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
 // ---- export: WS -> CSR (int64 crow/col, fp32 val), for SparseIndex.save (upstream index.py:181-202)
 __global__ void export_len_kernel(const WsView idx, const uint32_t *row_chunk, uint64_t *len) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > idx.n_rows) return;
     if (r == idx.n_rows) { len[r] = 0; return; }
     const uint16_t *c16 = (const uint16_t *)idx.cols;
-    uint64_t a = (uint64_t)row_chunk[r] * 8ull;
-    // the row's chunk count comes from its tail bit: walk chunks until the tail
-    uint64_t ch = row_chunk[r];
-    while (!((idx.tails[ch >> 5] >> (ch & 31)) & 1u)) ++ch;
-    uint64_t e = (ch + 1) * 8ull;
+    // the row's chunk count comes from its tail bit: walk (logical) chunks until the tail
     uint64_t n = 0;
-    for (uint64_t j = a; j < e; ++j) n += ((c16[j] & 0x7fffu) != (uint16_t)idx.n_cols);
+    for (uint64_t ch = row_chunk[r];; ++ch) {
+        const uint64_t a = ws_phys_chunk(ch, idx.cpl_shift) * 8ull;
+        for (int j = 0; j < 8; ++j) n += ((c16[a + j] & 0x7fffu) != (uint16_t)idx.n_cols);
+        if ((idx.tails[ch >> 5] >> (ch & 31)) & 1u) break;
+    }
     len[r] = n;
 }
 
@@ -410,17 +462,18 @@ __global__ void export_fill_kernel(const WsView idx, const uint32_t *row_chunk, 
     out_crow[r] = (int64_t)crow[r];
     if (r == idx.n_rows) return;
     const uint16_t *c16 = (const uint16_t *)idx.cols;
-    uint64_t a = (uint64_t)row_chunk[r] * 8ull;
+    const uint64_t ch0 = row_chunk[r];
     uint64_t o = crow[r], n = crow[r + 1] - crow[r];
     for (uint64_t j = 0, w = 0; w < n; ++j) {
-        uint16_t c = c16[a + j] & 0x7fffu;   // bit 15 of a chunk's first entry is the tail flag
+        const uint64_t at = ws_phys_chunk(ch0 + (j >> 3), idx.cpl_shift) * 8ull + (j & 7ull);
+        uint16_t c = c16[at] & 0x7fffu;   // bit 15 of a chunk's first entry is the tail flag
         if (c == (uint16_t)idx.n_cols) continue;
         out_col[o + w] = c;
         float v = 1.0f;
         if (idx.kind == 1) {
-            if (idx.store_dtype == VS_F32) v = ((const float *)idx.vals)[a + j];
-            else if (idx.store_dtype == VS_F16) v = __half2float(((const __half *)idx.vals)[a + j]);
-            else v = __bfloat162float(((const __nv_bfloat16 *)idx.vals)[a + j]);
+            if (idx.store_dtype == VS_F32) v = ((const float *)idx.vals)[at];
+            else if (idx.store_dtype == VS_F16) v = __half2float(((const __half *)idx.vals)[at]);
+            else v = __bfloat162float(((const __nv_bfloat16 *)idx.vals)[at]);
         }
         out_val[o + w] = v;
         ++w;

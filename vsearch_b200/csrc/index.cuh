@@ -4,14 +4,20 @@
 //   * entries are uint16 column ids packed 8 to a 16-byte CHUNK; every row owns
 //     ceil(len/8) chunks (>= 1), padded with the sentinel column V whose query slot is 0;
 //   * 32 consecutive chunks form a WINDOW = one coalesced 512-byte warp load;
+//   * a scan STEP of one warp covers 32 * C chunks, C = chunks per lane (8 for the binary index, 2 for
+//     16-bit values, 1 for fp32 values).  In LOGICAL order (the order rows run in) lane l of a step owns
+//     chunks l*C .. l*C+C-1, so a row of ~15 chunks spans only 2-3 lanes and ONE segmented warp scan
+//     serves 32*C chunks; in MEMORY the step is stored transposed -- logical chunk l*C+i sits at
+//     physical position i*32+l -- so that load #i of all 32 lanes is one coalesced 512-byte window
+//     (ws_phys_chunk());
 //   * the stream is cut into n_parts contiguous PARTS (one per resident warp of the
-//     persistent scan grid: #SMs x 24), each a whole number of 64-chunk steps holding whole
+//     persistent scan grid: #SMs x 24), each a whole number of steps holding whole
 //     rows, balanced by chunk count;
 //   * bit 15 of a chunk's FIRST entry is set when the chunk is the LAST chunk of its row (so
 //     n_cols <= 32,767): the scan kernel turns per-lane partial dot products into row scores
 //     with one segmented warp scan and reads no side stream and no row pointers;
-//   * tails[w] keeps the same flags as one bit per chunk of window w for the builders (bank
-//     placement, inverted lists); the scan does not read it;
+//   * tails[w] keeps the same flags as one bit per LOGICAL chunk for the builders (bank
+//     placement, export); the scan does not read it;
 //   * values (fp32 / fp16 / bf16) sit in a parallel array with the same chunk geometry;
 //     the binary bag-of-token index has none.
 // Algorithmic bytes of a pass: nnz*(2+b_val) + (N+1)*4.  The format streams
@@ -21,10 +27,14 @@
 #include "common.cuh"
 
 // windows of readable slack allocated past the end of the cols/vals/tails streams (prefetch never checks bounds)
-constexpr int kStreamSlack = 8;
-// warps per persistent scan CTA (= stream parts per SM).  24 warps x 80 registers fills the register file;
+constexpr int kStreamSlack = 16;
+// warps per persistent scan CTA (= stream parts per SM).  20 warps x 96 registers: the binary kernel keeps a whole
+// 8-chunk step in flight per lane (32 registers) and does not spill; 24 x 80 spills and measures 10 % slower;
 // 32 x 64 spills the prefetch ring.
-constexpr int kScanWarps = 24;
+#ifndef VS_SCAN_WARPS
+#define VS_SCAN_WARPS 20
+#endif
+constexpr int kScanWarps = VS_SCAN_WARPS;
 
 struct vs_index {
     int device = 0;
@@ -34,6 +44,7 @@ struct vs_index {
 
     // ---- WS format
     bool bank_aware = true;   // bank-aware entry placement at build (VSEARCH_B200_BANK_AWARE=0 disables: A/B runs)
+    int cpl_shift = 0;        // log2(chunks per lane per scan step): 3 binary, 1 fp16/bf16 values, 0 fp32 values
     int n_ctas = 0;           // persistent scan grid (= #SMs at build time)
     int warps_per_cta = kScanWarps;
     int n_parts = 0;          // n_ctas * warps_per_cta
@@ -62,6 +73,7 @@ struct vs_index {
 
     int64_t device_bytes = 0;
     int64_t stream_bytes = 0;
+    unsigned long long *scan_prof = nullptr;   // diagnostic (vs_debug_scan_profile): phase timestamps of the binary scan
 
     // ---- timing hook
     cudaEvent_t ev0[VS_TIMER_SLOTS] = {}, ev1[VS_TIMER_SLOTS] = {};
@@ -74,13 +86,20 @@ struct WsView {
     const uint4 *cols; const void *vals; const uint32_t *tails;
     const uint32_t *part_win_begin; const uint32_t *part_row_begin; const uint32_t *row_chunk;
     int64_t n_rows, n_cols;
-    int kind, store_dtype;
+    int kind, store_dtype, cpl_shift;
 };
+// logical chunk index (row order) -> physical chunk position in cols / vals: inside its step of 32 << cpl_shift
+// chunks, logical l*C+i is stored at i*32+l
+__host__ __device__ __forceinline__ uint64_t ws_phys_chunk(uint64_t c, int cpl_shift) {
+    const uint64_t m = (32ull << cpl_shift) - 1ull, r = c & m;
+    return (c & ~m) | ((r & ((1ull << cpl_shift) - 1ull)) << 5) | (r >> cpl_shift);
+}
 inline WsView ws_view(const vs_index *i) {
     WsView v;
     v.cols = i->cols; v.vals = i->vals; v.tails = i->tails;
     v.part_win_begin = i->part_win_begin; v.part_row_begin = i->part_row_begin; v.row_chunk = i->row_chunk;
     v.n_rows = i->n_rows; v.n_cols = i->n_cols; v.kind = i->kind; v.store_dtype = i->store_dtype;
+    v.cpl_shift = i->cpl_shift;
     return v;
 }
 
@@ -89,5 +108,6 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
                    const void *d_val, int val_dtype, cudaStream_t st);
 int export_ws_csr(const vs_index *idx, int64_t *d_crow, int64_t *d_col, float *d_val, cudaStream_t st);
 int build_inverted(vs_index *idx, cudaStream_t st);
+int debug_gather_wavefronts(const vs_index *idx, unsigned long long *d_out2, cudaStream_t st);
 int build_dense_index(vs_index *idx, const void *d_x, int x_dtype, int64_t ld, cudaStream_t st);
 }  // namespace vs

@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(kInvBuildThreads, 1) inv_build_kernel(const Ws
     const uint64_t base = FILL ? bl.blk_base[b] : 0ull;
     for (int64_t r = r0 + tid; r < r1; r += kInvBuildThreads) {
         const uint32_t c0 = idx.row_chunk[r], c1 = idx.row_chunk[r + 1];
-        for (uint32_t ch = c0; ch < c1; ++ch) {
+        for (uint32_t lc = c0; lc < c1; ++lc) {
+            const uint64_t ch = ws_phys_chunk(lc, idx.cpl_shift);
             const uint4 u = idx.cols[ch];
             const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(kInvBuildThreads, 1) inv_build_kernel(const Ws
                     const uint64_t pos = base + slot;
                     bl.post_row[pos] = (uint16_t)(r - r0);
                     if (idx.kind == 1) {
-                        const uint64_t src = (uint64_t)ch * 8ull + e;
+                        const uint64_t src = ch * 8ull + e;
                         if (idx.store_dtype == VS_F32) ((float *)bl.post_val)[pos] = ((const float *)idx.vals)[src];
                         else ((uint16_t *)bl.post_val)[pos] = ((const uint16_t *)idx.vals)[src];
                     }

@@ -5,11 +5,14 @@
 // One persistent CTA per SM, kScanWarps (24) warps.  Per query ("pass"):
 //   1. the dense fp32 query vector (V+1 slots, slot V = 0 for padding) is pulled into shared
 //      memory with 1-D bulk TMA copies (cp.async.bulk + mbarrier);
-//   2. every warp streams ITS part of the WS index (index.cuh): one 1024-byte double window (64
-//      chunks) per step, two adjacent 16-byte chunks per lane, D steps in flight per warp (register
-//      ring) -- loads never depend on row pointers, the row-end ("tail") flag of a chunk rides in
-//      bit 15 of its first entry; each lane gathers q[col] for its 16 entries from shared memory;
-//   3. ONE segmented warp scan per 64 chunks (6 shuffles) turns lane partials into row scores;
+//   2. every warp streams ITS part of the WS index (index.cuh) in steps of 32*C chunks, C consecutive (logical)
+//      chunks per lane stored transposed so every load is a coalesced 512-byte window -- C = 8 for the binary index
+//      (scan_bin_kernel: a whole step in flight per warp), 2 for 16-bit values, 1 for fp32 values (register ring of D
+//      steps); loads never depend on row pointers, the row-end ("tail") flag of a chunk rides in bit 15 of its first
+//      entry; each lane gathers q[col] for its entries from shared memory;
+//   3. ONE segmented warp scan per step turns lane partials into row scores -- with 8 chunks per lane a row of ~15
+//      chunks spans 2-3 lanes, so the scan needs 1-2 shuffle levels per 256 chunks (the levels nobody needs are
+//      skipped) instead of 5 per 64;
 //   4. the first rows of a pass are sampled into shared memory and ONE CTA-wide radix select sets the threshold;
 //      afterwards a float pre-filter rejects almost every row, rows whose rank key beats the threshold are appended
 //      to the warp's PRIVATE region with plain stores, and a warp whose region runs low raises a join epoch that all
@@ -39,11 +42,21 @@ struct ScanParams {
     int64_t n_rows;
     int B;
     int k;
+    int kout;              // keys per (query, CTA) list handed to the merge kernel (binary scan: > k, see scan_kout)
     int cap;               // CTA candidate buffer entries (>= k + kStage)
     int vpad;              // floats per prepared query (multiple of 4, > V)
     int score_round;
     uint32_t sentinel;     // V | V << 16
+    unsigned long long *prof;  // diagnostic: per (CTA, pass) phase timestamps (globaltimer ns), or nullptr
 };
+constexpr int kProfSlots = 8;
+__device__ __forceinline__ void prof_mark(const ScanParams &p, int b, int slot) {
+    if (p.prof != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.prof[((size_t)blockIdx.x * p.B + b) * kProfSlots + slot] = t;
+    }
+}
 
 // ---- per-chunk payload -----------------------------------------------------------------
 template <int VT> struct Chunk;
@@ -267,13 +280,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         constexpr int CPL = PAIR ? 2 : 1;       // chunks per lane per step
         constexpr int CPS = 32 * CPL;           // chunks per step
         constexpr int VS = (VT == 1) ? 2 : 1;   // uint4 of values per chunk
-        const uint4 *cp = p.cols + (uint64_t)w_begin * 32ull + CPL * lane;
-        const uint4 *vp = (const uint4 *)p.vals + ((uint64_t)w_begin * 32ull + CPL * lane) * VS;
+        // transposed steps (index.cuh): the lane's chunk #i of a step sits at step base + i*32 + lane
+        const uint4 *cp = p.cols + (uint64_t)w_begin * 32ull + lane;
+        const uint4 *vp = (const uint4 *)p.vals + ((uint64_t)w_begin * 32ull + lane) * VS;
         Chunk<VT> ra[D], rb[PAIR ? D : 1];
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             load_chunk<VT>(ra[j], cp + j * CPS, vp + j * CPS * VS);
-            if constexpr (PAIR) load_chunk<VT>(rb[j], cp + j * CPS + 1, vp + (j * CPS + 1) * VS);
+            if constexpr (PAIR) load_chunk<VT>(rb[j], cp + j * CPS + 32, vp + (j * CPS + 32) * VS);
         }
         float carry = 0.f;
         uint32_t row = row0;
@@ -293,7 +307,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     {                                                                                                              \
         VS_PROCESS(SAMPLE, J)                                                                                      \
         load_chunk<VT>(ra[J], cp + (D + J) * CPS, vp + (D + J) * CPS * VS);                                        \
-        if constexpr (PAIR) load_chunk<VT>(rb[J], cp + (D + J) * CPS + 1, vp + ((D + J) * CPS + 1) * VS);          \
+        if constexpr (PAIR) load_chunk<VT>(rb[J], cp + (D + J) * CPS + 32, vp + ((D + J) * CPS + 32) * VS);        \
     }
 #define VS_ADVANCE()                                                                                               \
     {                                                                                                              \
@@ -344,6 +358,267 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     }
 }
 
+// =====================================================================================================================
+// K2: binary bag-of-token scan, 8 chunks per lane per step (256 chunks = 4 KB of column ids per warp step).
+// Lane l owns the LOGICAL chunks 8l .. 8l+7 of the step (stored transposed: load #i of the warp is one coalesced
+// 512-byte window), so a row of ~15 chunks spans 2-3 lanes: one segmented warp scan per 256 chunks, and the levels
+// of that scan which no lane needs are skipped (usually 1-2 shuffles instead of 5).  The whole next step is in flight
+// while the current one is processed: chunk i's registers are refilled right after its gathers.
+// Per lane and step:  d[i] = sum of q[col] over chunk i;  the lane's chunks are walked in order -- the part up to
+// its FIRST row end is `head` (completed by what the lanes to the left hand over), the part after its LAST row end
+// is `v` (handed to the right); rows that start AND end inside the lane (shorter than 8 chunks: rare) are scored
+// locally in a warp-uniform side loop.
+constexpr int kBinC = 8;
+
+struct StepFlags {
+    uint32_t F;       // lanes with at least one row end
+    int nend;         // row ends in this lane
+    int rank;         // row ends in the lanes before this one
+    int total;        // row ends in the step
+    bool multi;       // some lane holds more than one row end
+};
+
+__device__ __forceinline__ StepFlags step_flags(const uint4 (&r)[kBinC], const uint32_t lt) {
+    StepFlags f;
+    uint32_t fm = 0;
+#pragma unroll
+    for (int i = 0; i < kBinC; ++i) fm |= ((r[i].x >> 15) & 1u) << i;
+    f.nend = __popc(fm);
+    f.F = __ballot_sync(0xffffffffu, fm != 0);
+    f.multi = __any_sync(0xffffffffu, f.nend > 1);
+    if (!f.multi) {
+        f.rank = __popc(f.F & lt);
+        f.total = __popc(f.F);
+    } else {
+        f.rank = 0;
+        f.total = 0;
+#pragma unroll
+        for (int bit = 0; bit < 4; ++bit) {   // nend <= 8
+            const uint32_t m = __ballot_sync(0xffffffffu, (f.nend >> bit) & 1);
+            f.rank += __popc(m & lt) << bit;
+            f.total += __popc(m) << bit;
+        }
+    }
+    return f;
+}
+
+__device__ __forceinline__ float bin_chunk_dot(const uint4 &c, const uint32_t qs) {
+    float g[8];
+    g[0] = lds_f32(qs + ((c.x & 0x7fffu) << 2));   // entry 0 carries the row-end flag in bit 15
+    g[1] = lds_f32(qs + (__byte_perm(c.x, 0, 0x4432) << 2));
+    g[2] = lds_f32(qs + (__byte_perm(c.y, 0, 0x4410) << 2));
+    g[3] = lds_f32(qs + (__byte_perm(c.y, 0, 0x4432) << 2));
+    g[4] = lds_f32(qs + (__byte_perm(c.z, 0, 0x4410) << 2));
+    g[5] = lds_f32(qs + (__byte_perm(c.z, 0, 0x4432) << 2));
+    g[6] = lds_f32(qs + (__byte_perm(c.w, 0, 0x4410) << 2));
+    g[7] = lds_f32(qs + (__byte_perm(c.w, 0, 0x4432) << 2));
+    return ((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]));
+}
+
+struct BinSmem {
+    uint64_t *cbuf;      // kCapMax keys: shared top-k set + per-warp private regions (topk.cuh)
+    uint32_t *hist;      // 256 words: radix-select scratch of the exact fallback
+    uint32_t *fine;      // kHistFine
+    uint32_t *coarse;    // kHistCoarse
+};
+__device__ __forceinline__ BinSmem bin_smem(uint8_t *smem, const ScanParams &p) {
+    BinSmem L;
+    L.cbuf = reinterpret_cast<uint64_t *>(smem + (size_t)p.vpad * 4);
+    L.hist = reinterpret_cast<uint32_t *>(L.cbuf + kCapMax);
+    L.fine = L.hist + 256;
+    L.coarse = L.fine + kHistFine;
+    return L;
+}
+
+// one row score -> (DIAG) the score matrix; float pre-filter, exact 64-bit test, count in the score histogram, append
+// to the warp's private region
+template <bool ROUND, bool DIAG>
+__device__ __forceinline__ void emit_row(const bool valid, float s, const uint32_t rid, const float tau_s, int &n_keys,
+                                         const uint32_t lt, uint8_t *smem, CtaState *st, const ScanParams &p, const int b) {
+    if constexpr (ROUND) s = round_score(s, p.score_round);
+    if constexpr (DIAG) {
+        if (valid) p.scores_out[(size_t)b * p.n_rows + rid] = s + 0.0f;
+    }
+    const bool maybe = valid && (s >= tau_s);
+    if (__any_sync(0xffffffffu, maybe)) {
+        const BinSmem L = bin_smem(smem, p);
+        const uint64_t tau = *(volatile uint64_t *)&st->tau;   // exact k-th key of the last CTA-wide join (0: none yet)
+        const uint64_t key = make_key(s, rid);
+        const bool ins = maybe && key > tau;
+        hist_count(L.coarse, L.fine, ins, (uint32_t)(key >> 32));
+        private_insert<kScanWarps>(ins, key, L.cbuf, n_keys, lt);
+    }
+}
+
+// MULTI: some lane of the step holds more than one row end (rows shorter than 8 chunks).  A row that starts AND ends
+// inside a lane is scored on the spot (warp-collective emit per chunk); the common case compiles without it.
+template <bool ROUND, bool DIAG, bool MULTI>
+__device__ __forceinline__ void process_step8(uint4 (&r)[kBinC], const uint4 *next, const StepFlags &f, const uint32_t qs,
+                                              const int lane, const uint32_t lt, float &carry, uint32_t &row, int &n_keys,
+                                              const float tau_s, uint8_t *smem, CtaState *st, const ScanParams &p,
+                                              const int b) {
+    // walk the lane's chunks in order
+    float run = 0.f, head = 0.f;
+    bool seen = false;
+    [[maybe_unused]] uint32_t ord = 0;   // MULTI: row ends of this lane so far
+#pragma unroll
+    for (int i = 0; i < kBinC; ++i) {
+        const bool end_i = (r[i].x & 0x8000u) != 0;   // bit 15 of the chunk's first entry: last chunk of its row
+        run += bin_chunk_dot(r[i], qs);
+        r[i] = ldg_stream(next + i * 32);   // same registers: chunk i of the next step
+        if constexpr (MULTI) {
+            emit_row<ROUND, DIAG>(end_i && seen, run, row + (uint32_t)f.rank + ord, tau_s, n_keys, lt, smem, st, p, b);
+            ord += end_i ? 1u : 0u;
+        }
+        if (end_i) {
+            if (!seen) head = run;
+            seen = true;
+            run = 0.f;
+        }
+    }
+    float v = run;   // what this lane hands to its right neighbour: the part after its last row end
+    const uint32_t F = f.F;
+    if (lane == 0 && !(F & 1u)) v += carry;  // lane 0 passes the carry through unless a row ends inside it
+    // inclusive segmented scan of v; a flagged lane RESTARTS the sum.  reach = lanes back to the nearest flagged lane.
+    const uint32_t upto = F & (lt | (1u << lane));
+    const int reach = upto ? lane - (31 - __clz(upto)) : lane;
+    // level d is needed iff some lane >= d has reach >= d, i.e. ~F holds a run of d ones above bit 0 (warp-uniform)
+    const uint32_t z1 = (~F) >> 1;
+    if (z1) {
+        float o = __shfl_up_sync(0xffffffffu, v, 1);
+        if (reach >= 1) v += o;
+        const uint32_t z2 = z1 & (z1 >> 1);
+        if (z2) {
+            o = __shfl_up_sync(0xffffffffu, v, 2);
+            if (reach >= 2) v += o;
+            const uint32_t z4 = z2 & (z2 >> 2);
+            if (z4) {
+                o = __shfl_up_sync(0xffffffffu, v, 4);
+                if (reach >= 4) v += o;
+                const uint32_t z8 = z4 & (z4 >> 4);
+                if (z8) {
+                    o = __shfl_up_sync(0xffffffffu, v, 8);
+                    if (reach >= 8) v += o;
+                    if (z8 & (z8 >> 8)) {
+                        o = __shfl_up_sync(0xffffffffu, v, 16);
+                        if (reach >= 16) v += o;
+                    }
+                }
+            }
+        }
+    }
+    const float rot = __shfl_sync(0xffffffffu, v, (lane + 31) & 31);  // left neighbour's running sum; lane 0 gets lane 31's
+    const float incoming = (lane == 0) ? carry : rot;
+    carry = rot;  // only lane 0's copy is used: the open row's partial sum at the end of this step
+    // the row ending at this lane's first row end
+    emit_row<ROUND, DIAG>(seen, incoming + head, row + (uint32_t)f.rank, tau_s, n_keys, lt, smem, st, p, b);
+    row += (uint32_t)f.total;
+}
+
+template <bool ROUND, bool DIAG>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_bin_kernel(const ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ CtaState st;
+    const uint32_t qs = smem_u32(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = lanemask_lt();
+    const int part = blockIdx.x * kScanWarps + warp;
+    const uint32_t w_begin = p.part_win_begin[part];
+    const int nstep = (int)(p.part_win_begin[part + 1] - w_begin) / kBinC;   // parts are whole steps (build_index.cu)
+    const uint32_t row0 = p.part_row_begin[part];
+    const uint32_t q_bytes = (uint32_t)p.vpad * 4u;
+    constexpr int SC = 32 * kBinC;   // chunks per step
+
+    if (tid == 0) {
+        mbar_init(&st.mbar, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    uint32_t phase = 0;
+    for (int b = 0; b < p.B; ++b) {
+        prof_mark(p, b, 0);
+        if (tid == 0) {
+            cta_state_reset(&st);
+            fence_proxy_async();  // earlier generic-proxy reads of qs are ordered before the async writes
+            mbar_arrive_expect_tx(&st.mbar, q_bytes);
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.q + (size_t)b * p.vpad);
+            for (uint32_t off = 0; off < q_bytes; off += 16384u) {
+                uint32_t n = min(16384u, q_bytes - off);
+                bulk_g2s(smem + off, src + off, n, &st.mbar);
+            }
+        }
+        // the first step's loads go out before anybody waits for the query vector
+        const uint4 *cp = p.cols + (uint64_t)w_begin * 32ull + lane;
+        uint4 r[kBinC];
+#pragma unroll
+        for (int i = 0; i < kBinC; ++i) r[i] = ldg_stream(cp + i * 32);
+        const BinSmem L = bin_smem(smem, p);
+        for (int i = tid; i < kHistFine + kHistCoarse; i += kScanThreads) L.fine[i] = 0u;   // coarse follows fine
+        __syncthreads();          // cnt/tau reset, empty histogram visible
+        mbar_wait(&st.mbar, phase);
+        phase ^= 1u;
+        prof_mark(p, b, 1);
+
+        float carry = 0.f;
+        uint32_t row = row0;
+        int n_keys = 0;   // keys in this warp's private region
+        uint32_t epoch = 0;
+        // ---- stream.  No sampling phase: while the pre-filter is still open (-inf) every row is a candidate and is
+        // counted in the score histogram; a warp whose region cannot take the next step's rows asks the histogram for
+        // the threshold (warp_refresh: no barrier), and only if that does not make room -- equal scores en masse,
+        // adversarial row order -- the CTA falls back to the exact re-selection (join protocol, topk.cuh).
+        for (int s = 0; s < nstep; ++s) {
+            const uint64_t gate = gate_load(&st);
+            const StepFlags f = step_flags(r, lt);
+            if (gate_epoch(gate) != epoch || n_keys + f.total > ScanGeom::kPrivate) {
+                if (gate_epoch(gate) == epoch) warp_refresh<kScanWarps>(L.coarse, L.fine, p.k, L.cbuf, n_keys, &st);
+                join_if_needed<kScanThreads, kScanWarps>(gate, epoch, f.total, L.cbuf, n_keys, p.k, L.hist, &st);
+            }
+            const float tau_s = gate_tau_score(gate_load(&st));
+            if (f.multi)
+                process_step8<ROUND, DIAG, true>(r, cp + (size_t)(s + 1) * SC, f, qs, lane, lt, carry, row, n_keys, tau_s, smem,
+                                                 &st, p, b);
+            else
+                process_step8<ROUND, DIAG, false>(r, cp + (size_t)(s + 1) * SC, f, qs, lane, lt, carry, row, n_keys, tau_s, smem,
+                                                  &st, p, b);
+        }
+        if (warp == 0) prof_mark(p, b, 4);
+        finish_streaming<kScanThreads, kScanWarps>(epoch, L.cbuf, n_keys, p.k, L.hist, &st);
+        prof_mark(p, b, 5);
+        // ---- end of pass: everything at or above the final histogram threshold goes to the merge kernel (between k
+        // and kout keys); more than kout (a bucket full of equal scores) -> the exact CTA-wide select
+        if (tid == 0) st.scratch = 0;
+        __syncthreads();
+        {
+            uint64_t *out = p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.kout;
+            const uint64_t tmin = (uint64_t)hist_threshold(L.coarse, L.fine, p.k) << 32;
+            const int n_sh = (int)st.cnt;
+            const uint64_t *priv = L.cbuf + kSharedKeys + warp * ScanGeom::kPrivate;
+            for (int i = tid; i < n_sh; i += kScanThreads) {
+                const uint64_t x = L.cbuf[i];
+                if (x != 0ull && x >= tmin) { const uint32_t o = atomicAdd(&st.scratch, 1u); if (o < (uint32_t)p.kout) out[o] = x; }
+            }
+            for (int i = lane; i < n_keys; i += 32) {
+                const uint64_t x = priv[i];
+                if (x >= tmin) { const uint32_t o = atomicAdd(&st.scratch, 1u); if (o < (uint32_t)p.kout) out[o] = x; }
+            }
+            __syncthreads();
+            const uint32_t total = *(volatile uint32_t *)&st.scratch;
+            if (total > (uint32_t)p.kout) {   // uniform
+                __syncthreads();
+                cta_write_topk<kScanThreads, kScanWarps>(L.cbuf, n_keys, p.k, L.hist, &st, out);
+                for (int i = p.k + tid; i < p.kout; i += kScanThreads) out[i] = 0ull;
+            } else {
+                for (int i = (int)total + tid; i < p.kout; i += kScanThreads) out[i] = 0ull;
+            }
+        }
+        __syncthreads();  // everyone is done with qs / cbuf before the next pass overwrites them
+        prof_mark(p, b, 6);
+    }
+}
+
 // ---- query preparation: [B, ldq] any float dtype -> fp32 [B, vpad], zero padded, optionally
 // rounded through the index dtype first (upstream index.py:89 `q.type(self.vector.dtype)`).
 __global__ void prep_query_kernel(const void *q, int q_dtype, int64_t ldq, int64_t n_cols, int vpad, int round_mode,
@@ -365,6 +640,13 @@ size_t scan_smem_bytes(int vpad, int cap) {
     (void)cap;
     return (size_t)vpad * 4 + (size_t)kCapMax * 8 + 256 * 4;
 }
+static size_t scan_bin_smem_bytes(int vpad) {
+    return (size_t)vpad * 4 + (size_t)kCapMax * 8 + 256 * 4 + (size_t)(kHistFine + kHistCoarse) * 4;
+}
+// Length of the per-(query, CTA) candidate lists the scan writes.  The binary kernel hands over every key at or above
+// its final histogram threshold -- between k and, for smooth score distributions, about 2k of them -- instead of
+// paying a CTA-wide exact select per pass; the valued kernels write exactly k.
+int scan_kout(const vs_index *idx, int k) { return idx->kind == 2 ? 2 * k + 64 : k; }
 
 int scan_cap_for_k(int k) { (void)k; return kCapMax; }
 
@@ -409,18 +691,35 @@ int launch_scan(const vs_index *idx, const float *d_qprep, int vpad, int64_t B, 
     p.n_rows = idx->n_rows;
     p.B = (int)B;
     p.k = k;
+    p.kout = scan_kout(idx, k);
     p.cap = scan_cap_for_k(k);
     p.vpad = vpad;
     p.score_round = score_round;
     p.sentinel = (uint32_t)idx->n_cols | ((uint32_t)idx->n_cols << 16);
+    p.prof = idx->scan_prof;
     size_t smem = scan_smem_bytes(vpad, p.cap);
     VS_REQUIRE(smem <= 227 * 1024, VS_ERR_UNSUPPORTED,
                "n_cols=%lld needs %zu bytes of shared memory (> 227 KB): vocabulary too large for the scan kernel",
                (long long)idx->n_cols, smem);
     static_assert(kStreamSlack >= 8, "prefetch ring deeper than the stream slack");
     static_assert(ScanGeom::kPrivate >= 3 * 64 + 32, "private region must take one group of steps");
+    static_assert(ScanGeom::kPrivate >= 32 * kBinC, "private region must take the rows of one binary step");
+    if (idx->kind == 2) {   // binary: 8 chunks per lane per step (idx->cpl_shift == 3)
+        smem = scan_bin_smem_bytes(vpad);
+        VS_REQUIRE(smem <= 227 * 1024, VS_ERR_UNSUPPORTED,
+                   "n_cols=%lld needs %zu bytes of shared memory (> 227 KB): vocabulary too large for the scan kernel",
+                   (long long)idx->n_cols, smem);
+        auto launch = [&](auto kern) -> int {
+            VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<idx->n_ctas, kScanThreads, smem, st>>>(p);
+            VS_CUDA(cudaGetLastError());
+            return VS_OK;
+        };
+        if (p.scores_out) return launch(scan_bin_kernel<true, true>);   // diagnostic path
+        if (p.score_round != VS_F32) return launch(scan_bin_kernel<true, false>);
+        return launch(scan_bin_kernel<false, false>);
+    }
     // <value type, steps in flight per warp, two chunks per lane?>; the placement at build uses the same mode
-    if (idx->kind == 2) return launch_scan_v<0, 3, true>(idx, p, smem, st);
     if (idx->store_dtype == VS_F32) return launch_scan_v<1, 2, false>(idx, p, smem, st);
     if (idx->store_dtype == VS_F16) return launch_scan_v<2, 2, true>(idx, p, smem, st);
     return launch_scan_v<3, 2, true>(idx, p, smem, st);

@@ -39,6 +39,7 @@ struct CtaState {
     uint32_t scratch;   // CTA-wide counter of the select routines
     uint32_t done;      // warps that finished streaming this pass
     uint32_t n_app;     // K3: keys in the CTA-wide append region cbuf[kSharedKeys, kCapMax) (may count past the end)
+    uint32_t tau_ob;    // K2: best histogram threshold so far, as ordered score bits (atomicMax)
 };
 static_assert(offsetof(CtaState, gate_tau_score) % 8 == 0, "gate must be 8-byte aligned");
 
@@ -49,6 +50,8 @@ __device__ __forceinline__ void cta_state_reset(CtaState *st) {
     st->gate_epoch = 0;
     st->done = 0;
     st->n_app = 0;
+    st->tau_ob = 0;
+    st->scratch = 0;
 }
 __device__ __forceinline__ uint64_t gate_load(const CtaState *st) {
     return *reinterpret_cast<const volatile uint64_t *>(&st->gate_tau_score);
@@ -146,6 +149,93 @@ __device__ __forceinline__ void cta_sample_select(uint64_t *cbuf, int n, int k, 
         if (mine[j] != 0ull && mine[j] >= kth) cbuf[atomicAdd(&st->cnt, 1u)] = mine[j];
     if (tid == 0) publish_tau(st, kth);  // 0 when the sample held fewer than k real keys: keep accepting everything
     __syncthreads();
+}
+
+// ---- score histogram (K2, scan.cu): every row that becomes a candidate is counted in a two-level histogram of its
+// ORDERED score bits (the high half of its rank key): 2^13 fine buckets (sign, exponent, 4 mantissa bits) and 128
+// coarse ones (each = 64 fine buckets).  The lower bound T of the highest fine bucket whose suffix count reaches k is
+// a safe filter at any time -- at least k rows with a score >= T have been seen, so a row scoring below T is not in
+// the top k -- and it only rises as rows are counted.  It replaces the sampling phase and its CTA-wide radix select:
+// a warp whose private region fills asks the histogram (one warp, ~100 instructions, no barrier), drops its keys
+// below T and goes on; at the end of a pass everything >= the final T (between k and ~2k keys) is handed to the merge
+// kernel.  The exact 64-bit machinery (cta_join) stays behind it for what a score bucket cannot separate: masses of
+// equal scores, adversarially ordered rows.
+constexpr int kHistFineBits = 13;
+constexpr int kHistFine = 1 << kHistFineBits;   // u32 counters: 32 KB
+constexpr int kHistCoarse = 128;
+
+// Count the warp's new candidates (`ins` lanes, ordered score bits `ob`).  Lanes of one fine bucket are aggregated
+// first: while the filter is still open every row is counted, and on a sparse query most rows share ONE score (0) --
+// per-lane atomics on one shared-memory word serialise.  All 32 lanes.
+__device__ __forceinline__ void hist_count(uint32_t *coarse, uint32_t *fine, bool ins, uint32_t ob) {
+    const uint32_t fb = ob >> (32 - kHistFineBits);
+    const uint32_t grp = __match_any_sync(0xffffffffu, ins ? fb : 0xffffffffu);
+    if (ins && (__ffs(grp) - 1) == (int)(threadIdx.x & 31)) {
+        const uint32_t n = (uint32_t)__popc(grp);
+        atomicAdd(&fine[fb], n);
+        atomicAdd(&coarse[fb >> (kHistFineBits - 7)], n);
+    }
+}
+
+// Called by all 32 lanes of a warp.  Returns the threshold as ordered score bits (bucket lower bound), 0 when fewer
+// than k rows have been counted.  Other warps may be counting meanwhile: every increment read here belongs to a
+// distinct real row of that bucket, so the answer is safe whatever the interleaving.
+static __device__ __noinline__ uint32_t hist_threshold(const uint32_t *coarse, const uint32_t *fine, int k) {
+    const int lane = threadIdx.x & 31;
+    const volatile uint32_t *vc = coarse + 4 * lane;
+    const uint32_t c[4] = {vc[0], vc[1], vc[2], vc[3]};
+    const uint32_t s = c[0] + c[1] + c[2] + c[3];
+    uint32_t incl = s;  // sum over lanes >= lane
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_down_sync(0xffffffffu, incl, d);
+        if (lane + d < 32) incl += o;
+    }
+    const uint32_t above = incl - s;
+    const bool mine = (above < (uint32_t)k) && ((uint32_t)k <= incl);
+    uint32_t cb = 0, above_cb = 0;
+    if (mine) {
+        uint32_t acc = above;
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {
+            if (acc < (uint32_t)k && acc + c[j] >= (uint32_t)k) { cb = 4 * lane + j; above_cb = acc; }
+            acc += c[j];
+        }
+    }
+    const uint32_t owner = __ballot_sync(0xffffffffu, mine);
+    if (owner == 0) return 0u;
+    const int src = __ffs(owner) - 1;
+    cb = __shfl_sync(0xffffffffu, cb, src);
+    above_cb = __shfl_sync(0xffffffffu, above_cb, src);
+    const volatile uint32_t *vf = fine + cb * 64 + 2 * lane;
+    const uint32_t f0 = vf[0], f1 = vf[1];
+    uint32_t incl2 = f0 + f1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_down_sync(0xffffffffu, incl2, d);
+        if (lane + d < 32) incl2 += o;
+    }
+    const uint32_t above2 = above_cb + incl2 - (f0 + f1);
+    const bool mine2 = (above2 < (uint32_t)k) && ((uint32_t)k <= above2 + f0 + f1);
+    const uint32_t fb = (above2 + f1 >= (uint32_t)k) ? cb * 64 + 2 * lane + 1 : cb * 64 + 2 * lane;
+    const uint32_t owner2 = __ballot_sync(0xffffffffu, mine2);
+    if (owner2 == 0) return (cb * 64) << (32 - kHistFineBits);   // fine counters lag the coarse ones: coarse bound
+    return __shfl_sync(0xffffffffu, fb, __ffs(owner2) - 1) << (32 - kHistFineBits);
+}
+
+// A warp raises the CTA's float pre-filter to the histogram threshold and drops its own keys below it.  All 32 lanes.
+template <int NW>
+__device__ __forceinline__ void warp_refresh(const uint32_t *coarse, const uint32_t *fine, int k, uint64_t *cbuf, int &n_priv,
+                                             CtaState *st) {
+    const uint32_t ob = hist_threshold(coarse, fine, k);
+    if (ob == 0) return;
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t old = atomicMax(&st->tau_ob, ob);
+        // a late writer may put back a slightly older (lower) bound: still a valid filter
+        if (ob > old) *(volatile uint32_t *)&st->gate_tau_score = __float_as_uint(key_score((uint64_t)ob << 32));
+    }
+    uint64_t *priv = cbuf + kSharedKeys + (threadIdx.x >> 5) * TopkGeom<NW>::kPrivate;
+    n_priv = warp_compact_ge(priv, n_priv, (uint64_t)ob << 32);
 }
 
 // ---- phase B: append this window's qualifying keys (`ins` lanes) to the warp's private region (room is
