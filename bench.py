@@ -343,8 +343,13 @@ def run_cfg2(ctx):
     retr = vs.Retriever(device=dev)
     retr.index = index
 
-    q_host = gen_queries(nnz=args.qnnz).pin_memory()
+    # queries travel as (token, weight) lists -- a torch sparse CSR tensor, what the reference's sparsifier emits
+    # (utils/sparse.py:8-19) -- unless --dense-queries asks for the [B, V] fp32 rows of round 1
+    q_host = gen_queries(nnz=args.qnnz)
+    q_host = q_host.pin_memory() if args.dense_queries else q_host.to_sparse_csr()
     q_dev = q_host.to(dev)
+    h2d_bytes = (q_host.numel() * 4 if args.dense_queries else
+                 q_host.crow_indices().numel() * 8 + q_host.col_indices().numel() * 8 + q_host.values().numel() * 4)
     ids_host = torch.empty((B, K), dtype=torch.int64).pin_memory()
     sc_host = torch.empty((B, K), dtype=torch.float32).pin_memory()
 
@@ -366,10 +371,14 @@ def run_cfg2(ctx):
         kern_ms = m["kernel_ms_per_launch"]
         if used == "scan":   # nnz * b_col + (N+1) * b_ptr, binary: b_val = 0; one pass per query (Q_tile = 1)
             bytes_pass = n_loc * TOKENS * 2 + (n_loc + 1) * 4
-            kernel, launches = "vs::scan_bin_kernel<0, 0>", steps * (3 if world == 1 else 4)
+            kernel = "vs::scan_bin_kernel<0, 0>"
         else:                # K3: postings of the query's tokens (uint16 block-local row ids; binary: no values)
             bytes_pass = int(args.qnnz * (n_loc * TOKENS / V)) * 2
-            kernel, launches = "vs::inv_search_kernel", steps * (4 if world == 1 else 5)
+            kernel = "vs::inv_search_kernel"
+        # our kernels per step: [prep_query (dense rows only)] + scan + merge; auto / inverted add the list kernel (extract
+        # or lists-from-CSR), the decision kernel and the inverted-list kernel (the loser of the two scoring kernels exits
+        # at once); N > 1 adds the merge of the gathered keys
+        launches = steps * ((2 if mode == "scan" else 5) + (1 if args.dense_queries else 0) + (1 if world > 1 else 0))
         achieved = B * bytes_pass / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
         traffic, traffic_src = profiled_traffic(used) if world == 1 else (None, None)
         peak = ctx.peaks["hbm"]
@@ -381,7 +390,7 @@ def run_cfg2(ctx):
                     "kernel_ms_per_step": kern_ms, "steps_timed": steps,
                     "kernel_share_of_step": m["kernel_share_of_step"],
                     "frac_of_8TBps": (achieved / 8000.0) if achieved else None, "q_tile": 1}
-        m["e2e"].update({"h2d_bytes_per_step": q_host.numel() * 4, "d2h_bytes_per_step": B * K * 12})
+        m["e2e"].update({"h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": B * K * 12})
         return {"mode": mode, "mode_used": used, "value": m["value"], "ms_per_step": m["ms_per_step"], "e2e": m["e2e"],
                 "gpu_launches": launches, "clocks": m["clocks"], "roofline": roofline}
 
@@ -420,8 +429,11 @@ def sparse_extra(ctx, name, batches):
     bytes_pass = n_loc * NNZ_CFG3 * 6 + (n_loc + 1) * 4   # uint16 column + fp32 value per entry, uint32 row pointers
     out = {}
     for bq in batches:
-        q_host = gen_queries(b=bq, nnz=QNNZ, seed=777).pin_memory()
+        q_host = gen_queries(b=bq, nnz=QNNZ, seed=777)
+        q_host = q_host.pin_memory() if ctx.args.dense_queries else q_host.to_sparse_csr()
         q_dev = q_host.to(dev)
+        h2d_bytes = (q_host.numel() * 4 if ctx.args.dense_queries else
+                     q_host.crow_indices().numel() * 8 + q_host.col_indices().numel() * 8 + q_host.values().numel() * 4)
         ids_host = torch.empty((bq, K_CFG3), dtype=torch.int64).pin_memory()
         sc_host = torch.empty((bq, K_CFG3), dtype=torch.float32).pin_memory()
 
@@ -442,7 +454,7 @@ def sparse_extra(ctx, name, batches):
             m = ctx.measure(step_resident, step_e2e, eng, bq, steps, 2, e2e_steps=max(2, steps // 2))
             used = index.last_mode()
             m["mode_used"] = used
-            m["e2e"].update({"h2d_bytes_per_step": q_host.numel() * 4, "d2h_bytes_per_step": bq * K_CFG3 * 12})
+            m["e2e"].update({"h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": bq * K_CFG3 * 12})
             if used == "scan":
                 kms = m["kernel_ms_per_launch"]
                 ach = bq * bytes_pass / (kms * 1e-3) / 1e9 if kms > 0 else None
@@ -545,7 +557,10 @@ def run_gpu(args):
             "config": {"workload": f"cfg2: binary bag-of-token index {N_TOTAL:,} x 29,523, 120 tokens/row, B={B}, "
                                    f"{args.qnnz} nnz/query, k=100",
                        "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
-                       "mode": args.mode, "mode_used": used_mode, "l2": "inputs larger than L2 (shard streams "
+                       "mode": args.mode, "mode_used": used_mode,
+                       "queries": "dense [B, V] fp32 rows" if args.dense_queries else
+                                  f"sparse (token, weight) lists, {args.qnnz} per query (torch sparse CSR -> vs_search_sparse)",
+                       "l2": "inputs larger than L2 (shard streams "
                                                 f"{stream_gb:.2f} GB per query pass; L2 is 126 MB)",
                        "index_build_s": round(build_s, 2)},
             "clocks": main_res["clocks"],
@@ -578,6 +593,7 @@ def main():
     ap.add_argument("--no-auto", action="store_true", help="skip the extra `auto`-mode measurement")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg3 / cfg4 measurements")
     ap.add_argument("--qnnz", type=int, default=QNNZ)
+    ap.add_argument("--dense-queries", action="store_true", help="queries as dense [B, V] fp32 rows instead of sparse (token, weight) lists")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=B, help="queries per step (default: the config's 1024; smaller only for profiling)")
     ap.add_argument("--rows", type=int, default=N_TOTAL, help="index rows (default: the config's 21,015,324; smaller only for profiling)")

@@ -12,7 +12,11 @@
  *  - every function returns a vs_status (0 = OK) and never throws; the message
  *    of the last failure on the calling thread is vs_last_error();
  *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the
- *    functions do not synchronise it unless stated ("SYNC");
+ *    functions do not synchronise it unless stated ("SYNC"): a search on a sparse /
+ *    bag-of-token index returns as soon as its kernels are enqueued -- host inputs are
+ *    staged through the caller's workspace (no allocation; pageable memory is consumed
+ *    before the call returns, pinned memory must stay valid until the stream has passed
+ *    the copy), and the scan-vs-inverted choice of the auto mode is made on the device;
  *  - pointers named d_* must be device pointers on the index's device; pointers
  *    named hd_* may be host or device (the library checks);
  *  - a handle may be used from one host thread at a time.
@@ -27,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VS_ABI_VERSION 1
+#define VS_ABI_VERSION 2
 
 typedef enum {
     VS_OK = 0,
@@ -92,6 +96,9 @@ int vs_index_export_csr(const vs_index *idx, int64_t *d_crow, int64_t *d_col, fl
  *             mirroring `q.type(vector.dtype)` / scores in the index dtype (index.py:89)
  *   d_workspace  >= vs_search_workspace_bytes(idx, B, k) bytes, 256-byte aligned
  * The [B, N] score matrix is never written. */
+/* Synchronisation: sparse / bag-of-token indices -- none (the first auto / inverted search on a handle builds the
+ * inverted lists once: SYNC that one time).  Dense index -- SYNC: the filtered sweeps read back one overflow counter
+ * per sweep. */
 #define VS_MAX_K 2048
 size_t vs_search_workspace_bytes(const vs_index *idx, int64_t B, int k);
 int vs_search(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int k, int mode,
@@ -104,6 +111,19 @@ int vs_search(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int
 int vs_search_keys(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int k, int mode,
                    int score_round, int64_t id_offset, uint64_t *d_keys,
                    void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Same search for SPARSE queries given as CSR-style (token, weight) lists -- what the reference's query sparsifier
+ * produces (utils/sparse.py:8-19: the a=768 activation budget, encoder/vdr.py:159-169) -- without the dense [B, V]
+ * detour: query b = sum_j hd_qw[j] * e(hd_qtok[j]) over j in [hd_qptr[b], hd_qptr[b+1]).
+ *   hd_qptr   B+1 offsets (VS_I32 | VS_I64), hd_qtok int32 columns, hd_qw float weights; all host or all device
+ *   tokens outside [0, n_cols) and zero weights are ignored, duplicate tokens of a query add up
+ *   outputs: d_ids + d_scores (as vs_search) and / or d_keys (as vs_search_keys); unused ones NULL
+ * 64 (token, weight) pairs are 512 bytes against the 118 KB of a dense fp32 query row.  The inverted lists take the
+ * pairs as they are; the scan kernels scatter them into their shared-memory query vector.  Sparse / bag-of-token
+ * indices only.  No synchronisation. */
+int vs_search_sparse(const vs_index *idx, const void *hd_qptr, int ptr_dtype, const int32_t *hd_qtok, const float *hd_qw,
+                     int64_t B, int k, int mode, int score_round, int64_t id_offset, int64_t *d_ids, float *d_scores,
+                     uint64_t *d_keys, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Diagnostic: the dense score matrix itself (upstream index.py:91), d_scores_full float [B, N].
  * Not used by the search path; lets tests separate scoring errors from selection errors. */
@@ -118,12 +138,15 @@ int vs_merge_keys(int device, const uint64_t *d_keys_in, int64_t P, int64_t stri
 /* Rerank stage: scores of GIVEN rows, d_scores[b, j] = <q_b, row d_ids[b, j]> (ids outside [0, N) -> -inf).
  * Replaces the re-embedding + bmm of the reference's `retrieve(rerank=True)` (src/ir/retriever/retriever.py:137-141)
  * when the candidates' parametric vectors already sit in a device-resident sparse index: B*k row gathers instead of
- * an encoder pass.  Sparse / bag-of-token indices.  Workspace >= B * vpad * 4 + 256 bytes (vs_search_workspace_bytes
- * covers it). */
+ * an encoder pass.  Sparse / bag-of-token indices.  Workspace >= vs_score_rows_workspace_bytes(idx, B) (the whole batch
+ * is prepared at once: not covered by vs_search_workspace_bytes for large B).  No synchronisation. */
+size_t vs_score_rows_workspace_bytes(const vs_index *idx, int64_t B);
 int vs_score_rows(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, const int64_t *d_ids, int k,
                   int score_round, float *d_scores, void *d_workspace, size_t workspace_bytes, void *stream);
 
-/* which kernel family (VS_MODE_SCAN | VS_MODE_INVERTED) served the last search on this handle */
+/* which kernel family (VS_MODE_SCAN | VS_MODE_INVERTED) served the last search on this handle.  SYNC when that search
+ * let the device choose (auto / inverted): the decision is read back.  A forced VS_MODE_INVERTED whose queries the
+ * lists cannot serve (> 4096 non-zeros or >= 2^32 postings in one query) is answered by the scan and reports so. */
 int vs_index_last_mode(const vs_index *idx, int *mode);
 
 /* timing hook for bench.py: every scan/score kernel launch made through this handle is bracketed by a
@@ -152,6 +175,16 @@ int vs_debug_gather_wavefronts(const vs_index *idx, unsigned long long *d_out2, 
  * encoder/vdr.py:159-169.  k = 0 keeps only those; k >= n_cols keeps everything. */
 int vs_sparsify_topk(int device, float *d_q, int64_t B, int64_t ld, int n_cols, int k, const int32_t *d_bow_ids, int bow_ld,
                      int bow_shift, void *stream);
+
+/* ---- dense -> CSR on the GPU -----------------------------------------------------------------------------------------
+ * The non-zeros of a dense device matrix d_x [n_rows, ld] (f32 | f16 | bf16; first n_cols columns) as a CSR triple,
+ * columns ascending.  Replaces `vectors.to_sparse_csr()` of the reference's Retriever.build_index
+ * (src/ir/retriever/retriever.py:299-305), and turns a sparsified query batch (vs_sparsify_topk) into the
+ * (token, weight) lists vs_search_sparse takes.  Two calls, like vs_bot_from_tokens: d_col == NULL writes the row
+ * lengths into d_row_nnz_or_crow[n_rows]; the caller scans them into row pointers and calls again with
+ * d_row_nnz_or_crow = crow (int64 [n_rows + 1]), d_col (int32 [nnz]) and d_val (float [nnz]).  No synchronisation. */
+int vs_dense_to_csr(int device, const void *d_x, int x_dtype, int64_t n_rows, int64_t ld, int n_cols,
+                    int64_t *d_row_nnz_or_crow, int32_t *d_col, float *d_val, void *stream);
 
 /* ---- bag-of-token rows from token-id batches, on the GPU -----------------------------------------------------------
  * Replaces Retriever._build_bot_vectors (reference src/ir/retriever/retriever.py:208-253: dense [batch, vocab]

@@ -373,9 +373,10 @@ def test_auto_mode_crossover(cuda_device):
         q = sparse_queries(3, V, qnnz, seed=qnnz)
         msg = ref_search.compare_results(idx.search(q, 50), ref_search.ref_scores(q, X), 50, exact=True)
         assert msg is None, f"qnnz={qnnz}: {msg}"
-    idx.search_mode = "inverted"
-    with pytest.raises(NotImplementedError):  # > 4096 non-zeros per query: inverted lists refuse, auto falls back
-        idx.search(sparse_queries(1, V, 6000, seed=1), 5)
+    idx.search_mode = "inverted"   # > 4096 non-zeros per query: the lists cannot serve it, the scan answers (and says so)
+    q = sparse_queries(1, V, 6000, seed=1)
+    assert ref_search.compare_results(idx.search(q, 5), ref_search.ref_scores(q, X), 5, exact=True) is None
+    assert idx.last_mode() == "scan"
 
 
 @pytest.mark.gpu
@@ -496,3 +497,263 @@ def test_malformed_csr_is_rejected_not_read_out_of_bounds(cuda_device):
     for bad_col in ([1, 5, 2, 10], [1, -1, 2, 7]):
         with pytest.raises(ValueError):
             _Engine.from_csr(good, torch.tensor(bad_col, dtype=torch.int64, device=dev), val, (3, 10), dev)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: sparse-query entry point (vs_search_sparse), no host wait, limits, larger oracle-backed cases
+def _sparse_forms(q):
+    """the same queries as a torch CSR tensor, a COO tensor, and host-resident CSR parts"""
+    csr = q.to_sparse_csr()
+    return {"csr": csr, "coo": q.to_sparse_coo(), "csr_cuda": csr.cuda()}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("binary", [True, False])
+def test_sparse_queries_match_dense_queries_and_oracle(binary, cuda_device):
+    """Index.search with (token, weight) lists (torch sparse tensors -> vs_search_sparse) through the scan, the inverted
+    lists and auto: bit-exact against the oracle on grid data, and equal to the dense-query path."""
+    n, m = 90_000, 96
+    crow, col, val = stratified_csr(n, V, m, seed=31, grid=True, binary=binary, jitter=9)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    idx = _mk("BoTIndex" if binary else "SparseIndex", crow, col, val, (n, V))
+    q = sparse_queries(7, V, 64, seed=8, neg=not binary)
+    q[3] = 0                                  # an empty query: all scores 0, ids 0..k-1
+    ref = ref_search.ref_scores(q, X)
+    for mode in ("scan", "inverted", "auto"):
+        idx.search_mode = mode
+        dense = idx.search(q, 50)
+        for name, qs in _sparse_forms(q).items():
+            res = idx.search(qs, 50)
+            msg = ref_search.compare_results(res, ref, 50, exact=True)
+            assert msg is None, f"{mode}/{name}: {msg}"
+            assert torch.equal(res.ids, dense.ids) and torch.equal(res.scores, dense.scores), f"{mode}/{name}"
+    assert idx.search(q[3].to_sparse(), 4).ids.tolist() == [0, 1, 2, 3]   # 1-D sparse query
+
+
+@pytest.mark.gpu
+def test_sparse_query_lists_raw_abi_host_and_device(cuda_device):
+    """vs_search_sparse with raw lists: host pointers (staged through the workspace), int32 / int64 offsets, tokens
+    outside [0, V) ignored, zero weights ignored, duplicate tokens of a query added up."""
+    n = 40_000
+    crow, col, val = stratified_csr(n, V, 64, seed=33, grid=True, binary=False)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    idx = _mk("SparseIndex", crow, col, val, (n, V))
+    eng = idx._require_engine()
+    g = torch.Generator().manual_seed(4)
+    toks, ws, ptr = [], [], [0]
+    qd = torch.zeros(5, V)
+    for b in range(5):
+        t = torch.randint(0, V, (40,), generator=g).to(torch.int32)
+        w = torch.randint(1, 65, (40,), generator=g).float() / 32.0
+        t[3] = t[5]                       # a duplicate token: weights add
+        w[7] = 0.0                        # ignored
+        t = torch.cat([t, torch.tensor([-5, V, V + 100], dtype=torch.int32)])   # ignored
+        w = torch.cat([w, torch.tensor([1.0, 2.0, 3.0])])
+        for tt, ww in zip(t.tolist(), w.tolist()):
+            if 0 <= tt < V:
+                qd[b, tt] += ww
+        toks.append(t); ws.append(w); ptr.append(ptr[-1] + t.numel())
+    tok, w = torch.cat(toks), torch.cat(ws)
+    ref = ref_search.ref_scores(qd, X)
+    for mode in ("scan", "inverted"):
+        for ptr_dtype in (torch.int64, torch.int32):
+            for dev in ("cpu", "cuda:0"):
+                p_ = torch.tensor(ptr, dtype=ptr_dtype, device=dev)
+                ids, sc = eng.search_sparse(p_, tok.to(dev), w.to(dev), 30, mode=mode)
+                torch.cuda.synchronize()
+                msg = ref_search.compare_results(ref_search.SearchResults(ids, sc), ref, 30, exact=True)
+                assert msg is None, f"{mode}/{ptr_dtype}/{dev}: {msg}"
+
+
+@pytest.mark.gpu
+def test_dense_queries_from_host_pointers_with_a_leading_dimension(cuda_device):
+    """vs_search straight from host memory (ctypes, no torch copy): staged through the workspace, ldq > n_cols."""
+    import ctypes
+
+    from vsearch_b200 import _native as nat
+
+    n = 30_000
+    crow, col, val = stratified_csr(n, V, 48, seed=35, grid=True, binary=True)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    idx = _mk("BoTIndex", crow, col, val, (n, V))
+    eng = idx._require_engine()
+    q = sparse_queries(6, V, 64, seed=2)
+    ld = V + 13
+    qh = torch.zeros(6, ld)
+    qh[:, :V] = q
+    ids = torch.empty((6, 20), dtype=torch.int64, device="cuda:0")
+    sc = torch.empty((6, 20), dtype=torch.float32, device="cuda:0")
+    for mode in ("scan", "auto"):
+        ws = eng.workspace(6, 20)
+        rc = nat.LIB.vs_search(eng.handle, ctypes.c_void_p(qh.data_ptr()), nat.VS_F32, 6, ld, 20, nat.MODES[mode], nat.VS_F32, 0,
+                               ids.data_ptr(), sc.data_ptr(), ws.data_ptr(), ws.numel(), None)
+        nat.check(rc)
+        torch.cuda.synchronize()
+        msg = ref_search.compare_results(ref_search.SearchResults(ids, sc), ref_search.ref_scores(q, X), 20, exact=True)
+        assert msg is None, f"{mode}: {msg}"
+
+
+@pytest.mark.gpu
+def test_search_does_not_wait_for_the_stream(cuda_device):
+    """The no-synchronisation contract of the header: with device queries, search (scan, inverted, auto) returns while
+    the stream is still busy with earlier work -- enqueue ~0.5 s of spinning first and time the calls."""
+    import time
+
+    n = 50_000
+    crow, col, val = stratified_csr(n, V, 64, seed=37, grid=True, binary=True)
+    idx = _mk("BoTIndex", crow, col, val, (n, V))
+    q = sparse_queries(4, V, 64, seed=2).cuda()
+    qs = q.to_sparse_csr()
+    for mode in ("scan", "inverted", "auto"):          # warm: inverted lists built, workspace allocated
+        idx.search_mode = mode
+        idx.search(q, 10); idx.search(qs, 10)
+    torch.cuda.synchronize()
+    spin = int(0.5 * 1.9e9)
+    for mode in ("scan", "inverted", "auto"):
+        idx.search_mode = mode
+        torch.cuda._sleep(spin)
+        t0 = time.perf_counter()
+        r1 = idx.search(q, 10)
+        r2 = idx.search(qs, 10)
+        dt = time.perf_counter() - t0
+        busy = not torch.cuda.current_stream().query()
+        torch.cuda.synchronize()
+        assert busy and dt < 0.1, f"{mode}: search blocked the host for {dt * 1e3:.1f} ms (stream busy: {busy})"
+        assert torch.equal(r1.ids, r2.ids)
+
+
+@pytest.mark.gpu
+def test_limits_k_2048_and_32767_columns(cuda_device):
+    """The two documented hard limits at their edge: k = VS_MAX_K = 2048 and n_cols = 32,767 (15 column bits + the
+    row-end flag), scan and inverted lists, against the oracle."""
+    g = torch.Generator().manual_seed(5)
+    n, vmax = 30_000, 32767
+    crow, col, val = stratified_csr(n, vmax, 40, seed=41, grid=True, binary=False, jitter=5)
+    col[-1] = vmax - 1                       # the last column is in use
+    X = ref_search.torch_csr(crow, col, val, (n, vmax))
+    idx = _mk("SparseIndex", crow, col, val, (n, vmax))
+    q = torch.zeros(3, vmax)
+    for b in range(3):
+        q[b, torch.randperm(vmax, generator=g)[:300]] = torch.randint(1, 64, (300,), generator=g).float() / 16.0
+    q[0, vmax - 1] = 2.0
+    ref = ref_search.ref_scores(q, X)
+    for mode in ("scan", "inverted"):
+        idx.search_mode = mode
+        for k in (2048, 7):
+            msg = ref_search.compare_results(idx.search(q, k), ref, k, exact=True)
+            assert msg is None, f"{mode} k={k}: {msg}"
+    with pytest.raises(NotImplementedError):
+        idx.search(q, 2049)
+    crow, col, val = stratified_csr(9000, V, 120, seed=42, grid=True, binary=True)   # binary scan at k = 2048
+    idx = _mk("BoTIndex", crow, col, val, (9000, V))
+    idx.search_mode = "scan"
+    qb = sparse_queries(2, V, 200, seed=6)
+    msg = ref_search.compare_results(idx.search(qb, 2048), ref_search.ref_scores(qb, ref_search.torch_csr(crow, col, val, (9000, V))),
+                                     2048, exact=True)
+    assert msg is None, msg
+
+
+@pytest.mark.gpu
+def test_inverted_and_scan_continuous_2m_rows(cuda_device):
+    """Oracle-backed continuous-data case at 2M rows x 256 nnz/row (512M postings): shared-memory float atomics make the
+    inverted lists' summation order vary from run to run, the scan's is fixed; both within 1e-5 of the reference with
+    the near-tie-aware id comparison."""
+    n, m = 2_000_000, 256
+    g = torch.Generator().manual_seed(77)
+    w = V // m
+    base = (torch.arange(m, dtype=torch.int32) * V) // m
+    col = (torch.randint(0, w, (n, m), generator=g, dtype=torch.int32) + base[None, :]).reshape(-1)
+    val = torch.rand(n * m, generator=g) * 1.99 + 0.01
+    crow = torch.arange(n + 1, dtype=torch.int64) * m
+    q = sparse_queries(4, V, 256, seed=19, grid=False)
+    X = ref_search.torch_csr(crow, col.to(torch.int64), val, (n, V))
+    ref = ref_search.ref_scores(q, X)
+    del X
+    import vsearch_b200 as vs
+    from vsearch_b200.index import _Engine
+
+    idx = vs.SparseIndex()
+    idx._engine = _Engine.from_csr(crow.cuda(), col.cuda(), val.cuda(), (n, V), torch.device("cuda:0"))
+    idx.device = "cuda:0"
+    for mode in ("inverted", "scan"):
+        idx.search_mode = mode
+        for k in (100, 1000):
+            res = idx.search(q, k)
+            assert idx.last_mode() == mode
+            msg = ref_search.compare_results(res, ref, k, rtol=1e-5, exact=False)
+            assert msg is None, f"{mode} k={k}: {msg}"
+
+
+@pytest.mark.gpu
+def test_score_rows_large_batch(cuda_device):
+    """vs_score_rows prepares the whole batch at once: B = 2,500 needs more than one search chunk's workspace."""
+    n = 20_000
+    crow, col, val = stratified_csr(n, V, 32, seed=43, grid=True, binary=False)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    idx = _mk("SparseIndex", crow, col, val, (n, V))
+    B = 2500
+    q = sparse_queries(B, V, 16, seed=3)
+    g = torch.Generator().manual_seed(9)
+    ids = torch.randint(0, n, (B, 3), generator=g)
+    got = idx.score_rows(q, ids).cpu()
+    ref = torch.gather(ref_search.ref_scores(q, X), 1, ids)
+    assert torch.equal(got, ref + 0.0)
+
+
+@pytest.mark.gpu
+def test_dense_to_csr_and_sparse_sparsifier_output(cuda_device):
+    """vs_dense_to_csr against torch's to_sparse_csr (fp32 / fp16 / bf16, empty rows, a strided view), the sparsifier's
+    as_sparse output, and build_index from a dense [N, V] matrix (sparsified on the GPU, .vector exports CSR)."""
+    import vsearch_b200 as vs
+
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(37, 1000, generator=g)
+    x[x < 0.9] = 0
+    x[5] = 0
+    for dt in (torch.float32, torch.float16, torch.bfloat16):
+        xd = x.to(dt).cuda()
+        crow, col, val = vs.dense_to_csr(xd)
+        ref = x.to(dt).float().to_sparse_csr()
+        assert torch.equal(crow.cpu(), ref.crow_indices()) and torch.equal(col.cpu().long(), ref.col_indices())
+        assert torch.equal(val.cpu(), ref.values())
+    wide = torch.zeros(37, 1200)
+    wide[:, :1000] = x
+    crow, col, val = vs.dense_to_csr(wide.cuda()[:, :1000])                 # row stride 1200
+    assert torch.equal(col.cpu().long(), x.to_sparse_csr().col_indices())
+    emb = torch.rand(5, V, generator=g)
+    sp = vs.topk_sparsify(emb.cuda(), 100, as_sparse=True)
+    de = vs.topk_sparsify(emb.cuda(), 100)
+    assert sp.layout == torch.sparse_csr and torch.equal(sp.to_dense(), de)
+    # build_index(vectors=dense [N, V]) -> GPU sparsification, same results as the CSR route
+    dense = torch.zeros(300, V)
+    crow, col, val = stratified_csr(300, V, 30, seed=44, grid=True, binary=False)
+    Xc = ref_search.torch_csr(crow, col, val, (300, V))
+    dense = Xc.to_dense()
+    r = vs.Retriever(device="cuda:0")
+    r.build_index(vectors=dense, index_type="sparse")
+    assert r.index.vector.layout == torch.sparse_csr and tuple(r.index.vector.shape) == (300, V)
+    q = sparse_queries(3, V, 64, seed=5)
+    assert ref_search.compare_results(r.retrieve(q, k=10), ref_search.ref_scores(q, Xc), 10, exact=True) is None
+    r.build_index(vectors=dense, index_type="bag_of_token")
+    Xb = ref_search.torch_csr(crow, col, torch.ones(col.numel()), (300, V))
+    res = r.retrieve(q, k=10)
+    assert res.scores.dtype == torch.float16
+    msg = ref_search.compare_results(ref_search.SearchResults(res.ids, res.scores.float()),
+                                     ref_search.quantize_like(ref_search.ref_scores(q, Xb), torch.float16), 10, exact=True)
+    assert msg is None, msg
+
+
+@pytest.mark.gpu
+def test_sharded_rank_without_rows(cuda_device):
+    """row_partition(10, 8): ranks 5..7 own no rows.  Such a rank contributes empty keys instead of failing on k = 0."""
+    import vsearch_b200 as vs
+    from vsearch_b200.index import _Engine
+
+    assert vs.row_partition(10, 8, 6) == (10, 10)
+    dev = torch.device("cuda:0")
+    idx = vs.SparseIndex()
+    idx._engine = _Engine.from_csr(torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.int64, device=dev),
+                                   torch.zeros(0, device=dev), (0, V), dev)
+    idx.device = "cuda:0"
+    res = vs.ShardedIndex(idx, 10, 10).search(sparse_queries(2, V, 8, seed=1), 3)
+    assert tuple(res.ids.shape) == (2, 3)

@@ -26,7 +26,8 @@ SYMBOLS = [
     "vs_index_info", "vs_index_export_csr", "vs_search_workspace_bytes", "vs_search", "vs_search_keys",
     "vs_scores", "vs_merge_keys", "vs_kernel_timer", "vs_index_last_mode",
     "vs_npz_open", "vs_npz_close", "vs_npz_member_info", "vs_npz_read", "vs_bot_from_tokens", "vs_score_rows", "vs_npz_write", "vs_sparsify_topk",
-    "vs_debug_scan_profile", "vs_debug_gather_wavefronts",
+    "vs_debug_scan_profile", "vs_debug_gather_wavefronts", "vs_search_sparse", "vs_score_rows_workspace_bytes",
+    "vs_dense_to_csr",
 ]
 
 
@@ -62,6 +63,10 @@ def _load() -> ctypes.CDLL:
                               c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.vs_search_keys.argtypes = [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int64,
                                    c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.vs_search_sparse.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.vs_score_rows_workspace_bytes.argtypes = [c_void_p, c_int64]
+    lib.vs_score_rows_workspace_bytes.restype = c_size_t
     lib.vs_scores.argtypes = [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t,
                               c_void_p]
     lib.vs_merge_keys.argtypes = [c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p,
@@ -75,6 +80,7 @@ def _load() -> ctypes.CDLL:
     lib.vs_bot_from_tokens.argtypes = [c_int, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p]
     lib.vs_sparsify_topk.argtypes = [c_int, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
+    lib.vs_dense_to_csr.argtypes = [c_int, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.vs_npz_write.argtypes = [c_char_p, c_void_p, c_int, c_int, c_int]
     lib.vs_npz_open.argtypes = [c_char_p, POINTER(c_void_p)]
     lib.vs_npz_close.argtypes = [c_void_p]
@@ -82,7 +88,7 @@ def _load() -> ctypes.CDLL:
     lib.vs_npz_read.argtypes = [c_void_p, c_char_p, c_void_p, c_int, c_int64, c_int64, c_int64]
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError here = header / library mismatch
-    if lib.vs_abi_version() != 1:
+    if lib.vs_abi_version() != 2:
         raise ImportError("libvsearch_b200.so ABI version mismatch")
     return lib
 

@@ -17,25 +17,29 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-// scan.cu / merge.cu
+// scan.cu / merge.cu / inverted.cu / dense.cu
 size_t scan_smem_bytes(int vpad, int cap);
 int scan_cap_for_k(int k);
 int scan_kout(const vs_index *idx, int k);
 int launch_prep_query(const void *d_q, int q_dtype, int64_t B, int64_t ldq, int64_t n_cols, int vpad, int round_mode,
                       float *d_out, cudaStream_t st);
-int launch_scan(const vs_index *idx, const float *d_qprep, int vpad, int64_t B, int k, int score_round,
-                uint64_t *d_cand, float *d_scores_out, cudaStream_t st);
+int launch_scan(const vs_index *idx, const float *d_qprep, const SparseQueries *sq, int vpad, int64_t B, int k,
+                int score_round, uint64_t *d_cand, float *d_scores_out, const int *d_use_inv, cudaStream_t st);
 size_t inverted_workspace_bytes(const vs_index *idx, int64_t Bc, int group);
-int inverted_extract(vs_index *idx, const float *d_qprep, int vpad, int64_t Bc, void *d_ws, uint32_t *max_nnz,
-                     double *mean_postings, uint64_t *max_postings, cudaStream_t st);
-bool inverted_usable(uint32_t max_nnz, uint64_t max_postings);
-int launch_inverted(vs_index *idx, int64_t Bc, int k, int score_round, int group, uint32_t max_nnz, void *d_ws,
-                    uint64_t *d_cand, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t st);
+int inverted_prepare(vs_index *idx, const float *d_qprep, int vpad, const void *d_qptr, int ptr_dtype, const int32_t *d_qtok,
+                     const float *d_qw, int64_t b0, int64_t Bc, int mode, int round_mode, double t_scan, double postings_per_sec,
+                     double t_rows_fixed, void *d_ws, int *d_flag, cudaStream_t st);
+int launch_inverted(vs_index *idx, int64_t Bc, int k, int cand_stride, int score_round, void *d_ws, uint64_t *d_cand,
+                    const int *d_flag, cudaStream_t st);
 size_t dense_workspace_bytes(const vs_index *idx, int64_t B, int k);
 int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t ldq, int k, int score_round,
                  int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, void *d_ws, cudaStream_t st);
 int launch_merge(const uint64_t *d_in, int64_t P, int64_t stride_p, int64_t stride_b, int64_t B, int k_in, int k_out,
                  int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, cudaStream_t st);
+size_t merge_scratch_bytes(int64_t P, int k_in, int k_out, int64_t B);
+int launch_merge_staged(const uint64_t *d_in, int64_t P, int64_t stride_p, int64_t stride_b, int64_t B, int k_in, int k_out,
+                        int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, const int *d_alt_flag, int k_in_alt,
+                        void *d_scratch, cudaStream_t st);
 
 static size_t dtype_size(int dt) {
     switch (dt) {
@@ -70,21 +74,32 @@ static inline int vpad_for(int64_t n_cols) { return (int)(((n_cols + 1) + 3) / 4
 
 // workspace layout for one query chunk of Bc queries
 struct Workspace {
-    float *qprep;      // [Bc, vpad]
-    uint64_t *cand;    // [Bc, n_ctas, k]
-    void *inv;         // K3: query lists + accumulators
+    int *flag;         // device decision of the auto mode (1 = inverted lists)
+    float *qprep;      // [Bc, vpad] prepared fp32 rows
+    uint64_t *cand;    // [Bc, n_ctas, scan_kout] per-CTA candidate lists
+    void *inv;         // K3: extracted (token, weight) lists
+    uint8_t *stage;    // host inputs land here first: dense rows [Bc, n_cols] in the caller's dtype, or sparse lists
+    size_t stage_bytes;
+    void *merge;       // group results of the multi-stage merge (merge.cu)
     size_t bytes;
 };
 constexpr int kInvGroup = 1;   // queries scored concurrently by the inverted-list path (accumulator rows)
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 static Workspace carve(const vs_index *idx, void *base, int64_t Bc, int k) {
     Workspace w;
-    size_t q_bytes = align256((size_t)Bc * vpad_for(idx->n_cols) * 4);
-    size_t c_bytes = align256((size_t)Bc * idx->n_ctas * (size_t)scan_kout(idx, k) * 8);   // scan lists are the longer ones
-    w.qprep = (float *)base;
-    w.cand = (uint64_t *)((uint8_t *)base + q_bytes);
-    w.inv = (uint8_t *)base + q_bytes + c_bytes;
-    w.bytes = q_bytes + c_bytes + align256(inverted_workspace_bytes(idx, Bc, kInvGroup));
+    const size_t q_bytes = align256((size_t)Bc * vpad_for(idx->n_cols) * 4);
+    const size_t c_bytes = align256((size_t)Bc * idx->n_ctas * (size_t)scan_kout(idx, k) * 8);   // scan lists are the longer ones
+    const size_t i_bytes = align256(inverted_workspace_bytes(idx, Bc, kInvGroup));
+    // staging: a dense fp32 chunk, or a sparse chunk as dense as the rows themselves (8 B per entry + offsets)
+    w.stage_bytes = align256((size_t)Bc * (size_t)idx->n_cols * 8 + (size_t)(Bc + 1) * 8);
+    uint8_t *p = (uint8_t *)base;
+    w.flag = (int *)p; p += 256;
+    w.qprep = (float *)p; p += q_bytes;
+    w.cand = (uint64_t *)p; p += c_bytes;
+    w.inv = p; p += i_bytes;
+    w.stage = p; p += w.stage_bytes;
+    w.merge = p; p += align256(merge_scratch_bytes(idx->n_ctas, scan_kout(idx, k), k, Bc));
+    w.bytes = (size_t)(p - (uint8_t *)base);
     return w;
 }
 constexpr int64_t kQueryChunk = 1024;
@@ -96,7 +111,7 @@ static int64_t query_chunk(const vs_index *idx, int64_t B, int k) {
     return B < c ? B : c;
 }
 // auto-mode cost model; refined from measurements (profiles/)
-constexpr double kScanBytesPerSecPair = 4.5e12;   // binary / 16-bit values (L1 data-pipe bound)
+constexpr double kScanBytesPerSecPair = 5.6e12;   // binary / 16-bit values
 constexpr double kScanBytesPerSecF32 = 6.2e12;    // fp32 values (HBM bound)
 constexpr double kInvPostingsPerSec = 3.5e11;     // shared-memory atomics, all SMs
 constexpr double kInvSecPerRow = 1.8e-12;         // zero + select of the block accumulators
@@ -177,6 +192,8 @@ int vs_index_create_csr(int device, int64_t n_rows, int64_t n_cols, int64_t nnz,
     idx->store_dtype = binary ? VS_NONE : store_dtype;
     idx->n_rows = n_rows; idx->n_cols = n_cols; idx->nnz = nnz;
     if (const char *e = getenv("VSEARCH_B200_BANK_AWARE")) idx->bank_aware = (e[0] != '0');
+    if (cudaMalloc(&idx->d_last_mode, 256) != cudaSuccess) { delete idx; VS_REQUIRE(false, VS_ERR_NOMEM, "out of device memory"); }
+    cudaMemsetAsync(idx->d_last_mode, 0, 256, st);
 
     int rc;
     {
@@ -234,7 +251,10 @@ int vs_index_create_dense(int device, int64_t n_rows, int64_t dim, const void *h
 
 int vs_index_destroy(vs_index *idx) {
     if (!idx) return VS_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);   // the caller's current device is left as it was (the handle may live on another GPU)
     cudaSetDevice(idx->device);
+    cudaFree(idx->d_last_mode);
     cudaFree(idx->cols); cudaFree(idx->vals); cudaFree(idx->tails);
     cudaFree(idx->part_win_begin); cudaFree(idx->part_row_begin); cudaFree(idx->row_chunk);
     cudaFree(idx->dense);
@@ -244,6 +264,7 @@ int vs_index_destroy(vs_index *idx) {
         if (idx->ev1[i]) cudaEventDestroy(idx->ev1[i]);
     }
     delete idx;
+    cudaSetDevice(prev);
     return VS_OK;
 }
 
@@ -268,18 +289,32 @@ int vs_index_export_csr(const vs_index *idx, int64_t *d_crow, int64_t *d_col, fl
 
 size_t vs_search_workspace_bytes(const vs_index *idx, int64_t B, int k) {
     if (!idx || B <= 0 || k <= 0) return 256;
-    if (idx->kind == 0) return dense_workspace_bytes(idx, B, k) + 256;
+    if (idx->kind == 0) return dense_workspace_bytes(idx, B, k) + align256((size_t)B * (size_t)idx->dim * 4) + 1024 + 256;
     return carve(idx, nullptr, query_chunk(idx, B, k), k).bytes + 256;
 }
 
-static int search_impl(const vs_index *cidx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int k, int mode,
-                       int score_round, int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys,
-                       float *d_scores_full, void *d_workspace, size_t workspace_bytes, void *stream) {
+// Queries of one call: dense rows (q != nullptr) or CSR-style (token, weight) lists (ptr != nullptr); host or device.
+struct QueryInput {
+    const void *q = nullptr; int q_dtype = VS_F32; int64_t ldq = 0;
+    const void *ptr = nullptr; int ptr_dtype = VS_I64; const int32_t *tok = nullptr; const float *w = nullptr;
+};
+
+static int search_impl(const vs_index *cidx, const QueryInput &in, int64_t B, int k, int mode, int score_round,
+                       int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, float *d_scores_full,
+                       void *d_workspace, size_t workspace_bytes, void *stream) {
     vs_index *idx = const_cast<vs_index *>(cidx);
     VS_REQUIRE(idx != nullptr, VS_ERR_INVALID, "index is NULL");
-    VS_REQUIRE(B >= 0 && ldq >= idx->n_cols, VS_ERR_INVALID, "query leading dimension %lld < n_cols %lld", (long long)ldq,
-               (long long)idx->n_cols);
-    VS_REQUIRE(q_dtype == VS_F32 || q_dtype == VS_F16 || q_dtype == VS_BF16, VS_ERR_INVALID, "bad query dtype");
+    const bool sparse_q = in.ptr != nullptr;
+    if (!sparse_q) {
+        VS_REQUIRE(B >= 0 && in.ldq >= idx->n_cols, VS_ERR_INVALID, "query leading dimension %lld < n_cols %lld", (long long)in.ldq,
+                   (long long)idx->n_cols);
+        VS_REQUIRE(in.q_dtype == VS_F32 || in.q_dtype == VS_F16 || in.q_dtype == VS_BF16, VS_ERR_INVALID, "bad query dtype");
+        VS_REQUIRE(in.q != nullptr || B == 0, VS_ERR_INVALID, "queries are NULL");
+    } else {
+        VS_REQUIRE(idx->kind != 0, VS_ERR_UNSUPPORTED, "sparse queries need a sparse / bag-of-token index");
+        VS_REQUIRE(in.ptr_dtype == VS_I32 || in.ptr_dtype == VS_I64, VS_ERR_INVALID, "query offsets must be int32 / int64");
+        VS_REQUIRE(B >= 0, VS_ERR_INVALID, "bad batch size");
+    }
     VS_REQUIRE(k >= 1, VS_ERR_INVALID, "k must be >= 1");
     VS_REQUIRE((int64_t)k <= idx->n_rows, VS_ERR_INVALID, "selected index k out of range (k=%d > N=%lld)", k,
                (long long)idx->n_rows);
@@ -293,70 +328,100 @@ static int search_impl(const vs_index *cidx, const void *hd_q, int q_dtype, int6
     VS_CUDA(cudaSetDevice(idx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int vpad = vpad_for(idx->n_cols);
-    void *ws_base = (void *)(((uintptr_t)d_workspace + 255) / 256 * 256);
+    uint8_t *ws_base = (uint8_t *)(((uintptr_t)d_workspace + 255) / 256 * 256);
 
-    const bool q_on_device = is_device_ptr(hd_q);
-    if (idx->kind == 0) {  // dense index: K4 (tcgen05 GEMM + fused top-k)
+    if (idx->kind == 0) {  // dense index: K4 (tcgen05 GEMM + fused top-k).  SYNC (candidate-list overflow checks)
         VS_REQUIRE(d_scores_full == nullptr, VS_ERR_UNSUPPORTED, "vs_scores is a sparse-path diagnostic");
-        Staged sq;
-        int rc = sq.init(hd_q, (size_t)B * ldq * dtype_size(q_dtype), st);
-        if (rc) return rc;
-        rc = search_dense(idx, sq.ptr, q_dtype, B, ldq, k, score_round, id_offset, d_ids, d_scores, d_keys, ws_base, st);
-        if (rc == VS_OK && sq.owned) VS_CUDA(cudaStreamSynchronize(st));
-        return rc;
+        const void *dq = in.q;
+        size_t ws_off = 0;
+        int64_t ld = in.ldq;
+        if (!is_device_ptr(in.q)) {   // stage the host batch (compact [B, dim]) at the head of the workspace
+            const size_t esz = dtype_size(in.q_dtype);
+            VS_CUDA(cudaMemcpy2DAsync(ws_base, (size_t)idx->dim * esz, in.q, (size_t)in.ldq * esz, (size_t)idx->dim * esz, (size_t)B,
+                                      cudaMemcpyHostToDevice, st));
+            dq = ws_base;
+            ld = idx->dim;
+            ws_off = align256((size_t)B * idx->dim * esz);
+        }
+        idx->last_mode = VS_MODE_SCAN; idx->last_mode_on_device = false;
+        return search_dense(idx, dq, in.q_dtype, B, ld, k, score_round, id_offset, d_ids, d_scores, d_keys, ws_base + ws_off, st);
     }
+
+    const bool q_on_device = sparse_q ? is_device_ptr(in.ptr) : is_device_ptr(in.q);
+    const bool f32 = idx->kind == 1 && idx->store_dtype == VS_F32;
+    const double t_scan = (double)idx->stream_bytes / (f32 ? kScanBytesPerSecF32 : kScanBytesPerSecPair);
+    const double t_rows_fixed = (double)idx->n_rows * kInvSecPerRow + kInvFixedSec;
+    const int kout = scan_kout(idx, k);
+    const bool try_inv = mode != VS_MODE_SCAN && !d_scores_full;
     const int64_t chunk = query_chunk(idx, B, k);
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int64_t Bc = (B - b0) < chunk ? (B - b0) : chunk;
         Workspace w = carve(idx, ws_base, Bc, k);
-        const uint8_t *qsrc = (const uint8_t *)hd_q + (size_t)b0 * ldq * dtype_size(q_dtype);
-        Staged sq;
-        if (!q_on_device) { int rc = sq.init(qsrc, (size_t)Bc * ldq * dtype_size(q_dtype), st); if (rc) return rc; }
-        else sq.ptr = qsrc;
-        int rc = launch_prep_query(sq.ptr, q_dtype, Bc, ldq, idx->n_cols, vpad, score_round, w.qprep, st);
-        if (rc) return rc;
-        // ---- scan (K1/K2) or inverted lists (K3)?
-        bool use_inv = false;
-        uint32_t max_nnz = 0;
-        if (mode != VS_MODE_SCAN && !d_scores_full) {
-            double mean_post = 0;
-            uint64_t max_post = 0;
-            rc = inverted_extract(idx, w.qprep, vpad, Bc, w.inv, &max_nnz, &mean_post, &max_post, st);  // SYNC
-            if (rc) return rc;
-            const bool usable = inverted_usable(max_nnz, max_post);
-            if (mode == VS_MODE_INVERTED) {
-                VS_REQUIRE(usable, VS_ERR_UNSUPPORTED,
-                           "inverted mode needs <= 4096 non-zeros and < 2^32 postings per query (got %u / %llu)", max_nnz,
-                           (unsigned long long)max_post);
-                use_inv = true;
-            } else {
-                // cost model (seconds per query), constants measured on B200
-                const bool f32 = idx->kind == 1 && idx->store_dtype == VS_F32;
-                const double t_scan = (double)idx->stream_bytes / (f32 ? kScanBytesPerSecF32 : kScanBytesPerSecPair);
-                const double t_inv = mean_post / kInvPostingsPerSec + (double)idx->n_rows * kInvSecPerRow + kInvFixedSec;
-                use_inv = usable && t_inv < t_scan;
+        SparseQueries sq;
+        int rc;
+        if (!sparse_q) {
+            // ---- dense rows -> prepared fp32 [Bc, vpad]
+            const size_t esz = dtype_size(in.q_dtype);
+            const uint8_t *qsrc = (const uint8_t *)in.q + (size_t)b0 * in.ldq * esz;
+            int64_t ld = in.ldq;
+            if (!q_on_device) {   // compact [Bc, n_cols] copy into the staging area (no allocation, no host wait)
+                VS_CUDA(cudaMemcpy2DAsync(w.stage, (size_t)idx->n_cols * esz, qsrc, (size_t)in.ldq * esz, (size_t)idx->n_cols * esz,
+                                          (size_t)Bc, cudaMemcpyHostToDevice, st));
+                qsrc = w.stage;
+                ld = idx->n_cols;
             }
-        }
-        idx->last_mode = use_inv ? VS_MODE_INVERTED : VS_MODE_SCAN;
-        const int slot = idx->timer_n < VS_TIMER_SLOTS ? idx->timer_n : -1;
-        if (use_inv) {
-            rc = launch_inverted(idx, Bc, k, score_round, kInvGroup, max_nnz, w.inv, w.cand,
-                                 slot >= 0 ? idx->ev0[slot] : nullptr, slot >= 0 ? idx->ev1[slot] : nullptr, st);
+            rc = launch_prep_query(qsrc, in.q_dtype, Bc, ld, idx->n_cols, vpad, score_round, w.qprep, st);
             if (rc) return rc;
         } else {
-            if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev0[slot], st));
-            rc = launch_scan(idx, w.qprep, vpad, Bc, k, score_round, w.cand,
-                             d_scores_full ? d_scores_full + (size_t)b0 * idx->n_rows : nullptr, st);
-            if (rc) return rc;
-            if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
+            // ---- (token, weight) lists: used as they are (device) or staged (host: offsets first, then the entries)
+            sq.ptr = in.ptr; sq.ptr_dtype = in.ptr_dtype; sq.tok = in.tok; sq.w = in.w; sq.b0 = b0;
+            if (!q_on_device) {
+                const size_t psz = dtype_size(in.ptr_dtype);
+                const uint8_t *hp = (const uint8_t *)in.ptr + (size_t)b0 * psz;
+                const int64_t lo = in.ptr_dtype == VS_I32 ? (int64_t)((const int32_t *)in.ptr)[b0] : ((const int64_t *)in.ptr)[b0];
+                const int64_t hi = in.ptr_dtype == VS_I32 ? (int64_t)((const int32_t *)in.ptr)[b0 + Bc] : ((const int64_t *)in.ptr)[b0 + Bc];
+                VS_REQUIRE(lo >= 0 && hi >= lo, VS_ERR_INVALID, "query offsets must be non-decreasing");
+                const size_t n_ent = (size_t)(hi - lo);
+                const size_t p_bytes = align256((size_t)(Bc + 1) * psz);
+                VS_REQUIRE(p_bytes + 2 * align256(n_ent * 4) <= w.stage_bytes, VS_ERR_UNSUPPORTED,
+                           "sparse query chunk holds more entries than dense rows would");
+                uint8_t *d_ptr = w.stage, *d_tok = w.stage + p_bytes, *d_w = d_tok + align256(n_ent * 4);
+                VS_CUDA(cudaMemcpyAsync(d_ptr, hp, (size_t)(Bc + 1) * psz, cudaMemcpyHostToDevice, st));
+                if (n_ent) {
+                    VS_CUDA(cudaMemcpyAsync(d_tok, in.tok + lo, n_ent * 4, cudaMemcpyHostToDevice, st));
+                    VS_CUDA(cudaMemcpyAsync(d_w, in.w + lo, n_ent * 4, cudaMemcpyHostToDevice, st));
+                }
+                // the staged offsets still count from the caller's array start: rebase the entry pointers instead
+                sq.ptr = d_ptr; sq.tok = (const int32_t *)d_tok - lo; sq.w = (const float *)d_w - lo; sq.b0 = 0;
+            }
         }
-        idx->timer_n += 1;
-        const int k_in = use_inv ? k : scan_kout(idx, k);   // length of the per-CTA lists
-        rc = launch_merge(w.cand, idx->n_ctas, k_in, (int64_t)idx->n_ctas * k_in, Bc, k_in, k, id_offset,
-                          d_ids ? d_ids + b0 * k : nullptr, d_scores ? d_scores + b0 * k : nullptr,
-                          d_keys ? d_keys + b0 * k : nullptr, st);
+        // ---- scan (K1/K2) or inverted lists (K3)?  Decided on the device (inv_decide_kernel): both kernels are
+        // enqueued, the one that lost exits at once, the merge reads the same flag.  No readback, no host wait.
+        if (try_inv) {
+            rc = inverted_prepare(idx, w.qprep, vpad, sparse_q ? sq.ptr : nullptr, sq.ptr_dtype, sparse_q ? sq.tok : nullptr,
+                                  sparse_q ? sq.w : nullptr, sparse_q ? sq.b0 : 0, Bc, mode, score_round, t_scan,
+                                  kInvPostingsPerSec, t_rows_fixed, w.inv, w.flag, st);
+            if (rc) return rc;
+            idx->last_mode_on_device = true;
+        } else {
+            idx->last_mode = VS_MODE_SCAN; idx->last_mode_on_device = false;
+        }
+        const int slot = idx->timer_n < VS_TIMER_SLOTS ? idx->timer_n : -1;
+        if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev0[slot], st));
+        if (try_inv) {
+            rc = launch_inverted(idx, Bc, k, kout, score_round, w.inv, w.cand, w.flag, st);
+            if (rc) return rc;
+        }
+        rc = launch_scan(idx, w.qprep, sparse_q ? &sq : nullptr, vpad, Bc, k, score_round, w.cand,
+                         d_scores_full ? d_scores_full + (size_t)b0 * idx->n_rows : nullptr, try_inv ? w.flag : nullptr, st);
         if (rc) return rc;
-        if (!q_on_device) VS_CUDA(cudaStreamSynchronize(st));  // staging buffer is freed at scope exit
+        if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
+        idx->timer_n += 1;
+        // per-CTA lists: scan_kout keys from the scan, k from the inverted lists (same stride)
+        rc = launch_merge_staged(w.cand, idx->n_ctas, kout, (int64_t)idx->n_ctas * kout, Bc, kout, k, id_offset,
+                                 d_ids ? d_ids + b0 * k : nullptr, d_scores ? d_scores + b0 * k : nullptr,
+                                 d_keys ? d_keys + b0 * k : nullptr, try_inv ? w.flag : nullptr, k, w.merge, st);
+        if (rc) return rc;
     }
     return VS_OK;
 }
@@ -365,23 +430,45 @@ int vs_search(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int
               int score_round, int64_t id_offset, int64_t *d_ids, float *d_scores, void *d_workspace,
               size_t workspace_bytes, void *stream) {
     VS_REQUIRE(d_ids != nullptr && d_scores != nullptr, VS_ERR_INVALID, "output pointers are NULL");
-    return search_impl(idx, hd_q, q_dtype, B, ldq, k, mode, score_round, id_offset, d_ids, d_scores, nullptr, nullptr,
-                       d_workspace, workspace_bytes, stream);
+    QueryInput in;
+    in.q = hd_q; in.q_dtype = q_dtype; in.ldq = ldq;
+    return search_impl(idx, in, B, k, mode, score_round, id_offset, d_ids, d_scores, nullptr, nullptr, d_workspace,
+                       workspace_bytes, stream);
 }
 
 int vs_search_keys(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int k, int mode,
                    int score_round, int64_t id_offset, uint64_t *d_keys, void *d_workspace, size_t workspace_bytes,
                    void *stream) {
     VS_REQUIRE(d_keys != nullptr, VS_ERR_INVALID, "output pointer is NULL");
-    return search_impl(idx, hd_q, q_dtype, B, ldq, k, mode, score_round, id_offset, nullptr, nullptr, d_keys, nullptr,
-                       d_workspace, workspace_bytes, stream);
+    QueryInput in;
+    in.q = hd_q; in.q_dtype = q_dtype; in.ldq = ldq;
+    return search_impl(idx, in, B, k, mode, score_round, id_offset, nullptr, nullptr, d_keys, nullptr, d_workspace,
+                       workspace_bytes, stream);
+}
+
+int vs_search_sparse(const vs_index *idx, const void *hd_qptr, int ptr_dtype, const int32_t *hd_qtok, const float *hd_qw,
+                     int64_t B, int k, int mode, int score_round, int64_t id_offset, int64_t *d_ids, float *d_scores,
+                     uint64_t *d_keys, void *d_workspace, size_t workspace_bytes, void *stream) {
+    VS_REQUIRE((d_ids != nullptr && d_scores != nullptr) || d_keys != nullptr, VS_ERR_INVALID, "output pointers are NULL");
+    VS_REQUIRE(hd_qptr != nullptr, VS_ERR_INVALID, "query offsets are NULL");
+    QueryInput in;
+    in.ptr = hd_qptr; in.ptr_dtype = ptr_dtype; in.tok = hd_qtok; in.w = hd_qw;
+    return search_impl(idx, in, B, k, mode, score_round, id_offset, d_ids, d_scores, d_keys, nullptr, d_workspace,
+                       workspace_bytes, stream);
 }
 
 int vs_scores(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int score_round,
               float *d_scores_full, void *d_workspace, size_t workspace_bytes, void *stream) {
     VS_REQUIRE(d_scores_full != nullptr, VS_ERR_INVALID, "output pointer is NULL");
-    return search_impl(idx, hd_q, q_dtype, B, ldq, 1, VS_MODE_SCAN, score_round, 0, nullptr, nullptr, nullptr,
-                       d_scores_full, d_workspace, workspace_bytes, stream);
+    QueryInput in;
+    in.q = hd_q; in.q_dtype = q_dtype; in.ldq = ldq;
+    return search_impl(idx, in, B, 1, VS_MODE_SCAN, score_round, 0, nullptr, nullptr, nullptr, d_scores_full, d_workspace,
+                       workspace_bytes, stream);
+}
+
+size_t vs_score_rows_workspace_bytes(const vs_index *idx, int64_t B) {
+    if (!idx || B <= 0) return 256;
+    return align256((size_t)B * vpad_for(idx->n_cols) * 4) + align256((size_t)B * (size_t)idx->n_cols * 4) + 512;
 }
 
 int vs_score_rows(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, const int64_t *d_ids, int k,
@@ -395,18 +482,24 @@ int vs_score_rows(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B,
     cudaStream_t st = (cudaStream_t)stream;
     const int vpad = vpad_for(idx->n_cols);
     void *ws = (void *)(((uintptr_t)d_workspace + 255) / 256 * 256);
-    VS_REQUIRE(d_workspace != nullptr && workspace_bytes >= (size_t)B * vpad * 4 + 256, VS_ERR_INVALID,
-               "workspace too small: vs_score_rows needs B * %d * 4 + 256 bytes", vpad);
-    Staged sq;
-    int rc = sq.init(hd_q, (size_t)B * ldq * dtype_size(q_dtype), st);
-    if (rc) return rc;
-    rc = launch_prep_query(sq.ptr, q_dtype, B, ldq, idx->n_cols, vpad, score_round, (float *)ws, st);
+    VS_REQUIRE(d_workspace != nullptr && workspace_bytes >= vs_score_rows_workspace_bytes(idx, B), VS_ERR_INVALID,
+               "workspace too small: vs_score_rows needs vs_score_rows_workspace_bytes(idx, B) bytes");
+    const void *dq = hd_q;
+    int64_t ld = ldq;
+    if (!is_device_ptr(hd_q)) {   // host batch: compact copy behind the prepared rows, no allocation, no host wait
+        uint8_t *stage = (uint8_t *)ws + align256((size_t)B * vpad * 4);
+        const size_t esz = dtype_size(q_dtype);
+        VS_CUDA(cudaMemcpy2DAsync(stage, (size_t)idx->n_cols * esz, hd_q, (size_t)ldq * esz, (size_t)idx->n_cols * esz, (size_t)B,
+                                  cudaMemcpyHostToDevice, st));
+        dq = stage;
+        ld = idx->n_cols;
+    }
+    int rc = launch_prep_query(dq, q_dtype, B, ld, idx->n_cols, vpad, score_round, (float *)ws, st);
     if (rc) return rc;
     const int64_t n_pairs = B * (int64_t)k;
     score_rows_kernel<<<(unsigned)((n_pairs + 7) / 8), 256, 0, st>>>(ws_view(idx), (const float *)ws, vpad, d_ids, n_pairs, k,
                                                                     score_round, d_scores);
     VS_CUDA(cudaGetLastError());
-    if (sq.owned) VS_CUDA(cudaStreamSynchronize(st));   // staging buffer is freed at scope exit
     return VS_OK;
 }
 
@@ -415,13 +508,22 @@ int vs_merge_keys(int device, const uint64_t *d_keys_in, int64_t P, int64_t stri
     VS_REQUIRE(d_keys_in != nullptr && d_ids != nullptr && d_scores != nullptr, VS_ERR_INVALID, "NULL pointer");
     VS_REQUIRE(P >= 1 && k_in >= 1 && k_out >= 1 && B >= 0, VS_ERR_INVALID, "bad merge shape");
     VS_CUDA(cudaSetDevice(device));
-    return launch_merge(d_keys_in, P, stride_p, stride_b, B, k_in, k_out, 0, d_ids, d_scores, nullptr,
-                        (cudaStream_t)stream);
+    // register-resident kernel when the P lists fit one CTA (8 ranks x k <= 2048 do), else the streaming one
+    return launch_merge_staged(d_keys_in, P, stride_p, stride_b, B, k_in, k_out, 0, d_ids, d_scores, nullptr, nullptr, 0, nullptr,
+                               (cudaStream_t)stream);
 }
 
 int vs_index_last_mode(const vs_index *idx, int *mode) {
     VS_REQUIRE(idx != nullptr && mode != nullptr, VS_ERR_INVALID, "NULL pointer");
     *mode = idx->last_mode;
+    if (idx->last_mode_on_device) {   // the device chose (auto / inverted): read its decision back.  SYNC
+        int prev = 0;
+        cudaGetDevice(&prev);
+        VS_CUDA(cudaSetDevice(idx->device));
+        cudaError_t e = cudaMemcpy(mode, idx->d_last_mode, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaSetDevice(prev);
+        VS_CUDA(e);
+    }
     return VS_OK;
 }
 
@@ -439,15 +541,20 @@ int vs_debug_scan_profile(vs_index *idx, unsigned long long *d_buf) {
 
 int vs_kernel_timer(vs_index *idx, int reset, float *total_ms, int *launches) {
     VS_REQUIRE(idx != nullptr, VS_ERR_INVALID, "NULL pointer");
+    int prev = 0;
+    cudaGetDevice(&prev);
     VS_CUDA(cudaSetDevice(idx->device));
     const int n = idx->timer_n < VS_TIMER_SLOTS ? idx->timer_n : VS_TIMER_SLOTS;
     float total = 0.f;
-    for (int i = 0; i < n; ++i) {
+    cudaError_t err = cudaSuccess;
+    for (int i = 0; i < n && err == cudaSuccess; ++i) {
         float ms = 0.f;
-        VS_CUDA(cudaEventSynchronize(idx->ev1[i]));
-        VS_CUDA(cudaEventElapsedTime(&ms, idx->ev0[i], idx->ev1[i]));
+        err = cudaEventSynchronize(idx->ev1[i]);
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, idx->ev0[i], idx->ev1[i]);
         total += ms;
     }
+    cudaSetDevice(prev);   // leave the caller's current device as it was
+    VS_CUDA(err);
     if (total_ms) *total_ms = total;
     if (launches) *launches = n;
     if (reset) idx->timer_n = 0;

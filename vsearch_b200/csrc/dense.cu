@@ -604,7 +604,7 @@ int launch_merge(const uint64_t *d_in, int64_t P, int64_t stride_p, int64_t stri
                  int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, cudaStream_t st);
 int launch_merge_counted(const uint64_t *d_in, const uint32_t *d_counts, int64_t P, int64_t stride_p, int64_t stride_b,
                          int64_t B, int k_in, int k_out, int64_t id_offset, int64_t *d_ids, float *d_scores,
-                         uint64_t *d_keys, cudaStream_t st);
+                         uint64_t *d_keys, cudaStream_t st, const int *d_alt_flag = nullptr, int k_in_alt = 0);
 
 // workspace carve for one query chunk
 struct DenseWs {

@@ -77,7 +77,9 @@ struct vs_index {
 
     // ---- timing hook
     cudaEvent_t ev0[VS_TIMER_SLOTS] = {}, ev1[VS_TIMER_SLOTS] = {};
-    int last_mode = VS_MODE_SCAN;  // kernel family the last search used
+    int last_mode = VS_MODE_SCAN;  // kernel family the last search used, when the host chose it (forced scan / dense)
+    bool last_mode_on_device = false;   // the last search let the device decide: the answer is in *d_last_mode
+    int *d_last_mode = nullptr;    // device int written by inv_decide_kernel
     int timer_n = 0;         // launches recorded since the last reset (may exceed the ring)
 };
 
@@ -102,6 +104,13 @@ inline WsView ws_view(const vs_index *i) {
     v.cpl_shift = i->cpl_shift;
     return v;
 }
+
+// CSR-style sparse queries on the device: query b of a launch = entries [ptr[b0 + b], ptr[b0 + b + 1]) of tok / w
+struct SparseQueries {
+    const void *ptr; int ptr_dtype;    // VS_I32 | VS_I64 offsets
+    const int32_t *tok; const float *w;
+    int64_t b0;
+};
 
 namespace vs {
 int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void *d_col, int col_dtype,

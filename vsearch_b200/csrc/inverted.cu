@@ -257,6 +257,85 @@ __global__ void __launch_bounds__(256) inv_extract_kernel(const float *q, int vp
     if (tid == 0) { pref[m] = (uint32_t)run; L.total[b] = s_total; }
 }
 
+// Sparse queries given as CSR-style (token, weight) lists (vs_search_sparse; what the reference's top-k sparsifier
+// produces, upstream utils/sparse.py:8-19): one CTA per query copies the valid entries (0 <= token < V, weight != 0
+// after rounding to the index dtype) into the same QueryLists the extract kernel fills -- no dense [B, V] detour.
+__global__ void __launch_bounds__(256) inv_lists_from_csr_kernel(const void *q_ptr, int ptr_dtype, const int32_t *q_tok,
+                                                                 const float *q_w, int64_t b0, int V, int round_mode,
+                                                                 const uint64_t *post_ptr, QueryLists L) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint64_t s_total;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int64_t lo = ptr_dtype == VS_I32 ? (int64_t)((const int32_t *)q_ptr)[b0 + b] : ((const int64_t *)q_ptr)[b0 + b];
+    const int64_t hi = ptr_dtype == VS_I32 ? (int64_t)((const int32_t *)q_ptr)[b0 + b + 1] : ((const int64_t *)q_ptr)[b0 + b + 1];
+    uint32_t *tok = L.tok + (size_t)b * kMaxQueryNnz;
+    float *w = L.w + (size_t)b * kMaxQueryNnz;
+    uint32_t *pref = L.pref + (size_t)b * (kMaxQueryNnz + 1);
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    uint32_t n_out = 0;
+    uint64_t run = 0;
+    unsigned long long my_total = 0;
+    for (int64_t base = lo; base < hi; base += 256) {
+        const int64_t j = base + tid;
+        int32_t t = -1;
+        float v = 0.f;
+        if (j < hi) { t = q_tok[j]; v = round_score(q_w[j], round_mode); }
+        const bool keep = t >= 0 && t < V && v != 0.0f;
+        uint64_t len = 0;
+        if (keep) { len = post_ptr[t + 1] - post_ptr[t]; my_total += len; }
+        uint32_t n_tile, len_tile;
+        const uint32_t off = block_exclusive_scan_256(keep ? 1u : 0u, s_warp, n_tile);
+        const uint32_t ex = block_exclusive_scan_256((uint32_t)len, s_warp, len_tile);
+        const uint32_t at = n_out + off;
+        if (keep && at < (uint32_t)kMaxQueryNnz) { tok[at] = (uint32_t)t; w[at] = v; pref[at] = (uint32_t)(run + ex); }
+        n_out += n_tile;
+        run += len_tile;
+    }
+    atomicAdd((unsigned long long *)&s_total, my_total);
+    __syncthreads();
+    if (tid == 0) {
+        L.cnt[b] = n_out;
+        pref[min(n_out, (uint32_t)kMaxQueryNnz)] = (uint32_t)run;
+        L.total[b] = s_total;
+    }
+}
+
+// scan or inverted lists?  One CTA looks at the extracted queries of the chunk and writes the decision where the two
+// scoring kernels and the merge read it -- the host never waits for it.  mode: VS_MODE_AUTO applies the cost model
+// (seconds per query, constants measured on B200), VS_MODE_INVERTED takes the lists whenever they can serve the chunk
+// (<= kMaxQueryNnz non-zeros and < 2^32 postings per query; otherwise the scan answers).
+__global__ void __launch_bounds__(256) inv_decide_kernel(const QueryLists L, int Bc, int mode, double t_scan, double postings_per_sec,
+                                                         double t_rows_fixed, int *flag, int *last_mode) {
+    __shared__ uint32_t s_max_cnt;
+    __shared__ unsigned long long s_max_tot, s_sum_tot;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_max_cnt = 0; s_max_tot = 0; s_sum_tot = 0; }
+    __syncthreads();
+    uint32_t mc = 0;
+    unsigned long long mt = 0, st = 0;
+    for (int i = tid; i < Bc; i += 256) {
+        mc = max(mc, L.cnt[i]);
+        const unsigned long long t = L.total[i];
+        mt = max(mt, t);
+        st += t;
+    }
+    atomicMax(&s_max_cnt, mc);
+    atomicMax(&s_max_tot, mt);
+    atomicAdd(&s_sum_tot, st);
+    __syncthreads();
+    if (tid == 0) {
+        const bool usable = s_max_cnt <= (uint32_t)kMaxQueryNnz && s_max_tot < (1ull << 32);
+        bool use = usable;
+        if (mode == VS_MODE_AUTO) {
+            const double t_inv = ((double)s_sum_tot / (double)Bc) / postings_per_sec + t_rows_fixed;
+            use = usable && t_inv < t_scan;
+        }
+        *flag = use ? 1 : 0;
+        *last_mode = use ? VS_MODE_INVERTED : VS_MODE_SCAN;
+    }
+}
+
 // ------------------------------------------------------------------------------------------- search
 struct InvSearchParams {
     QueryLists L;
@@ -267,9 +346,10 @@ struct InvSearchParams {
     int val_kind;        // 0 none (binary), 1 f32, 2 f16, 3 bf16
     int V, rows_per_block, n_blocks, blocks_per_cta;
     int64_t n_rows;
-    uint64_t *cand;      // [B, gridDim.x, k]
-    int k, score_round;
+    uint64_t *cand;      // [B, gridDim.x, cand_stride]: k keys per list
+    int k, score_round, cand_stride;
     int flags;           // experiment switches (VSEARCH_B200_K3_FLAGS): 1 = re-select after the first block, 2 = L2 prefetch
+    const int *use_inv;  // device flag written by inv_decide_kernel: 0 = the scan serves this chunk, this kernel exits
 };
 
 __device__ __forceinline__ float posting_value(const void *vals, int kind, uint64_t pos) {
@@ -325,6 +405,7 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     float *acc = reinterpret_cast<float *>(s_len + kTokTile);                  // rows_per_block
     __shared__ CtaState st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (*p.use_inv == 0) return;
     const int q = blockIdx.y;
     const int cnt = (int)min(p.L.cnt[q], (uint32_t)kMaxQueryNnz);
     const uint32_t *tok = p.L.tok + (size_t)q * kMaxQueryNnz;
@@ -478,7 +559,7 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
         sampled = true;
         __syncthreads();
     }
-    cta_write_topk_flat<NT>(cbuf, p.k, hist, &st, p.cand + ((size_t)q * gridDim.x + blockIdx.x) * (size_t)p.k);
+    cta_write_topk_flat<NT>(cbuf, p.k, hist, &st, p.cand + ((size_t)q * gridDim.x + blockIdx.x) * (size_t)p.cand_stride);
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -502,43 +583,30 @@ static QueryLists carve_lists(uint8_t *base, int64_t Bc, uint8_t **end) {
 
 int scan_cap_for_k(int k);
 
-// Extract the sparse form of Bc prepared queries and report (SYNC: a 12*Bc-byte readback) the largest
-// non-zero count and the mean postings per query, so the caller can choose scan vs inverted.
-int inverted_extract(vs_index *idx, const float *d_qprep, int vpad, int64_t Bc, void *d_ws, uint32_t *max_nnz,
-                     double *mean_postings, uint64_t *max_postings, cudaStream_t st) {
-    int rc = build_inverted(idx, st);
+// Sparse form of Bc queries -> QueryLists in d_ws, from the prepared dense rows (extract) or from caller-supplied
+// (token, weight) lists; then the scan-vs-inverted decision, all on the stream (no readback).  d_flag: device int the
+// scoring kernels and the merge read; idx->d_last_mode keeps the decision for vs_index_last_mode.
+int inverted_prepare(vs_index *idx, const float *d_qprep, int vpad, const void *d_qptr, int ptr_dtype, const int32_t *d_qtok,
+                     const float *d_qw, int64_t b0, int64_t Bc, int mode, int round_mode, double t_scan, double postings_per_sec,
+                     double t_rows_fixed, void *d_ws, int *d_flag, cudaStream_t st) {
+    int rc = build_inverted(idx, st);   // lazy, first use only (SYNC once)
     if (rc) return rc;
     uint8_t *end;
     QueryLists L = carve_lists((uint8_t *)d_ws, Bc, &end);
-    inv_extract_kernel<<<(unsigned)Bc, 256, 0, st>>>(d_qprep, vpad, (int)idx->n_cols, idx->post_ptr, L);
+    if (d_qptr != nullptr)
+        inv_lists_from_csr_kernel<<<(unsigned)Bc, 256, 0, st>>>(d_qptr, ptr_dtype, d_qtok, d_qw, b0, (int)idx->n_cols, round_mode,
+                                                                idx->post_ptr, L);
+    else
+        inv_extract_kernel<<<(unsigned)Bc, 256, 0, st>>>(d_qprep, vpad, (int)idx->n_cols, idx->post_ptr, L);
     VS_CUDA(cudaGetLastError());
-    std::vector<uint32_t> h_cnt((size_t)Bc);
-    std::vector<uint64_t> h_tot((size_t)Bc);
-    VS_CUDA(cudaMemcpyAsync(h_cnt.data(), L.cnt, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
-    VS_CUDA(cudaMemcpyAsync(h_tot.data(), L.total, (size_t)Bc * 8, cudaMemcpyDeviceToHost, st));
-    VS_CUDA(cudaStreamSynchronize(st));
-    uint32_t mx = 0;
-    uint64_t mp = 0;
-    double sum = 0;
-    for (int64_t i = 0; i < Bc; ++i) {
-        mx = h_cnt[i] > mx ? h_cnt[i] : mx;
-        mp = h_tot[i] > mp ? h_tot[i] : mp;
-        sum += (double)h_tot[i];
-    }
-    *max_nnz = mx;
-    *max_postings = mp;
-    *mean_postings = Bc ? sum / (double)Bc : 0.0;
+    inv_decide_kernel<<<1, 256, 0, st>>>(L, (int)Bc, mode, t_scan, postings_per_sec, t_rows_fixed, d_flag, idx->d_last_mode);
+    VS_CUDA(cudaGetLastError());
     return VS_OK;
 }
 
-bool inverted_usable(uint32_t max_nnz, uint64_t max_postings) {
-    return max_nnz <= (uint32_t)kMaxQueryNnz && max_postings < (1ull << 32);
-}
-
-// Score Bc extracted queries (lists already in d_ws) -> cand [Bc, n_ctas, k].
-int launch_inverted(vs_index *idx, int64_t Bc, int k, int score_round, int group, uint32_t max_nnz, void *d_ws, uint64_t *d_cand,
-                    cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t st) {
-    (void)group; (void)max_nnz;
+// Score Bc extracted queries (lists already in d_ws) -> cand [Bc, n_ctas, k]; a no-op when *d_flag == 0.
+int launch_inverted(vs_index *idx, int64_t Bc, int k, int cand_stride, int score_round, void *d_ws, uint64_t *d_cand,
+                    const int *d_flag, cudaStream_t st) {
     uint8_t *end;
     QueryLists L = carve_lists((uint8_t *)d_ws, Bc, &end);
     const size_t smem = (size_t)kCapMax * 8 + 256 * 4 + (size_t)kTokTile * 4 * 4 + (size_t)idx->blk_rows * 4;
@@ -548,12 +616,11 @@ int launch_inverted(vs_index *idx, int64_t Bc, int k, int score_round, int group
     p.L = L; p.blk_ptr = idx->blk_ptr; p.blk_base = idx->blk_base; p.post_row = idx->post_row; p.post_val = idx->post_val;
     p.val_kind = idx->kind == 1 ? (idx->store_dtype == VS_F32 ? 1 : (idx->store_dtype == VS_F16 ? 2 : 3)) : 0;
     p.V = (int)idx->n_cols; p.rows_per_block = idx->blk_rows; p.n_blocks = idx->n_blocks; p.blocks_per_cta = idx->blocks_per_cta;
-    p.n_rows = idx->n_rows; p.cand = d_cand; p.k = k; p.score_round = score_round;
-    const char *fl = getenv("VSEARCH_B200_K3_FLAGS");
-    p.flags = fl ? atoi(fl) : 3;
-    if (ev0) VS_CUDA(cudaEventRecord(ev0, st));
+    p.n_rows = idx->n_rows; p.cand = d_cand; p.k = k; p.score_round = score_round; p.cand_stride = cand_stride;
+    static const int k3_flags = getenv("VSEARCH_B200_K3_FLAGS") ? atoi(getenv("VSEARCH_B200_K3_FLAGS")) : 3;
+    p.flags = k3_flags;
+    p.use_inv = d_flag;
     inv_search_kernel<<<dim3(idx->n_ctas, (unsigned)Bc), kInvThreads, smem, st>>>(p);
-    if (ev1) VS_CUDA(cudaEventRecord(ev1, st));
     VS_CUDA(cudaGetLastError());
     return VS_OK;
 }

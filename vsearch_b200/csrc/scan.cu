@@ -48,6 +48,15 @@ struct ScanParams {
     int score_round;
     uint32_t sentinel;     // V | V << 16
     unsigned long long *prof;  // diagnostic: per (CTA, pass) phase timestamps (globaltimer ns), or nullptr
+    // sparse queries (vs_search_sparse): CSR-style lists instead of prepared dense rows; query b of this launch is
+    // entries [q_ptr[b0 + b], q_ptr[b0 + b + 1]) of q_tok / q_w
+    const void *q_ptr;
+    int ptr_dtype;
+    const int32_t *q_tok;
+    const float *q_w;
+    int64_t b0;
+    int64_t n_cols;
+    const int *use_inv;        // device flag (auto mode): != 0 -> the inverted lists serve this chunk, this kernel exits
 };
 constexpr int kProfSlots = 8;
 __device__ __forceinline__ void prof_mark(const ScanParams &p, int b, int slot) {
@@ -123,6 +132,47 @@ __device__ __forceinline__ float chunk_dot(const Chunk<VT> &ch, const uint32_t q
             b = fmaf(g[2 * i + 1], half_hi(v[i], VT), b);
         }
         return a + b;
+    }
+}
+
+// Stage query b into shared memory (fp32 [vpad], slot V.. = 0).  Dense input: 1-D bulk TMA copies of the prepared row,
+// completion on the CTA's mbarrier.  Sparse input: zero the vector, scatter the (token, weight) list (weights rounded
+// like the prepared rows; duplicate tokens add up, tokens outside [0, V) are ignored).  Called by all threads; returns
+// with the vector visible to the whole CTA.  `between` runs after the copies are issued and before anybody waits.
+template <int NT, typename F>
+__device__ __forceinline__ void stage_query(uint8_t *smem, CtaState *st, const ScanParams &p, const int b, uint32_t &phase,
+                                            F between) {
+    const int tid = threadIdx.x;
+    const uint32_t q_bytes = (uint32_t)p.vpad * 4u;
+    if (p.q_ptr == nullptr) {
+        if (tid == 0) {
+            cta_state_reset(st);
+            fence_proxy_async();  // earlier generic-proxy reads of the vector are ordered before the async writes
+            mbar_arrive_expect_tx(&st->mbar, q_bytes);
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.q + (size_t)b * p.vpad);
+            for (uint32_t off = 0; off < q_bytes; off += 16384u) {
+                uint32_t n = min(16384u, q_bytes - off);
+                bulk_g2s(smem + off, src + off, n, &st->mbar);
+            }
+        }
+        between();
+        __syncthreads();          // cnt/tau reset visible
+        mbar_wait(&st->mbar, phase);
+        phase ^= 1u;
+    } else {
+        if (tid == 0) cta_state_reset(st);
+        float4 *q4 = reinterpret_cast<float4 *>(smem);
+        for (int i = tid; i < (p.vpad >> 2); i += NT) q4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        between();
+        __syncthreads();
+        const int64_t lo = p.ptr_dtype == VS_I32 ? (int64_t)((const int32_t *)p.q_ptr)[p.b0 + b] : ((const int64_t *)p.q_ptr)[p.b0 + b];
+        const int64_t hi = p.ptr_dtype == VS_I32 ? (int64_t)((const int32_t *)p.q_ptr)[p.b0 + b + 1] : ((const int64_t *)p.q_ptr)[p.b0 + b + 1];
+        float *qf = reinterpret_cast<float *>(smem);
+        for (int64_t j = lo + tid; j < hi; j += NT) {
+            const int32_t t = p.q_tok[j];
+            if (t >= 0 && (int64_t)t < p.n_cols) atomicAdd(&qf[t], round_score(p.q_w[j], p.score_round));
+        }
+        __syncthreads();
     }
 }
 
@@ -248,7 +298,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     const uint32_t w_begin = p.part_win_begin[part];
     const int nwin = (int)(p.part_win_begin[part + 1] - w_begin);
     const uint32_t row0 = p.part_row_begin[part];
-    const uint32_t q_bytes = (uint32_t)p.vpad * 4u;
 
     if (tid == 0) {
         mbar_init(&st.mbar, 1);
@@ -257,22 +306,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     }
     __syncthreads();
 
+    if (p.use_inv != nullptr && *p.use_inv != 0) return;   // auto mode chose the inverted lists for this chunk
     uint32_t phase = 0;
     for (int b = 0; b < p.B; ++b) {
-        // ---- stage the query vector: bulk TMA into shared memory
-        if (tid == 0) {
-            cta_state_reset(&st);
-            fence_proxy_async();  // earlier generic-proxy reads of qs are ordered before the async writes
-            mbar_arrive_expect_tx(&st.mbar, q_bytes);
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.q + (size_t)b * p.vpad);
-            for (uint32_t off = 0; off < q_bytes; off += 16384u) {
-                uint32_t n = min(16384u, q_bytes - off);
-                bulk_g2s(smem + off, src + off, n, &st.mbar);
-            }
-        }
-        __syncthreads();          // cnt/tau reset visible
-        mbar_wait(&st.mbar, phase);
-        phase ^= 1u;
+        // ---- stage the query vector
+        stage_query<kScanThreads>(smem, &st, p, b, phase, [] {});
 
         // ---- stream this warp's part, 64 chunks (two per lane) per step.  The stream carries kStreamSlack windows
         // of slack past its end, so the prefetch ring never needs a bounds check: loads are unconditional,
@@ -526,7 +564,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_bin_kernel(const ScanPar
     const uint32_t w_begin = p.part_win_begin[part];
     const int nstep = (int)(p.part_win_begin[part + 1] - w_begin) / kBinC;   // parts are whole steps (build_index.cu)
     const uint32_t row0 = p.part_row_begin[part];
-    const uint32_t q_bytes = (uint32_t)p.vpad * 4u;
     constexpr int SC = 32 * kBinC;   // chunks per step
 
     if (tid == 0) {
@@ -536,29 +573,19 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_bin_kernel(const ScanPar
     }
     __syncthreads();
 
+    if (p.use_inv != nullptr && *p.use_inv != 0) return;   // auto mode chose the inverted lists for this chunk
     uint32_t phase = 0;
     for (int b = 0; b < p.B; ++b) {
         prof_mark(p, b, 0);
-        if (tid == 0) {
-            cta_state_reset(&st);
-            fence_proxy_async();  // earlier generic-proxy reads of qs are ordered before the async writes
-            mbar_arrive_expect_tx(&st.mbar, q_bytes);
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.q + (size_t)b * p.vpad);
-            for (uint32_t off = 0; off < q_bytes; off += 16384u) {
-                uint32_t n = min(16384u, q_bytes - off);
-                bulk_g2s(smem + off, src + off, n, &st.mbar);
-            }
-        }
         // the first step's loads go out before anybody waits for the query vector
         const uint4 *cp = p.cols + (uint64_t)w_begin * 32ull + lane;
         uint4 r[kBinC];
-#pragma unroll
-        for (int i = 0; i < kBinC; ++i) r[i] = ldg_stream(cp + i * 32);
         const BinSmem L = bin_smem(smem, p);
-        for (int i = tid; i < kHistFine + kHistCoarse; i += kScanThreads) L.fine[i] = 0u;   // coarse follows fine
-        __syncthreads();          // cnt/tau reset, empty histogram visible
-        mbar_wait(&st.mbar, phase);
-        phase ^= 1u;
+        stage_query<kScanThreads>(smem, &st, p, b, phase, [&] {
+#pragma unroll
+            for (int i = 0; i < kBinC; ++i) r[i] = ldg_stream(cp + i * 32);
+            for (int i = tid; i < kHistFine + kHistCoarse; i += kScanThreads) L.fine[i] = 0u;   // coarse follows fine
+        });
         prof_mark(p, b, 1);
 
         float carry = 0.f;
@@ -676,10 +703,18 @@ static int launch_scan_v(const vs_index *idx, const ScanParams &p, size_t smem, 
     return launch_scan_t<VT, D, PAIR, false, false>(idx, p, smem, st);
 }
 
-// d_qprep: [B, vpad] fp32; d_cand: [B, n_ctas, k] keys; d_scores_out optional [B, N]
-int launch_scan(const vs_index *idx, const float *d_qprep, int vpad, int64_t B, int k, int score_round,
-                uint64_t *d_cand, float *d_scores_out, cudaStream_t st) {
+// Queries: d_qprep [B, vpad] fp32 prepared rows, or (sq != nullptr) CSR-style lists.  d_cand: [B, n_ctas, scan_kout]
+// keys; d_scores_out optional [B, N]; d_use_inv optional device flag (auto mode).
+int launch_scan(const vs_index *idx, const float *d_qprep, const SparseQueries *sq, int vpad, int64_t B, int k,
+                int score_round, uint64_t *d_cand, float *d_scores_out, const int *d_use_inv, cudaStream_t st) {
     ScanParams p;
+    p.q_ptr = sq ? sq->ptr : nullptr;
+    p.ptr_dtype = sq ? sq->ptr_dtype : VS_I64;
+    p.q_tok = sq ? sq->tok : nullptr;
+    p.q_w = sq ? sq->w : nullptr;
+    p.b0 = sq ? sq->b0 : 0;
+    p.n_cols = idx->n_cols;
+    p.use_inv = d_use_inv;
     p.cols = idx->cols;
     p.vals = idx->vals;
     p.tails = idx->tails;

@@ -82,9 +82,62 @@ __global__ void __launch_bounds__(kSparsifyThreads) sparsify_topk_kernel(float *
         if (s_bow_col[j] >= 0) row[s_bow_col[j]] = s_bow_val[j];
 }
 
+// ---- dense [n_rows, ld] -> CSR: one warp per row, 32 columns per step (coalesced), the
+// survivors of a step are ranked with one ballot.  Replaces `vectors.to_sparse_csr()` of the reference's build_index
+// (retriever.py:299-305) and turns a sparsified query batch into the (token, weight) lists vs_search_sparse takes.
+// Two calls: count (col == nullptr: row lengths into out[r]) and fill (crow given).
+template <typename T>
+__device__ __forceinline__ float dense_load(const T *p) { return (float)*p; }
+template <>
+__device__ __forceinline__ float dense_load<__half>(const __half *p) { return __half2float(*p); }
+template <>
+__device__ __forceinline__ float dense_load<__nv_bfloat16>(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) dense_to_csr_kernel(const T *x, int64_t n_rows, int64_t ld, int n_cols, int64_t *row_nnz_or_crow,
+                                                           int32_t *col, float *val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const T *row = x + r * ld;
+    const bool fill = col != nullptr;
+    int64_t at = fill ? row_nnz_or_crow[r] : 0;
+    int64_t n = 0;
+    for (int c0 = 0; c0 < n_cols; c0 += 32) {
+        const int c = c0 + lane;
+        const float v = c < n_cols ? dense_load<T>(row + c) : 0.f;
+        const bool nz = v != 0.0f;
+        const uint32_t m = __ballot_sync(0xffffffffu, nz);
+        if (fill && nz) {
+            const int64_t o = at + n + __popc(m & ((1u << lane) - 1u));
+            col[o] = c;
+            val[o] = v;
+        }
+        n += __popc(m);
+    }
+    if (!fill && lane == 0) row_nnz_or_crow[r] = n;
+}
+
 }  // namespace vs
 
 using namespace vs;
+
+extern "C" int vs_dense_to_csr(int device, const void *d_x, int x_dtype, int64_t n_rows, int64_t ld, int n_cols,
+                               int64_t *d_row_nnz_or_crow, int32_t *d_col, float *d_val, void *stream) {
+    VS_REQUIRE(d_x != nullptr && n_rows >= 0 && n_cols > 0 && ld >= n_cols && d_row_nnz_or_crow != nullptr, VS_ERR_INVALID,
+               "vs_dense_to_csr: bad argument");
+    VS_REQUIRE(x_dtype == VS_F32 || x_dtype == VS_F16 || x_dtype == VS_BF16, VS_ERR_INVALID, "vs_dense_to_csr: f32 / f16 / bf16 input");
+    VS_REQUIRE((d_col == nullptr) == (d_val == nullptr), VS_ERR_INVALID, "vs_dense_to_csr: d_col and d_val go together");
+    if (n_rows == 0) return VS_OK;
+    VS_CUDA(cudaSetDevice(device));
+    const unsigned blocks = (unsigned)((n_rows + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == VS_F32) dense_to_csr_kernel<float><<<blocks, 256, 0, st>>>((const float *)d_x, n_rows, ld, n_cols, d_row_nnz_or_crow, d_col, d_val);
+    else if (x_dtype == VS_F16) dense_to_csr_kernel<__half><<<blocks, 256, 0, st>>>((const __half *)d_x, n_rows, ld, n_cols, d_row_nnz_or_crow, d_col, d_val);
+    else dense_to_csr_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16 *)d_x, n_rows, ld, n_cols, d_row_nnz_or_crow, d_col, d_val);
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
+}
 
 extern "C" int vs_sparsify_topk(int device, float *d_q, int64_t B, int64_t ld, int n_cols, int k, const int32_t *d_bow_ids, int bow_ld,
                                 int bow_shift, void *stream) {

@@ -119,7 +119,7 @@ class _Engine:
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
         if h and nat is not None and getattr(nat, "LIB", None) is not None:  # module may be gone at interpreter exit
-            nat.LIB.vs_index_destroy(h)
+            nat.LIB.vs_index_destroy(h)   # restores the caller's current device itself
 
     def workspace(self, B: int, k: int) -> torch.Tensor:
         need = int(nat.LIB.vs_search_workspace_bytes(self.handle, B, k))
@@ -127,6 +127,40 @@ class _Engine:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
+
+    def _sparse_q(self, q: torch.Tensor):
+        """A sparse ``[B, V]`` query tensor (CSR or COO layout) -> (crow, col int32, val fp32) on the index device."""
+        if q.dim() != 2 or q.shape[1] != self.n_cols:
+            raise RuntimeError(f"query shape {tuple(q.shape)} does not match index width {self.n_cols}")
+        q = q.to(self.device)
+        if q.layout != torch.sparse_csr:
+            q = q.coalesce().to_sparse_csr() if q.layout == torch.sparse_coo else q.to_sparse_csr()
+        crow = q.crow_indices()
+        if crow.dtype not in (torch.int32, torch.int64):
+            crow = crow.to(torch.int64)
+        return crow.contiguous(), q.col_indices().to(torch.int32).contiguous(), q.values().to(torch.float32).contiguous()
+
+    def search_sparse(self, crow: torch.Tensor, col: torch.Tensor, val: torch.Tensor, k: int, mode: str = "auto",
+                      score_round: int = nat.VS_F32, id_offset: int = 0, keys_only: bool = False):
+        """Search with CSR-style (token, weight) query lists (``vs_search_sparse``): ``crow`` ``[B+1]`` int32/int64 offsets,
+        ``col`` int32 tokens, ``val`` fp32 weights, on this device (or all on the host)."""
+        B = crow.numel() - 1
+        k = int(k)
+        with torch.cuda.device(self.device):
+            ws = self.workspace(B, max(k, 1))
+            st = _stream_ptr(self.device)
+            keys = ids = scores = None
+            if keys_only:
+                keys = torch.empty((B, max(k, 0)), dtype=torch.int64, device=self.device)
+            else:
+                ids = torch.empty((B, max(k, 0)), dtype=torch.int64, device=self.device)
+                scores = torch.empty((B, max(k, 0)), dtype=torch.float32, device=self.device)
+            rc = nat.LIB.vs_search_sparse(self.handle, crow.data_ptr(), _TORCH2VS[crow.dtype], col.data_ptr(), val.data_ptr(), B, k,
+                                          nat.MODES[mode], score_round, id_offset,
+                                          None if ids is None else ids.data_ptr(), None if scores is None else scores.data_ptr(),
+                                          None if keys is None else keys.data_ptr(), ws.data_ptr(), ws.numel(), st)
+        nat.check(rc)
+        return keys if keys_only else (ids, scores)
 
     def _prep_q(self, q: torch.Tensor):
         q = q.to(self.device, non_blocking=True)
@@ -138,6 +172,11 @@ class _Engine:
 
     def search(self, q: torch.Tensor, k: int, mode: str = "auto", score_round: int = nat.VS_F32,
                id_offset: int = 0, keys_only: bool = False):
+        if q.layout != torch.strided:   # sparse queries: (token, weight) lists, no dense [B, V] rows
+            if self.kind == 0:
+                raise TypeError("sparse queries need a SparseIndex / BoTIndex")
+            return self.search_sparse(*self._sparse_q(q), k, mode=mode, score_round=score_round, id_offset=id_offset,
+                                      keys_only=keys_only)
         q = self._prep_q(q)
         B = q.shape[0]
         k = int(k)
@@ -180,7 +219,11 @@ class _Engine:
         B, k = ids.shape
         out = torch.empty((B, k), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            ws = self.workspace(B, 1)
+            need = int(nat.LIB.vs_score_rows_workspace_bytes(self.handle, B))   # the whole batch is prepared at once
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = None
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            ws = self._ws
             rc = nat.LIB.vs_score_rows(self.handle, q.data_ptr(), _TORCH2VS[q.dtype], B, q.stride(0), ids.data_ptr(), k,
                                        score_round, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
         nat.check(rc)
@@ -202,11 +245,41 @@ class _Engine:
         return float(ms.value), int(n.value)
 
 
-def topk_sparsify(emb_dense: torch.Tensor, k: int, bow_ids: Optional[torch.Tensor] = None, shift: int = 0) -> torch.Tensor:
+def dense_to_csr(x: torch.Tensor):
+    """Non-zeros of a dense ``[n, V]`` CUDA tensor as ``(crow int64 [n+1], col int32, val fp32)`` on the same device
+    (``vs_dense_to_csr``: count -> scan -> fill on the GPU; upstream uses ``Tensor.to_sparse_csr``, retriever.py:299-305)."""
+    if x.device.type != "cuda":
+        raise RuntimeError("vsearch_b200.dense_to_csr runs on CUDA tensors only (no CPU fallback)")
+    if x.dim() != 2:
+        raise ValueError("dense_to_csr needs a [n, V] matrix")
+    if x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        x = x.to(torch.float32)
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    n, v = x.shape
+    dev = x.device
+    crow = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    args = (dev.index, x.data_ptr(), _TORCH2VS[x.dtype], n, x.stride(0) if n else v, v)
+    with torch.cuda.device(dev):
+        if n:
+            nat.check(nat.LIB.vs_dense_to_csr(*args, crow[1:].data_ptr(), None, None, _stream_ptr(dev)))
+            torch.cumsum(crow[1:], 0, out=crow[1:])
+        nnz = int(crow[-1]) if n else 0
+        col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        val = torch.empty(nnz, dtype=torch.float32, device=dev)
+        if nnz:
+            nat.check(nat.LIB.vs_dense_to_csr(*args, crow.data_ptr(), col.data_ptr(), val.data_ptr(), _stream_ptr(dev)))
+    return crow, col, val
+
+
+def topk_sparsify(emb_dense: torch.Tensor, k: int, bow_ids: Optional[torch.Tensor] = None, shift: int = 0,
+                  as_sparse: bool = False) -> torch.Tensor:
     """Keep the ``k`` largest activations of every row of ``emb_dense`` ``[B, V]`` (ties -> lower column), zero the
     rest; with ``bow_ids`` ``[B, L]`` the columns ``id - shift`` of the row's own tokens survive too.  Upstream
     ``utils/sparse.py:8-19`` (``topk_sparsify`` / ``build_topk_mask``) and the ``logical_or(bow_mask, topk_mask)`` of
-    ``encoder/vdr.py:159-169``; returns a new fp32 tensor on the embedding's CUDA device."""
+    ``encoder/vdr.py:159-169``; returns a new fp32 tensor on the embedding's CUDA device -- dense like upstream's, or
+    with ``as_sparse=True`` a ``torch.sparse_csr`` tensor of the survivors (the (token, weight) lists ``Index.search``
+    hands to ``vs_search_sparse`` without a dense ``[B, V]`` detour)."""
     if emb_dense.device.type != "cuda":
         raise RuntimeError("vsearch_b200.topk_sparsify runs on CUDA tensors only (no CPU fallback)")
     one_d = emb_dense.dim() == 1
@@ -219,6 +292,9 @@ def topk_sparsify(emb_dense: torch.Tensor, k: int, bow_ids: Optional[torch.Tenso
         nat.check(nat.LIB.vs_sparsify_topk(out.device.index, out.data_ptr(), B, out.stride(0), V, int(k),
                                            None if ids is None else ids.data_ptr(), 0 if ids is None else ids.shape[1],
                                            int(shift), _stream_ptr(out.device)))
+    if as_sparse:
+        crow, col, val = dense_to_csr(out)
+        return torch.sparse_csr_tensor(crow, col.to(torch.int64), val, size=(B, V))
     return out[0] if one_d else out
 
 
@@ -265,10 +341,13 @@ class Index:
     def vector(self, value):
         self._vector = value
         self._engine = None
+        self._logical_dtype = None
 
     def _value_dtype(self):
         if self._vector is not None:
             return self._vector.dtype
+        if getattr(self, "_logical_dtype", None) is not None:   # engine-only index: dtype the logical vector would have
+            return self._logical_dtype
         sd = self._engine.store_dtype if self._engine is not None else nat.VS_F32
         return {nat.VS_F16: torch.float16, nat.VS_BF16: torch.bfloat16}.get(sd, torch.float32)
 
@@ -363,7 +442,7 @@ class Index:
         """``scores = q @ vector.t(); scores.topk(k)`` (upstream index.py:88-94) without the [B, N] matrix."""
         eng = self._require_engine()
         one_d = q_embs.dim() == 1
-        q = q_embs.unsqueeze(0) if one_d else q_embs
+        q = q_embs.unsqueeze(0) if one_d else q_embs   # strided, or a sparse [B, V] tensor of (token, weight) lists
         ids, scores = eng.search(q, k, mode=self.search_mode, score_round=self._score_round())
         scores = scores.to(self._value_dtype())
         if one_d:
@@ -477,10 +556,28 @@ class SparseIndex(Index):
             v = v.to_sparse_csr()
         return v.crow_indices(), v.col_indices(), v.values(), v.shape
 
-    def _build_engine(self, device):
+    def _device_csr(self, dev):
+        """(crow, col, val, shape) on ``dev``; a strided ``.vector`` is sparsified there (``vs_dense_to_csr``)."""
+        v = self._vector
+        if v.layout == torch.strided:
+            crow, col, val = dense_to_csr(v.to(dev))
+            return crow, col, val.to(v.dtype if v.dtype in (torch.float16, torch.bfloat16) else torch.float32), v.shape
         crow, col, val, shape = self._csr_parts()
+        return crow.to(dev), col.to(dev), val.to(dev), shape
+
+    def _drop_dense_vector(self):
+        """A strided ``.vector`` was sparsified on the GPU: keep only the engine; ``.vector`` exports CSR on demand
+        (upstream's ``.vector`` of a sparse index is a CSR tensor, retriever.py:304)."""
+        if self._vector is not None and self._vector.layout == torch.strided:
+            dt = self._vector.dtype
+            self._vector = None
+            self._logical_dtype = dt
+
+    def _build_engine(self, device):
         dev = self._resolve(device)
-        self._engine = _Engine.from_csr(crow.to(dev), col.to(dev), val.to(dev), shape, dev)
+        crow, col, val, shape = self._device_csr(dev)
+        self._engine = _Engine.from_csr(crow, col, val, shape, dev)
+        self._drop_dense_vector()
 
     def save(self, path):
         """scipy-loadable ``.npz`` (upstream index.py:181-202)."""
@@ -505,10 +602,11 @@ class BoTIndex(SparseIndex):
     index_type = IndexType.BAG_OF_TOKEN
 
     def _build_engine(self, device):
-        crow, col, val, shape = self._csr_parts()
         dev = self._resolve(device)
+        crow, col, val, shape = self._device_csr(dev)
         binary = bool((val == 1).all().item()) if val.numel() else True
-        self._engine = _Engine.from_csr(crow.to(dev), col.to(dev), None if binary else val.to(dev), shape, dev)
+        self._engine = _Engine.from_csr(crow, col, None if binary else val, shape, dev)
+        self._drop_dense_vector()
 
     @classmethod
     def from_token_csr(cls, crow: torch.Tensor, col: torch.Tensor, shape, device="cuda", dtype=torch.float32):
@@ -552,7 +650,3 @@ class BoTIndex(SparseIndex):
                 nat.check(nat.LIB.vs_bot_from_tokens(*args, crow.data_ptr(), col.data_ptr(), _sp(dev)))
         return cls.from_token_csr(crow, col, (n, int(vocab_size) - int(num_shift)), device=dev, dtype=dtype)
 
-    def _value_dtype(self):
-        if self._vector is None and getattr(self, "_logical_dtype", None) is not None:
-            return self._logical_dtype
-        return super()._value_dtype()

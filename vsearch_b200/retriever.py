@@ -88,33 +88,6 @@ class Retriever:
         ids = torch.gather(ret_indices.reshape(-1, k), 1, order.indices)
         return SearchResults(ids, order.values)
 
-    # ---- in-training negative mining (a caller of retrieve, upstream retriever.py:150-205) ------------------
-    def retireve_negatives(self, q_emb, answers, ret_neg_num: int = 1, ret_topk: int = 100, pool_size: int = 20,
-                           ret_dropout: float = 0, index: Optional[Index] = None, is_positive=None):
-        """(sic: upstream's spelling.)  Retrieve ``ret_topk`` passages per query, keep those that do NOT contain an
-        answer string (first ``pool_size`` of them), pad with random passages when fewer than ``ret_neg_num`` remain,
-        sample ``ret_neg_num`` per query.  ``is_positive(answers, text)`` defaults to an uncased token-sequence match
-        (upstream ``has_answer(..., 'string')``, utils/qa_utils.py:258-283)."""
-        import random
-
-        index = self.index or index   # upstream's precedence
-        assert index, "No index Found"
-        assert answers, "No answer strings Found"
-        is_positive = is_positive or _has_answer
-        ret_indices, _ = self.retrieve(q_emb, a=768, k=ret_topk, dropout=ret_dropout, index=index)
-        batch_neg_texts = []
-        for sample_id, sample_ret in enumerate(ret_indices.tolist()):
-            pool = []
-            for ind in sample_ret:
-                if not is_positive(answers[sample_id], index.get_sample(ind)):
-                    pool.append(ind)
-                if len(pool) >= pool_size:
-                    break
-            if len(pool) < ret_neg_num:
-                pool += random.sample(range(len(index)), ret_neg_num - len(pool))
-            batch_neg_texts.append([_normalize_text(index.get_sample(i)) for i in random.sample(pool, ret_neg_num)])
-        return batch_neg_texts
-
     # ---- index construction -------------------------------------------------------------------------
     def build_index(self, texts=None, batch_size: int = 32, index_type=IndexType.DENSE, bag_of_token: bool = False,
                     vectors: Optional[torch.Tensor] = None):
@@ -140,11 +113,15 @@ class Retriever:
             self.index.vector = vectors
         elif index_type == IndexType.SPARSE:
             self.index = SparseIndex()
-            self.index.vector = vectors if vectors.layout == torch.sparse_csr else vectors.to_sparse_csr()
+            # a dense [N, V] matrix is sparsified on the GPU when the index moves there (vs_dense_to_csr) instead of
+            # upstream's vectors.to_sparse_csr() (retriever.py:304)
+            self.index.vector = vectors if vectors.layout in (torch.sparse_csr, torch.strided) else vectors.to_sparse_csr()
         elif index_type == IndexType.BAG_OF_TOKEN:
             self.index = BoTIndex()
-            if vectors.layout != torch.sparse_csr:
-                vectors = (vectors != 0).to(torch.float16).to_sparse_csr()  # upstream: fp16 ones (:232-251)
+            if vectors.layout == torch.strided:
+                vectors = (vectors != 0).to(torch.float16)  # upstream: fp16 ones (:232-251); sparsified on the GPU
+            elif vectors.layout != torch.sparse_csr:
+                vectors = vectors.to_sparse_csr()
             self.index.vector = vectors
         else:
             raise NotImplementedError
@@ -182,28 +159,3 @@ class Retriever:
         self.index_type = index_type
         cls = {IndexType.DENSE: Index, IndexType.SPARSE: SparseIndex, IndexType.BAG_OF_TOKEN: BoTIndex}[index_type]
         self.index = cls(index_file, data_file, device=self.device)
-
-
-def _normalize_text(text: str) -> str:
-    """upstream data/biencoder_dataset.py:27-29"""
-    return text.replace("\u2019", "'").replace("\n", " ")
-
-
-def _words(text: str):
-    """Uncased alphanumeric-run / single-symbol tokens of the NFD-normalised text (the DPR-style tokenizer upstream's
-    ``has_answer`` relies on, utils/qa_utils.py:244-246, 271-279)."""
-    import unicodedata
-
-    import regex
-
-    text = unicodedata.normalize("NFD", _normalize_text(text))
-    return [t.lower() for t in regex.findall(r"[\p{L}\p{N}\p{M}]+|[^\p{Z}\p{C}]", text)]
-
-
-def _has_answer(answers, text) -> bool:
-    words = _words(text)
-    for a in answers:
-        aw = _words(a)
-        if aw and any(aw == words[i:i + len(aw)] for i in range(len(words) - len(aw) + 1)):
-            return True
-    return False

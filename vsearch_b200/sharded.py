@@ -49,12 +49,16 @@ class ShardedIndex:
             raise RuntimeError(f"selected index k out of range (k={k} > N={self.n_rows_total})")
         one_d = q_embs.dim() == 1
         q = q_embs.unsqueeze(0) if one_d else q_embs
-        n_local = self.local._require_engine().n_rows
+        eng = self.local._require_engine()
+        n_local = eng.n_rows
         k_local = min(k, n_local)
-        keys = self.local.search_keys(q, k_local, id_offset=self.row_offset)
-        if k_local < k:  # short shard: pad with empty keys so every rank gathers the same shape
-            pad = torch.zeros((keys.shape[0], k - k_local), dtype=keys.dtype, device=keys.device)
-            keys = torch.cat([keys, pad], dim=1)
+        if k_local == 0:   # a rank without rows (more ranks than rows): it contributes empty keys only
+            keys = torch.zeros((q.shape[0], k), dtype=torch.int64, device=eng.device)
+        else:
+            keys = self.local.search_keys(q, k_local, id_offset=self.row_offset)
+            if k_local < k:  # short shard: pad with empty keys so every rank gathers the same shape
+                pad = torch.zeros((keys.shape[0], k - k_local), dtype=keys.dtype, device=keys.device)
+                keys = torch.cat([keys, pad], dim=1)
         gathered = gather_keys(keys, self.group) if dist.is_initialized() else keys.unsqueeze(0)
         ids, scores = self._merge(gathered, k)
         scores = scores.to(self.local._value_dtype())
