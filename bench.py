@@ -159,6 +159,15 @@ def profiled_traffic(mode="scan"):
         return None, None
 
 
+def smem_atomic_ceiling():
+    """Measured shared-memory fp32 atomic-add rate of one B200 (all SMs), from the committed micro-benchmark run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2e_smem_atomics.json")) as f:
+            return float(json.load(f)["atomicAdd(float) CAS loop"]["ops_per_s"]), "profiles/r2e_smem_atomics.json (scripts/micro/smem_atomics.cu)"
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 # ---------------------------------------------------------------------------------------------- CPU reference
 def cpu_reference(steps, warmup, budget_s=25.0, rows=1_000_000, bq=16):
     """The reference's CPU path (index.py:88-94 via oracle/ref_search.py) on a bounded sample:
@@ -390,6 +399,14 @@ def run_cfg2(ctx):
                     "kernel_ms_per_step": kern_ms, "steps_timed": steps,
                     "kernel_share_of_step": m["kernel_share_of_step"],
                     "frac_of_8TBps": (achieved / 8000.0) if achieved else None, "q_tile": 1}
+        if used != "scan":
+            # K3 is bound by shared-memory read-modify-write throughput, not HBM: postings/s against the measured ceiling of
+            # the operation it issues (atomicAdd(float) in shared memory = an ATOMS.CAST.SPIN loop; scripts/micro/smem_atomics.cu)
+            postings = args.qnnz * (n_loc * TOKENS / V)
+            ceil_ops, ceil_src = smem_atomic_ceiling()
+            pps = B * postings / (kern_ms * 1e-3) if kern_ms > 0 else None
+            roofline["shared_atomics"] = {"achieved_postings_per_s": pps, "ceiling_ops_per_s": ceil_ops,
+                                          "frac": (pps / ceil_ops) if (pps and ceil_ops) else None, "ceiling_source": ceil_src}
         m["e2e"].update({"h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": B * K * 12})
         return {"mode": mode, "mode_used": used, "value": m["value"], "ms_per_step": m["ms_per_step"], "e2e": m["e2e"],
                 "gpu_launches": launches, "clocks": m["clocks"], "roofline": roofline}

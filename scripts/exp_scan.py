@@ -83,6 +83,15 @@ if args.prof and index.last_mode() == "scan":
     ph["pass_total_max_cta_mean"] = round(float(tot.mean(dim=1).max()), 2)
     ph["pass_total_min_cta_mean"] = round(float(tot.mean(dim=1).min()), 2)
     out["phases_us"] = ph
+if args.prof and index.last_mode() == "inverted":
+    buf = torch.zeros(n_ctas * args.batch * 8, dtype=torch.int64, device=dev)
+    nat.check(nat.LIB.vs_debug_scan_profile(eng.handle, ctypes.c_void_p(buf.data_ptr())))
+    index.search(q, args.k)
+    torch.cuda.synchronize()
+    nat.check(nat.LIB.vs_debug_scan_profile(eng.handle, None))
+    t = buf.view(args.batch, n_ctas, 8).double() / 1e3   # us per (query, CTA)
+    names = ["setup", "zero", "accumulate", "first_block_histogram", "block_select", "refresh_compact", "final_write", "total"]
+    out["phases_us_per_query_cta"] = {n: round(float(t[:, :, i].mean()), 2) for i, n in enumerate(names)}
 wf = torch.zeros(2, dtype=torch.int64, device=dev)
 nat.check(nat.LIB.vs_debug_gather_wavefronts(eng.handle, ctypes.c_void_p(wf.data_ptr()), None))
 torch.cuda.synchronize()

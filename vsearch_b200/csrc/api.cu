@@ -417,10 +417,10 @@ static int search_impl(const vs_index *cidx, const QueryInput &in, int64_t B, in
         if (rc) return rc;
         if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
         idx->timer_n += 1;
-        // per-CTA lists: scan_kout keys from the scan, k from the inverted lists (same stride)
+        // per-CTA lists: up to scan_kout keys each (zero padded), whichever kernel family wrote them
         rc = launch_merge_staged(w.cand, idx->n_ctas, kout, (int64_t)idx->n_ctas * kout, Bc, kout, k, id_offset,
                                  d_ids ? d_ids + b0 * k : nullptr, d_scores ? d_scores + b0 * k : nullptr,
-                                 d_keys ? d_keys + b0 * k : nullptr, try_inv ? w.flag : nullptr, k, w.merge, st);
+                                 d_keys ? d_keys + b0 * k : nullptr, nullptr, 0, w.merge, st);
         if (rc) return rc;
     }
     return VS_OK;

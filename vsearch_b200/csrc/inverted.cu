@@ -1,19 +1,26 @@
 // inverted.cu -- K3: token-major inverted-list scoring for sparse queries, sm_100a.
 // Same contract as the scan (replaces upstream index.py:91-92) but touches only the posting lists of the query's
-// non-zero tokens.  The lists are BLOCK-PARTITIONED: the rows are cut into blocks of R = 36,864 consecutive rows
-// (fewer for a smaller index), and every block keeps its own token-major posting
-// lists with 16-bit block-local row ids.  A block's fp32 score accumulator (R x 4 B <= 144 KB) lives in SHARED
-// memory, so scoring one query against one block is
+// non-zero tokens.  The lists are BLOCK-PARTITIONED: the rows are cut into blocks of R <= ~38,000 consecutive rows,
+// and every block keeps its own token-major posting lists with 16-bit block-local row ids.  A block's fp32 score
+// accumulator (R x 4 B) lives in SHARED memory, so scoring one query against one block is
 //   zero the accumulator -> add w_t (x value) at every posting of the query's tokens (shared-memory atomics)
 //   -> stream the accumulator through the fused top-k (topk.cuh)
 // without a byte of accumulator traffic to L2/HBM (the first version kept an [N] fp32 row in global memory:
 // RED.ADD.F32 into L2 + a read-and-clear pass over 2 x 4N bytes per query = 200 us per query at 21M rows).
-//   build   : WS stream -> blk_ptr[n_blocks][V+1] (uint32 offsets inside the block), blk_base[n_blocks] (uint64),
+//   build   : WS stream -> blk_rng[V][n_blocks] (uint2: start / end of the token's list inside the block; token-major so
+//             that the bounds a CTA needs for its consecutive blocks share a 32-byte sector), blk_base[n_blocks] (uint64),
 //             post_row[nnz] (uint16) (+ post_val[nnz]), post_ptr[V+1] = global list lengths (cost model) -- lazy
-//   extract : prepared query [vpad] -> compact (token, weight) list + total postings
+//   extract : prepared query [vpad] -> compact (token, weight) list + total postings (or the caller's lists as they are)
 //   search  : grid (n_ctas, queries); CTA x owns blocks [x*bpc, (x+1)*bpc) -> one candidate list per CTA -> merge.cu
+// Accumulate: the block's postings of ALL query tokens form one sequence (prefix sums of the list lengths); every warp
+// takes an equal share of it, 32 consecutive postings per load, 8 loads in flight per lane -- balanced whatever the list
+// lengths (heavy-tailed token popularity included), no per-list ramp-up.
+// Thresholds: the score histogram of topk.cuh.  The CTA's first block is counted whole (one pass over its accumulator),
+// the k-th bucket's lower bound becomes the float pre-filter; later blocks count and append only what passes it, and the
+// bound only rises.  At the end everything >= the final bound (k .. ~2k keys) goes to the merge kernel.  The exact
+// 64-bit machinery (CTA-wide radix selects) remains as the fallback for masses of equal scores / adversarial order.
 // Rows never touched keep score 0 and compete like any other row.
-// Algorithmic bytes per query: sum_t len(post_t) * (2 + b_val)  (+ 8 B of block pointers per (block, token)).
+// Algorithmic bytes per query: sum_t len(post_t) * (2 + b_val)  (+ 8 B of list bounds per (block, token)).
 #include <cub/device/device_scan.cuh>
 
 #include <stdlib.h>
@@ -29,11 +36,13 @@ constexpr int kInvThreads = 768;      // 24 warps, one CTA per SM (shared memory
 constexpr int kInvWarps = kInvThreads / 32;
 constexpr int kInvBuildThreads = 1024;
 constexpr int kMaxQueryNnz = 4096;    // queries denser than this are served by the scan kernels
-constexpr int kBlockRowsMax = 36864;  // accumulator rows per block: 144 KB of the 227 KB
+constexpr int kBlockRowsMax = 37120;  // accumulator rows per block: 145 KB of the 227 KB
+constexpr int kInvAppend = 5120;      // keys in the CTA-wide append region (>= one replay step of kInvThreads * 4 rows)
+static_assert(kInvAppend >= kInvThreads * 4, "a replay step must fit the append region");
 constexpr int kTokTile = 512;         // query tokens staged per pass over a block
 
 struct BlockLists {
-    uint32_t *blk_ptr;     // [n_blocks, V + 1]
+    uint2 *blk_rng;        // [V, n_blocks]: (start, end) of the token's list inside the block's posting region
     uint64_t *blk_base;    // [n_blocks + 1]
     uint16_t *post_row;    // [nnz]
     void *post_val;        // [nnz] in store_dtype, or nullptr
@@ -63,8 +72,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
 
 // ------------------------------------------------------------------------------------------- build
 // One CTA per row block, one thread per row (rows are runs of 16-byte chunks in the WS stream, row_chunk[] = first
-// chunk of each row).  Count pass: per-token histogram in shared memory -> exclusive offsets blk_ptr[b][*];
-// fill pass: the same walk with the offsets as cursors.
+// chunk of each row).  Count pass: per-token histogram in shared memory -> exclusive offsets -> blk_rng[*][b];
+// fill pass: the same walk with the list starts as cursors.
 template <bool FILL>
 __global__ void __launch_bounds__(kInvBuildThreads, 1) inv_build_kernel(const WsView idx, const BlockLists bl, int *err) {
     extern __shared__ uint32_t s_cnt[];  // V counters / cursors
@@ -72,8 +81,8 @@ __global__ void __launch_bounds__(kInvBuildThreads, 1) inv_build_kernel(const Ws
     __shared__ unsigned long long s_total;
     const int V = bl.V, tid = threadIdx.x, b = blockIdx.x;
     if (tid == 0) s_total = 0;
-    uint32_t *my_ptr = bl.blk_ptr + (size_t)b * (V + 1);
-    for (int i = tid; i < V; i += kInvBuildThreads) s_cnt[i] = FILL ? my_ptr[i] : 0u;
+    const size_t nb = (size_t)bl.n_blocks;
+    for (int i = tid; i < V; i += kInvBuildThreads) s_cnt[i] = FILL ? bl.blk_rng[(size_t)i * nb + b].x : 0u;
     __syncthreads();
     const int64_t r0 = (int64_t)b * bl.rows_per_block;
     const int64_t r1 = min(idx.n_rows, r0 + bl.rows_per_block);
@@ -112,13 +121,12 @@ __global__ void __launch_bounds__(kInvBuildThreads, 1) inv_build_kernel(const Ws
         uint32_t run = block_exclusive_scan<kInvBuildThreads>((uint32_t)sum, s_warp, total);
         for (int i = lo; i < hi; ++i) {
             const uint32_t c = s_cnt[i];
-            my_ptr[i] = run;
+            bl.blk_rng[(size_t)i * nb + b] = make_uint2(run, run + c);
             run += c;
             if (c) atomicAdd((unsigned long long *)&bl.tok_total[i], (unsigned long long)c);
         }
         if (tid == 0) {
             if (s_total >= (1ull << 32)) atomicExch(err, 1);
-            my_ptr[V] = total;
             bl.blk_base[b] = s_total;  // sizes now, exclusive prefix after the host-side scan
         }
     }
@@ -130,11 +138,16 @@ __global__ void __launch_bounds__(kInvBuildThreads, 1) inv_build_kernel(const Ws
 static void block_geometry(const vs_index *idx, int *rows_per_block, int *n_blocks, int *blocks_per_cta) {
     const int64_t N = idx->n_rows > 0 ? idx->n_rows : 1;
     int64_t R = N < kBlockRowsMax ? N : kBlockRowsMax;
+    int64_t nb = (N + R - 1) / R;
+    int64_t bpc = (nb + idx->n_ctas - 1) / idx->n_ctas;
+    if (nb > idx->n_ctas) {   // a large index: equal blocks, the same number for every CTA
+        R = (N + idx->n_ctas * bpc - 1) / (idx->n_ctas * bpc);
+    }
     R = (R + 3) / 4 * 4;
-    const int64_t nb = (N + R - 1) / R;
+    nb = (N + R - 1) / R;
     *rows_per_block = (int)R;
     *n_blocks = (int)nb;
-    *blocks_per_cta = (int)((nb + idx->n_ctas - 1) / idx->n_ctas);
+    *blocks_per_cta = (int)bpc;
 }
 
 int build_inverted(vs_index *idx, cudaStream_t st) {
@@ -152,14 +165,14 @@ int build_inverted(vs_index *idx, cudaStream_t st) {
     VS_CUDA(cudaMemsetAsync(d_err, 0, 4, st));
     VS_CUDA(cudaMalloc(&idx->post_ptr, (size_t)(V + 1) * 8));
     VS_CUDA(cudaMemsetAsync(idx->post_ptr, 0, (size_t)(V + 1) * 8, st));
-    VS_CUDA(cudaMalloc(&idx->blk_ptr, (size_t)nb * (V + 1) * 4));
+    VS_CUDA(cudaMalloc(&idx->blk_ptr, (size_t)nb * V * sizeof(uint2)));
     VS_CUDA(cudaMalloc(&idx->blk_base, (size_t)(nb + 1) * 8));
     VS_CUDA(cudaMemsetAsync(idx->blk_base, 0, (size_t)(nb + 1) * 8, st));
     VS_CUDA(cudaMalloc(&idx->post_row, idx->nnz ? (size_t)idx->nnz * 2 : 4));
     const size_t vbytes = idx->kind == 1 ? (idx->store_dtype == VS_F32 ? 4 : 2) : 0;
     if (vbytes) VS_CUDA(cudaMalloc(&idx->post_val, idx->nnz ? (size_t)idx->nnz * vbytes : 4));
     BlockLists bl;
-    bl.blk_ptr = idx->blk_ptr; bl.blk_base = idx->blk_base; bl.post_row = idx->post_row; bl.post_val = idx->post_val;
+    bl.blk_rng = (uint2 *)idx->blk_ptr; bl.blk_base = idx->blk_base; bl.post_row = idx->post_row; bl.post_val = idx->post_val;
     bl.tok_total = idx->post_ptr; bl.rows_per_block = idx->blk_rows; bl.n_blocks = nb; bl.V = V;
 
     VS_CUDA(cudaFuncSetAttribute(inv_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -179,7 +192,7 @@ int build_inverted(vs_index *idx, cudaStream_t st) {
     cleanup();
     VS_CUDA(e);
     VS_REQUIRE(h_err == 0, VS_ERR_UNSUPPORTED, "a row block holds 2^32 or more postings");
-    idx->inv_bytes = (int64_t)((size_t)idx->nnz * (2 + vbytes) + (size_t)nb * (V + 1) * 4 + (size_t)(V + 1) * 8);
+    idx->inv_bytes = (int64_t)((size_t)idx->nnz * (2 + vbytes) + (size_t)nb * V * 8 + (size_t)(V + 1) * 8);
     idx->device_bytes += idx->inv_bytes;
     idx->inv_built = true;
     return VS_OK;
@@ -339,17 +352,35 @@ __global__ void __launch_bounds__(256) inv_decide_kernel(const QueryLists L, int
 // ------------------------------------------------------------------------------------------- search
 struct InvSearchParams {
     QueryLists L;
-    const uint32_t *blk_ptr;
+    const uint2 *blk_rng;        // [V, n_blocks]
     const uint64_t *blk_base;
     const uint16_t *post_row;
     const void *post_val;
     int val_kind;        // 0 none (binary), 1 f32, 2 f16, 3 bf16
     int V, rows_per_block, n_blocks, blocks_per_cta;
     int64_t n_rows;
-    uint64_t *cand;      // [B, gridDim.x, cand_stride]: k keys per list
-    int k, score_round, cand_stride;
-    int flags;           // experiment switches (VSEARCH_B200_K3_FLAGS): 1 = re-select after the first block, 2 = L2 prefetch
+    uint64_t *cand;      // [B, gridDim.x, cand_stride]: up to kout keys per list, zero padded
+    int k, kout, score_round, cand_stride;
+    int flags;           // experiment switches (VSEARCH_B200_K3_FLAGS): 2 = L2 prefetch of the next block's lists
     const int *use_inv;  // device flag written by inv_decide_kernel: 0 = the scan serves this chunk, this kernel exits
+    unsigned long long *prof;   // diagnostic (vs_debug_scan_profile): per (query, CTA) nanoseconds spent per phase, or nullptr
+};
+// phases: 0 setup, 1 zero, 2 accumulate, 3 first-block histogram, 4 block select, 5 refresh / compaction, 6 final write, 7 total
+struct InvProf {
+    unsigned long long t, acc[8];
+    bool on;
+    __device__ __forceinline__ static unsigned long long now() {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    }
+    __device__ __forceinline__ void start(bool enabled) {
+        on = enabled;
+        if (on) { for (int i = 0; i < 8; ++i) acc[i] = 0; t = now(); acc[7] = t; }
+    }
+    __device__ __forceinline__ void lap(int phase) {
+        if (on) { const unsigned long long n = now(); acc[phase] += n - t; t = n; }
+    }
 };
 
 __device__ __forceinline__ float posting_value(const void *vals, int kind, uint64_t pos) {
@@ -365,6 +396,14 @@ __device__ __forceinline__ uint32_t atom_shared_add(uint32_t *p, uint32_t v) {  
     uint32_t old;
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
     return old;
+}
+__device__ __forceinline__ uint32_t ordered_bits(float s) {   // high half of make_key(): larger = better, -0 folded into +0
+    const uint32_t b = __float_as_uint(s + 0.0f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ void hist_count_plain(uint32_t *coarse, uint32_t *fine, uint32_t ob, uint32_t n = 1u) {
+    atomicAdd(&fine[ob >> (32 - kHistFineBits)], n);
+    atomicAdd(&coarse[ob >> 25], n);
 }
 
 constexpr uint32_t kLongList = 1024;   // postings; longer (block, token) lists are shared by all warps of the CTA
@@ -396,13 +435,18 @@ __device__ __forceinline__ void accumulate_slice(float *acc, const uint16_t *row
 __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSearchParams p) {
     constexpr int NT = kInvThreads, NW = kInvWarps;
     extern __shared__ __align__(128) uint8_t ssmem[];
-    uint64_t *cbuf = reinterpret_cast<uint64_t *>(ssmem);                      // kCapMax keys
-    uint32_t *hist = reinterpret_cast<uint32_t *>(cbuf + kCapMax);             // 256
-    uint32_t *s_tok = hist + 256;                                              // kTokTile each
+    // the score histogram and the exact fallback's shared top-k set share their memory: a query that has to fall back
+    // to exact CTA-wide selections (masses of equal scores, adversarial row order) stops using the histogram
+    uint32_t *fine = reinterpret_cast<uint32_t *>(ssmem);                       // kHistFine counters (32 KB) ...
+    uint64_t *shset = reinterpret_cast<uint64_t *>(ssmem);                      // ... or kSharedKeys keys (16 KB)
+    uint32_t *coarse = fine + kHistFine;                                        // kHistCoarse
+    uint32_t *hist = coarse + kHistCoarse;                                      // 256: radix-select scratch of the fallback
+    uint64_t *app = reinterpret_cast<uint64_t *>(hist + 256);                   // kInvAppend keys: CTA-wide append region
+    uint32_t *s_tok = reinterpret_cast<uint32_t *>(app + kInvAppend);           // kTokTile each
     float *s_w = reinterpret_cast<float *>(s_tok + kTokTile);
     uint32_t *s_beg = reinterpret_cast<uint32_t *>(s_w + kTokTile);
     uint32_t *s_len = s_beg + kTokTile;
-    float *acc = reinterpret_cast<float *>(s_len + kTokTile);                  // rows_per_block
+    float *acc = reinterpret_cast<float *>(s_len + kTokTile);                   // rows_per_block
     __shared__ CtaState st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (*p.use_inv == 0) return;
@@ -414,45 +458,86 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     const int blk0 = blockIdx.x * p.blocks_per_cta, blk1 = min(p.n_blocks, blk0 + p.blocks_per_cta);
     const bool cached = cnt <= kTokTile;   // the whole token list stays in shared memory across blocks
     const int vbytes = p.val_kind == 0 ? 0 : (p.val_kind == 1 ? 4 : 2);
+    const size_t nb = (size_t)p.n_blocks;
+    InvProf prof;
+    prof.start(p.prof != nullptr && tid == 0);
     if (tid == 0) cta_state_reset(&st);
+    for (int i = tid; i < kHistFine + kHistCoarse; i += NT) fine[i] = 0u;   // coarse follows fine
     if (cached && tid < cnt) { s_tok[tid] = tok[tid]; s_w[tid] = w[tid]; }
     __syncthreads();
     // list bounds of token `tid` in the NEXT block to score: loaded one block ahead, and the lists themselves are
     // pulled into L2 while the previous block is being selected
-    uint32_t np0 = 0, np1 = 0;
+    uint2 nrng = make_uint2(0u, 0u);
     uint64_t nbase = 0;
-    if (cached && blk0 < blk1 && tid < cnt) {
-        const uint32_t *bp = p.blk_ptr + (size_t)blk0 * (p.V + 1) + s_tok[tid];
-        np0 = bp[0]; np1 = bp[1];
-    }
-    bool sampled = false;
+    if (cached && blk0 < blk1 && tid < cnt) nrng = p.blk_rng[(size_t)s_tok[tid] * nb + blk0];
     float4 *acc4 = reinterpret_cast<float4 *>(acc);
-    uint64_t *app = cbuf + kSharedKeys;    // CTA-wide append region of the top-k machinery (topk.cuh)
+    float tau_s = -INFINITY;               // float pre-filter: lower bound of the histogram's k-th bucket
+    bool booted = false;                   // the CTA's first block has set the pre-filter
+    bool exact = false;                    // exact fallback engaged: histogram memory now holds the shared top-k set
+
+    // one pass over rows [r_begin, rows_b) of the block's accumulator: rows at or above the pre-filter (and above the exact
+    // threshold, if any) are counted in the histogram (rows >= count_from only) and appended.  STEP = rows per thread.
+    auto select_rows = [&](const int rb, const int rows_b, const int64_t row0, const uint64_t tau, const int count_from) {
+        const int r = rb + tid * 4;
+        if (r < rows_b) {
+            const float4 v = acc4[r >> 2];
+            const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            if (round_score(mx, p.score_round) >= tau_s) {   // rounding is monotonic
+                const float sc[4] = {v.x, v.y, v.z, v.w};
+                uint64_t key[4];
+                uint32_t n = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float se = round_score(sc[e], p.score_round);
+                    key[e] = 0ull;
+                    if (r + e < rows_b && se >= tau_s) {
+                        const uint64_t ke = make_key(se, (uint32_t)(row0 + r + e));
+                        if (ke > tau) {
+                            key[e] = ke; ++n;
+                            if (!exact && r + e >= count_from) hist_count_plain(coarse, fine, (uint32_t)(ke >> 32));
+                        }
+                    }
+                }
+                if (n) {
+                    uint32_t slot = atom_shared_add(&st.n_app, n);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (key[e] != 0ull) { if (slot < (uint32_t)kInvAppend) app[slot] = key[e]; ++slot; }
+                }
+            }
+        }
+    };
+    // raise the pre-filter to the histogram's k-th bucket (all warps compute the same bound)
+    auto refresh = [&]() -> uint32_t {
+        const uint32_t ob = hist_threshold(coarse, fine, p.k);
+        if (ob) tau_s = fmaxf(tau_s, key_score((uint64_t)ob << 32));
+        return ob;
+    };
 
     for (int b = blk0; b < blk1; ++b) {
         const int64_t row0 = (int64_t)b * R;
         const int rows_b = (int)min((int64_t)R, p.n_rows - row0);
         const uint64_t base = p.blk_base[b];
+        prof.lap(0);
         for (int i = tid; i < (R >> 2); i += NT) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         // ---- accumulate: tiles of <= kTokTile query tokens
         for (int t0 = 0; t0 < cnt; t0 += kTokTile) {
             const int tn = min(kTokTile, cnt - t0);
-            uint32_t p0 = np0, p1 = np1;
+            uint2 rng = nrng;
             if (!cached) {
                 __syncthreads();  // previous tile fully consumed
                 if (tid < tn) {
                     const uint32_t t = tok[t0 + tid];
                     s_tok[tid] = t; s_w[tid] = w[t0 + tid];
-                    const uint32_t *bp = p.blk_ptr + (size_t)b * (p.V + 1) + t;
-                    p0 = bp[0]; p1 = bp[1];
+                    rng = p.blk_rng[(size_t)t * nb + b];
                 }
             } else if (b + 1 < blk1 && tid < cnt) {  // in flight under this block's accumulate
-                const uint32_t *bp = p.blk_ptr + (size_t)(b + 1) * (p.V + 1) + s_tok[tid];
-                np0 = bp[0]; np1 = bp[1];
+                nrng = p.blk_rng[(size_t)s_tok[tid] * nb + b + 1];
                 nbase = p.blk_base[b + 1];
             }
-            if (tid < tn) { s_beg[tid] = p0; s_len[tid] = p1 - p0; }
+            if (tid < tn) { s_beg[tid] = rng.x; s_len[tid] = rng.y - rng.x; }
             __syncthreads();  // also orders the zeroing above before the first atomic
+            prof.lap(1);
             // short lists: one warp per list piece, round robin; few tokens -> lists are cut in 2 or 4 pieces so that
             // every warp gets about the same number of postings
             const int psh = tn >= 2 * NW ? 0 : (tn >= NW ? 1 : 2);   // 1, 2 or 4 pieces per list
@@ -477,9 +562,10 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
             }
         }
         __syncthreads();
+        prof.lap(2);
         if ((p.flags & 2) && cached && b + 1 < blk1 && tid < cnt) {  // next block's lists -> L2 while this block is selected
-            const uint64_t npos = nbase + np0;
-            const uint32_t nlen = min(np1 - np0, 2048u);
+            const uint64_t npos = nbase + nrng.x;
+            const uint32_t nlen = min(nrng.y - nrng.x, 2048u);
             const uint8_t *r8 = reinterpret_cast<const uint8_t *>(p.post_row + npos);
             for (uint32_t o = 0; o < nlen * 2u; o += 128u) prefetch_l2(r8 + o);
             if (vbytes) {
@@ -487,79 +573,125 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                 for (uint32_t o = 0; o < nlen * (uint32_t)vbytes; o += 128u) prefetch_l2(v8 + o);
             }
         }
-        // ---- select: the block's scores go through the fused top-k
-        int i0 = 0;
-        if (!sampled) {  // phase A: the CTA's first kCapMax rows set the threshold
-            for (int i = tid; i < (kCapMax >> 2); i += NT) {
-                const int r = i * 4;
-                const float4 v = r < rows_b ? acc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float s[4] = {v.x, v.y, v.z, v.w};
+        // ---- first block of the CTA: its first NT*4 rows are counted whole (rows at score 0 -- untouched rows, most of
+        // a sparse query's -- through one warp reduction instead of per-lane atomics) and give the first pre-filter
+        int count_from = 0;
+        if (!booted) {
+            const int r = tid * 4;
+            uint32_t zeros = 0;
+            if (r < rows_b) {
+                const float4 v = acc4[r >> 2];
+                const float sc[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    cbuf[r + e] = (r + e < rows_b) ? make_key(round_score(s[e], p.score_round), (uint32_t)(row0 + r + e)) : 0ull;
+                    if (r + e < rows_b) {
+                        const float se = round_score(sc[e], p.score_round);
+                        if (se == 0.0f) ++zeros; else hist_count_plain(coarse, fine, ordered_bits(se));
+                    }
             }
+            zeros = __reduce_add_sync(0xffffffffu, zeros);
+            if (lane == 0 && zeros) hist_count_plain(coarse, fine, ordered_bits(0.0f), zeros);
             __syncthreads();
-            cta_sample_select<NT, true>(cbuf, kCapMax, p.k, hist, &st, max(2 * p.k, 512) < kSharedKeys ? max(2 * p.k, 512) : kSharedKeys);
-            i0 = kCapMax;
+            refresh();
+            count_from = NT * 4;
+            prof.lap(3);
         }
-        // phase B.  Optimistic: the whole block in one go, survivors appended through a CTA-wide counter; when the
-        // append region overflows (adversarial score order) the block is replayed in steps of NT*4 rows with a
-        // re-selection whenever the next step might not fit.
+        // ---- select.  Optimistic: the whole block in one go, survivors appended through a CTA-wide counter; when the
+        // append region overflows (masses of equal scores, adversarial order) the query switches to the exact machinery:
+        // the block is replayed in steps of NT*4 rows with a CTA-wide re-selection whenever the next step might not fit.
         const uint32_t app0 = *(volatile uint32_t *)&st.n_app;
-        bool stepwise = false;
         for (;;) {
-            float tau_s = gate_tau_score(gate_load(&st));
-            uint64_t tau = *(volatile uint64_t *)&st.tau;
-            for (int rb = i0; rb < rows_b; rb += NT * 4) {
-                if (stepwise) {
+            uint64_t tau = *(volatile uint64_t *)&st.tau;   // exact k-th key of the last re-selection (0: none yet)
+            int it = 0;
+            for (int rb = 0; rb < rows_b; rb += NT * 4, ++it) {
+                if (exact) {
                     // the thread that appended last reads the final count, so the OR is exact
-                    if (__syncthreads_or(*(volatile uint32_t *)&st.n_app + NT * 4 > (uint32_t)kAppendCap)) {
-                        cta_join_flat<NT>(cbuf, p.k, hist, &st);
-                        tau_s = gate_tau_score(gate_load(&st));
+                    if (__syncthreads_or(*(volatile uint32_t *)&st.n_app + NT * 4 > (uint32_t)kInvAppend)) {
+                        cta_join_flat<NT, kInvAppend>(shset, app, p.k, hist, &st);
+                        tau_s = fmaxf(tau_s, gate_tau_score(gate_load(&st)));
                         tau = *(volatile uint64_t *)&st.tau;
                     }
+                } else if (!booted && (it == 1 || it == 3 || it == 7)) {
+                    __syncthreads();   // the pre-filter of the first block tightens as its rows are counted
+                    refresh();
                 }
-                const int r = rb + tid * 4;
-                if (r < rows_b) {
-                    const float4 v = acc4[r >> 2];
-                    const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-                    if (round_score(mx, p.score_round) >= tau_s) {   // rounding is monotonic
-                        const float s[4] = {v.x, v.y, v.z, v.w};
-                        uint64_t key[4];
-                        uint32_t n = 0;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float se = round_score(s[e], p.score_round);
-                            key[e] = 0ull;
-                            if (r + e < rows_b && se >= tau_s) {
-                                const uint64_t ke = make_key(se, (uint32_t)(row0 + r + e));
-                                if (ke > tau) { key[e] = ke; ++n; }
-                            }
-                        }
-                        if (n) {
-                            uint32_t slot = atom_shared_add(&st.n_app, n);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (key[e] != 0ull) { if (slot < (uint32_t)kAppendCap) app[slot] = key[e]; ++slot; }
-                        }
-                    }
-                }
+                select_rows(rb, rows_b, row0, tau, count_from);
             }
             __syncthreads();
-            if (stepwise || *(volatile uint32_t *)&st.n_app <= (uint32_t)kAppendCap) break;
+            if (exact || *(volatile uint32_t *)&st.n_app <= (uint32_t)kInvAppend) break;
             __syncthreads();
-            if (tid == 0) st.n_app = app0;   // drop this block's partial appends and replay it safely
-            stepwise = true;
+            if (tid == 0) { st.n_app = app0 <= (uint32_t)kInvAppend ? app0 : 0u; st.cnt = 0; }
+            exact = true;   // from here on the histogram memory holds the shared top-k set
             __syncthreads();
         }
-        // tighten the threshold after the CTA's first block (the sample saw kCapMax rows, the block has R), and keep
-        // room for the next block's optimistic pass
-        if (b + 1 < blk1 && ((!sampled && (p.flags & 1)) || *(volatile uint32_t *)&st.n_app > (uint32_t)(kAppendCap / 4)))
-            cta_join_flat<NT>(cbuf, p.k, hist, &st);
-        sampled = true;
+        booted = true;
+        prof.lap(4);
+        // ---- raise the pre-filter for the next block; when the region is half full, drop what fell below it
+        if (!exact && b + 1 < blk1) {
+            const uint32_t ob = refresh();
+            const uint32_t n_app = *(volatile uint32_t *)&st.n_app;
+            if (n_app > (uint32_t)(kInvAppend / 2)) {
+                constexpr int PER = (kInvAppend + NT - 1) / NT;
+                uint64_t keep[PER];
+                const uint64_t tmin = (uint64_t)ob << 32;
+#pragma unroll
+                for (int j = 0; j < PER; ++j) { const int i = tid + j * NT; keep[j] = (i < (int)n_app) ? app[i] : 0ull; }
+                __syncthreads();
+                if (tid == 0) st.n_app = 0;
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < PER; ++j)
+                    if (keep[j] != 0ull && keep[j] >= tmin) app[atom_shared_add(&st.n_app, 1u)] = keep[j];
+                __syncthreads();
+                if (*(volatile uint32_t *)&st.n_app > (uint32_t)(kInvAppend / 2)) {   // a bucket full of equal scores: go exact
+                    if (tid == 0) st.cnt = 0;
+                    exact = true;
+                    __syncthreads();
+                    cta_join_flat<NT, kInvAppend>(shset, app, p.k, hist, &st);
+                    tau_s = fmaxf(tau_s, gate_tau_score(gate_load(&st)));
+                }
+            }
+        } else if (exact && b + 1 < blk1 && *(volatile uint32_t *)&st.n_app > (uint32_t)(kInvAppend / 4)) {
+            cta_join_flat<NT, kInvAppend>(shset, app, p.k, hist, &st);
+            tau_s = fmaxf(tau_s, gate_tau_score(gate_load(&st)));
+        }
         __syncthreads();
+        prof.lap(5);
     }
-    cta_write_topk_flat<NT>(cbuf, p.k, hist, &st, p.cand + ((size_t)q * gridDim.x + blockIdx.x) * (size_t)p.cand_stride);
+    // ---- end of query: everything at or above the final histogram bound goes to the merge kernel (k .. kout keys);
+    // more than kout (a bucket full of equal scores), or a query in exact mode -> the exact CTA-wide select
+    {
+        uint64_t *out = p.cand + ((size_t)q * gridDim.x + blockIdx.x) * (size_t)p.cand_stride;
+        if (tid == 0) st.scratch = 0;
+        __syncthreads();
+        bool use_exact = exact;
+        if (!exact) {
+            const uint64_t tmin = (uint64_t)hist_threshold(coarse, fine, p.k) << 32;
+            const int n_app = (int)min(*(volatile uint32_t *)&st.n_app, (uint32_t)kInvAppend);
+            for (int i = tid; i < n_app; i += NT) {
+                const uint64_t x = app[i];
+                if (x != 0ull && x >= tmin) { const uint32_t o = atomicAdd(&st.scratch, 1u); if (o < (uint32_t)p.kout) out[o] = x; }
+            }
+            __syncthreads();
+            const uint32_t total = *(volatile uint32_t *)&st.scratch;
+            if (total > (uint32_t)p.kout) {   // uniform: too many ties for the list -> exact select of what was kept
+                if (tid == 0) st.cnt = 0;
+                use_exact = true;
+                __syncthreads();
+            } else {
+                for (int i = (int)total + tid; i < p.kout; i += NT) out[i] = 0ull;
+            }
+        }
+        if (use_exact) {
+            cta_write_topk_flat<NT, kInvAppend>(shset, app, p.k, hist, &st, out);
+            for (int i = p.k + tid; i < p.kout; i += NT) out[i] = 0ull;
+        }
+    }
+    if (prof.on) {
+        prof.lap(6);
+        prof.acc[7] = prof.t - prof.acc[7];
+        for (int i = 0; i < 8; ++i) p.prof[((size_t)q * gridDim.x + blockIdx.x) * 8 + i] = prof.acc[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -609,17 +741,20 @@ int launch_inverted(vs_index *idx, int64_t Bc, int k, int cand_stride, int score
                     const int *d_flag, cudaStream_t st) {
     uint8_t *end;
     QueryLists L = carve_lists((uint8_t *)d_ws, Bc, &end);
-    const size_t smem = (size_t)kCapMax * 8 + 256 * 4 + (size_t)kTokTile * 4 * 4 + (size_t)idx->blk_rows * 4;
+    static_assert(kHistFine * 4 >= kSharedKeys * 8, "the exact fallback's top-k set lives in the histogram's memory");
+    const size_t smem = (size_t)(kHistFine + kHistCoarse + 256) * 4 + (size_t)kInvAppend * 8 + (size_t)kTokTile * 4 * 4 +
+                        (size_t)idx->blk_rows * 4;
     VS_REQUIRE(smem <= 227 * 1024, VS_ERR_UNSUPPORTED, "inverted-list search needs %zu bytes of shared memory", smem);
     VS_CUDA(cudaFuncSetAttribute(inv_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     InvSearchParams p;
-    p.L = L; p.blk_ptr = idx->blk_ptr; p.blk_base = idx->blk_base; p.post_row = idx->post_row; p.post_val = idx->post_val;
+    p.L = L; p.blk_rng = (const uint2 *)idx->blk_ptr; p.blk_base = idx->blk_base; p.post_row = idx->post_row; p.post_val = idx->post_val;
     p.val_kind = idx->kind == 1 ? (idx->store_dtype == VS_F32 ? 1 : (idx->store_dtype == VS_F16 ? 2 : 3)) : 0;
     p.V = (int)idx->n_cols; p.rows_per_block = idx->blk_rows; p.n_blocks = idx->n_blocks; p.blocks_per_cta = idx->blocks_per_cta;
-    p.n_rows = idx->n_rows; p.cand = d_cand; p.k = k; p.score_round = score_round; p.cand_stride = cand_stride;
+    p.n_rows = idx->n_rows; p.cand = d_cand; p.k = k; p.kout = cand_stride; p.score_round = score_round; p.cand_stride = cand_stride;
     static const int k3_flags = getenv("VSEARCH_B200_K3_FLAGS") ? atoi(getenv("VSEARCH_B200_K3_FLAGS")) : 3;
     p.flags = k3_flags;
     p.use_inv = d_flag;
+    p.prof = idx->scan_prof;
     inv_search_kernel<<<dim3(idx->n_ctas, (unsigned)Bc), kInvThreads, smem, st>>>(p);
     VS_CUDA(cudaGetLastError());
     return VS_OK;

@@ -15,6 +15,7 @@
 
 #include <new>
 #include <string>
+#include <memory>
 #include <vector>
 
 #include "../../include/vsearch_b200.h"
@@ -227,14 +228,20 @@ int npz_open_impl(const char *path, vs_npz **out) {
                     "%s: bad ZIP64 end-of-central-directory record", path);
         n_entries = rd64(r + 32); cd_size = rd64(r + 40); cd_off = rd64(r + 48);
     }
+    // sizes come from the file: bound them by the file before they size a buffer or an index
+    NPZ_REQUIRE(cd_off <= fsize && cd_size <= fsize - cd_off, VS_ERR_INVALID, "%s: central directory lies outside the file", path);
+    NPZ_REQUIRE(n_entries <= cd_size / 46, VS_ERR_INVALID, "%s: central directory too small for its entry count", path);
     std::vector<uint8_t> cd((size_t)cd_size);
     NPZ_REQUIRE(fseeko(fh.f, (off_t)cd_off, SEEK_SET) == 0 && fread(cd.data(), 1, (size_t)cd_size, fh.f) == cd_size, VS_ERR_INVALID,
                 "%s: cannot read the central directory", path);
-    vs_npz *z = new vs_npz;
+    std::unique_ptr<vs_npz> z(new vs_npz);
     z->path = path;
     size_t p = 0;
     for (uint64_t i = 0; i < n_entries; ++i) {
-        if (p + 46 > cd.size() || rd32(&cd[p]) != 0x02014b50u) { delete z; NPZ_REQUIRE(false, VS_ERR_INVALID, "%s: corrupt central directory", path); }
+        NPZ_REQUIRE(p + 46 <= cd.size() && rd32(&cd[p]) == 0x02014b50u, VS_ERR_INVALID, "%s: corrupt central directory", path);
+        // name, extra field and comment lengths are file data too: the whole entry must lie inside the directory
+        NPZ_REQUIRE(p + 46 + (size_t)rd16(&cd[p + 28]) + rd16(&cd[p + 30]) + rd16(&cd[p + 32]) <= cd.size(), VS_ERR_INVALID,
+                    "%s: central directory entry %llu runs past the directory", path, (unsigned long long)i);
         NpzMember m;
         m.method = rd16(&cd[p + 10]);
         m.crc = rd32(&cd[p + 16]);
@@ -246,6 +253,7 @@ int npz_open_impl(const char *path, vs_npz **out) {
         const size_t xend = x + xl;
         while (x + 4 <= xend) {   // ZIP64 extended information: only the fields that overflowed, in this order
             const uint16_t id = rd16(&cd[x]), sz = rd16(&cd[x + 2]);
+            if (x + 4 + (size_t)sz > xend) break;   // a field that claims more than the extra block holds
             if (id == 0x0001) {
                 size_t f = x + 4;
                 if (m.raw_size == 0xffffffffu && f + 8 <= x + 4 + sz) { m.raw_size = rd64(&cd[f]); f += 8; }
@@ -259,7 +267,7 @@ int npz_open_impl(const char *path, vs_npz **out) {
         z->members.push_back(m);
         p += 46 + (size_t)nl + xl + cl;
     }
-    *out = z;
+    *out = z.release();
     return VS_OK;
 }
 

@@ -389,8 +389,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
 #undef VS_ADVANCE
         {
             // ---- exact top-k of this CTA's rows, written unsorted (merge.cu sorts)
-            cta_write_topk<kScanThreads, kScanWarps>(L.cbuf, n_keys, p.k, L.hist, &st,
-                                                     p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.k);
+            uint64_t *out = p.cand + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)p.kout;
+            cta_write_topk<kScanThreads, kScanWarps>(L.cbuf, n_keys, p.k, L.hist, &st, out);
+            for (int i = p.k + tid; i < p.kout; i += kScanThreads) out[i] = 0ull;   // lists are kout long for every kernel family
         }
         __syncthreads();  // everyone is done with qs / cbuf before the next pass overwrites them
     }
@@ -670,10 +671,10 @@ size_t scan_smem_bytes(int vpad, int cap) {
 static size_t scan_bin_smem_bytes(int vpad) {
     return (size_t)vpad * 4 + (size_t)kCapMax * 8 + 256 * 4 + (size_t)(kHistFine + kHistCoarse) * 4;
 }
-// Length of the per-(query, CTA) candidate lists the scan writes.  The binary kernel hands over every key at or above
-// its final histogram threshold -- between k and, for smooth score distributions, about 2k of them -- instead of
-// paying a CTA-wide exact select per pass; the valued kernels write exactly k.
-int scan_kout(const vs_index *idx, int k) { return idx->kind == 2 ? 2 * k + 64 : k; }
+// Length of the per-(query, CTA) candidate lists.  The binary scan and the inverted-list kernel hand over every key at
+// or above their final histogram threshold -- between k and, for smooth score distributions, about 2k of them --
+// instead of paying a CTA-wide exact select per pass; the valued scan kernels write exactly k and pad.
+int scan_kout(const vs_index *idx, int k) { (void)idx; return 2 * k + 64; }
 
 int scan_cap_for_k(int k) { (void)k; return kCapMax; }
 

@@ -351,17 +351,15 @@ __device__ __forceinline__ void cta_write_topk(uint64_t *cbuf, int n_priv, int k
 }
 
 // ---- K3 (inverted.cu): one CTA-WIDE append region cbuf[kSharedKeys, kCapMax) filled through st->n_app by any thread
-// (the CTA runs in lockstep phases there, so no per-warp regions and no polling are needed).
-constexpr int kAppendCap = kCapMax - kSharedKeys;
+// (the CTA runs in lockstep phases there, so no per-warp regions and no polling are needed).  kAppendCap = its size.
 
 // Fold the append region into the shared set, keep the k best, raise tau, empty the region.  Whole CTA.
-template <int NT>
-__device__ __noinline__ void cta_join_flat(uint64_t *cbuf, int k, uint32_t *hist, CtaState *st) {
+template <int NT, int kAppendCap>
+__device__ __noinline__ void cta_join_flat(uint64_t *cbuf, uint64_t *app, int k, uint32_t *hist, CtaState *st) {
     const int tid = threadIdx.x;
     __syncthreads();
     const int n_sh = (int)st->cnt;
     const int n_app = min((int)st->n_app, kAppendCap);
-    uint64_t *app = cbuf + kSharedKeys;
     uint64_t kth = 0;
     if (n_sh + n_app > k) kth = radix_kth_largest2<true, true>(cbuf, n_sh, tid, NT, app, n_app, tid, NT, k, hist, tid, NT);
     constexpr int SH_PER = (kSharedKeys + NT - 1) / NT;
@@ -385,13 +383,13 @@ __device__ __noinline__ void cta_join_flat(uint64_t *cbuf, int k, uint32_t *hist
 }
 
 // End of pass: exact top-k of the shared set plus the append region -> out[0..k) (unsorted, zero padded).  Whole CTA.
-template <int NT>
-__device__ __forceinline__ void cta_write_topk_flat(uint64_t *cbuf, int k, uint32_t *hist, CtaState *st, uint64_t *out) {
+template <int NT, int kAppendCap>
+__device__ __forceinline__ void cta_write_topk_flat(uint64_t *cbuf, const uint64_t *app, int k, uint32_t *hist, CtaState *st,
+                                                    uint64_t *out) {
     const int tid = threadIdx.x;
     __syncthreads();
     const int n_sh = (int)st->cnt;
     const int n_app = min((int)st->n_app, kAppendCap);
-    const uint64_t *app = cbuf + kSharedKeys;
     uint64_t kth = 0;
     if (n_sh + n_app > k) kth = radix_kth_largest2<true, true>(cbuf, n_sh, tid, NT, app, n_app, tid, NT, k, hist, tid, NT);
     __syncthreads();
