@@ -42,7 +42,8 @@ typedef enum {
 } vs_status;
 
 typedef enum {
-    VS_F32 = 0, VS_F16 = 1, VS_BF16 = 2, VS_I32 = 3, VS_I64 = 4, VS_U16 = 5, VS_U32 = 6, VS_NONE = 7
+    VS_F32 = 0, VS_F16 = 1, VS_BF16 = 2, VS_I32 = 3, VS_I64 = 4, VS_U16 = 5, VS_U32 = 6, VS_NONE = 7,
+    VS_F64 = 8   /* .npz members only (scipy's default value dtype): converted to f32 / f16 while loading */
 } vs_dtype;
 
 /* which kernel family serves vs_search on a sparse / binary index */
@@ -218,6 +219,22 @@ int vs_npz_member_info(vs_npz *z, const char *name, int *dtype, int *ndim, int64
  * Streaming: 2 MB of scratch per call, no inflated copy of the member. */
 int vs_npz_read(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t skip_elems, int64_t n_elems,
                 int64_t add_offset);
+
+/* Loader: row shards written by scipy.sparse.save_npz (reference SparseIndex.save, index.py:195-197) -> one device
+ * index, replacing SparseIndex.init_index (index.py:163-179: glob -> load_npz -> [:, shift:] -> vstack -> astype ->
+ * torch CSR -> .to(device)) without any host copy of the index.  `paths` are concatenated by rows in the order given
+ * (the caller sorts them lexicographically like upstream: index10 before index2).  Every (shard, member) pair is
+ * inflated by one of `threads` host threads (<= 0: all cores), narrowed on the fly (columns -> uint16 when the file's
+ * vocabulary fits, values -> float16 when value_dtype == VS_F16 -- upstream's fp16=True --, row pointers offset by the
+ * shards before) into pinned staging buffers and copied asynchronously to its place in the device CSR arrays.
+ *   shift            columns < shift are dropped and the rest renumbered (done by the index build on the GPU)
+ *   value_dtype      device value type of a valued index: VS_F32 | VS_F16 | VS_BF16
+ *   binary_if_ones   != 0: an all-ones `data` member gives the binary bag-of-token index (BoTIndex)
+ *   shard_rows       optional out, int64[n_paths]: rows of each file (global id offsets of row-sharded ranks)
+ * A rank of the row-sharded layout passes only ITS files (upstream writes one file per shard,
+ * examples/inference_sparse/README.md:86-107).  SYNC. */
+int vs_index_load_npz(int device, const char *const *paths, int n_paths, int shift, int value_dtype, int binary_if_ones,
+                      int threads, void *stream, vs_index **out, int64_t *shard_rows);
 
 /* Writer: a zip of deflated .npy members, byte-compatible with scipy.sparse.save_npz / numpy.savez_compressed
  * (reference SparseIndex.save, index.py:195-197), compressed by `threads` threads (independent 4 MB deflate blocks

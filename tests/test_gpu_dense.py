@@ -109,3 +109,17 @@ def test_dense_continuous_ids_and_scores_at_2e3(cuda_device):
     ref = ref_search.ref_scores(ref_search.quantize_like(q, torch.bfloat16), ref_search.quantize_like(x, torch.bfloat16))
     msg = ref_search.compare_results(ref_search.SearchResults(res.ids, res.scores.float()), ref, k, rtol=2e-3, exact=False)
     assert msg is None, msg
+
+
+def test_dense_fp32_vector_is_refused_not_narrowed(cuda_device):
+    """upstream's Index(fp16=False) keeps an fp32 matrix and does an fp32 GEMM (index.py:36-44); the tensor-core kernel
+    stores bf16 / fp16, so an fp32 vector is refused (no silent narrowing) until an fp32-accurate path exists."""
+    import vsearch_b200 as vs
+
+    idx = vs.Index(fp16=False)
+    idx.vector = torch.randn(100, 64)
+    with pytest.raises(NotImplementedError):
+        idx.move_to_device("cuda:0")
+    idx.vector = torch.randn(100, 64).to(torch.bfloat16)      # the explicit conversion works
+    idx.move_to_device("cuda:0")
+    assert idx.search(torch.randn(2, 64), 5).scores.dtype == torch.bfloat16

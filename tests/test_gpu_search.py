@@ -757,3 +757,45 @@ def test_sharded_rank_without_rows(cuda_device):
     idx.device = "cuda:0"
     res = vs.ShardedIndex(idx, 10, 10).search(sparse_queries(2, V, 8, seed=1), 3)
     assert tuple(res.ids.shape) == (2, 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shift", [0, 100])
+def test_loader_direct_to_device_matches_reference_loader(shift, tmp_path, cuda_device):
+    """SparseIndex(index_file, device='cuda'): the native loader (vs_index_load_npz: parallel inflate -> pinned staging ->
+    device CSR -> index build with the column shift on the GPU) against what the unmodified reference loader produced
+    from the same shard files (tests/golden/load_shift*.npz: sorted-glob order index10 < index2, `[:, shift:]`, row
+    concatenation; index.py:172-176), then float64 / int64 shard files and the fp16 default."""
+    import os
+
+    import scipy.sparse as sp
+
+    import vsearch_b200 as vs
+    from tests.util import GOLDEN
+
+    z = np.load(os.path.join(GOLDEN, f"load_shift{shift}.npz"))
+    idx = vs.SparseIndex(os.path.join(GOLDEN, "shards", "index*.npz"), None, fp16=False, device="cuda:0", shift=shift)
+    assert idx._engine is not None and idx._vector is None          # no host copy was made
+    assert sum(idx.shard_rows) == int(z["shape"][0])
+    v = idx.vector.cpu()                                             # exported from the engine on demand
+    assert tuple(v.shape) == tuple(z["shape"]) and v.values().dtype == torch.float32
+    assert np.array_equal(v.crow_indices().numpy(), z["crow"])
+    assert np.array_equal(v.col_indices().numpy(), z["col"])
+    assert np.array_equal(v.values().numpy(), z["val"])
+    X = ref_search.torch_csr(z["crow"], z["col"], z["val"], tuple(z["shape"]))
+    q = sparse_queries(3, int(z["shape"][1]), 40, seed=4)
+    assert ref_search.compare_results(idx.search(q, 5), ref_search.ref_scores(q, X), 5, rtol=1e-5, exact=False) is None
+    half = vs.SparseIndex(os.path.join(GOLDEN, "shards", "index1.npz"), device="cuda:0")    # fp16=True is upstream's default
+    assert half.vector.values().dtype == torch.float16 and half._engine.store_dtype == 1
+    # a shard as scipy writes it by default: float64 values, int64 indices after a vstack of large parts
+    m = sp.load_npz(os.path.join(GOLDEN, "shards", "index1.npz")).astype(np.float64)
+    m.indices, m.indptr = m.indices.astype(np.int64), m.indptr.astype(np.int64)
+    sp.save_npz(str(tmp_path / "f64.npz"), m)
+    wide = vs.SparseIndex(str(tmp_path / "f64.npz"), fp16=False, device="cuda:0")
+    assert np.array_equal(wide.vector.cpu().values().numpy(), m.data.astype(np.float32))
+    bot = vs.BoTIndex(str(tmp_path / "f64.npz"), fp16=False, device="cuda:0")                # values are not all 1: stays valued
+    assert bot._engine.kind == 1
+    m.data[:] = 1.0
+    sp.save_npz(str(tmp_path / "ones.npz"), m)
+    bot = vs.BoTIndex(str(tmp_path / "ones.npz"), device="cuda:0")
+    assert bot._engine.kind == 2                                                             # all ones: column ids only

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VSEARCH_B200_LIB") or os.path.join(_HERE, "lib", "libvsearch_b200.so")
 
 VS_OK, VS_ERR_INVALID, VS_ERR_UNSUPPORTED, VS_ERR_CUDA, VS_ERR_NOMEM = 0, 1, 2, 3, 4
-VS_F32, VS_F16, VS_BF16, VS_I32, VS_I64, VS_U16, VS_U32, VS_NONE = range(8)
+VS_F32, VS_F16, VS_BF16, VS_I32, VS_I64, VS_U16, VS_U32, VS_NONE, VS_F64 = range(9)
 VS_MODE_AUTO, VS_MODE_SCAN, VS_MODE_INVERTED = 0, 1, 2
 VS_MAX_K = 2048
 MODES = {"auto": VS_MODE_AUTO, "scan": VS_MODE_SCAN, "inverted": VS_MODE_INVERTED}
@@ -27,7 +27,7 @@ SYMBOLS = [
     "vs_scores", "vs_merge_keys", "vs_kernel_timer", "vs_index_last_mode",
     "vs_npz_open", "vs_npz_close", "vs_npz_member_info", "vs_npz_read", "vs_bot_from_tokens", "vs_score_rows", "vs_npz_write", "vs_sparsify_topk",
     "vs_debug_scan_profile", "vs_debug_gather_wavefronts", "vs_search_sparse", "vs_score_rows_workspace_bytes",
-    "vs_dense_to_csr",
+    "vs_dense_to_csr", "vs_index_load_npz",
 ]
 
 
@@ -81,6 +81,8 @@ def _load() -> ctypes.CDLL:
                                        c_void_p, c_void_p]
     lib.vs_sparsify_topk.argtypes = [c_int, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
     lib.vs_dense_to_csr.argtypes = [c_int, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.vs_index_load_npz.argtypes = [c_int, POINTER(c_char_p), c_int, c_int, c_int, c_int, c_int, c_void_p, POINTER(c_void_p),
+                                      POINTER(c_int64)]
     lib.vs_npz_write.argtypes = [c_char_p, c_void_p, c_int, c_int, c_int]
     lib.vs_npz_open.argtypes = [c_char_p, POINTER(c_void_p)]
     lib.vs_npz_close.argtypes = [c_void_p]

@@ -156,6 +156,42 @@ __global__ void __launch_bounds__(256) score_rows_kernel(const WsView idx, const
     if (lane == 0) out[pair] = round_score(s, score_round);
 }
 
+int create_csr_from_device(int device, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *d_crow, int crow_dtype,
+                           const void *d_col, int col_dtype, const void *d_val, int val_dtype, int store_dtype,
+                           int64_t col_shift, cudaStream_t st, vs_index **out) {
+    *out = nullptr;
+    VS_REQUIRE(n_rows >= 0 && n_cols >= 1 && nnz >= 0 && col_shift >= 0, VS_ERR_INVALID, "bad shape");
+    VS_REQUIRE(n_cols <= 32767, VS_ERR_UNSUPPORTED,
+               "n_cols=%lld does not fit the uint16 column format (15 bits + the row-end flag)", (long long)n_cols);
+    VS_REQUIRE(n_rows < 0xffffffffll, VS_ERR_UNSUPPORTED, "n_rows must be < 2^32 - 1 per shard");
+    const bool binary = (d_val == nullptr || val_dtype == VS_NONE);
+    if (!binary) {
+        VS_REQUIRE(val_dtype == VS_F32 || val_dtype == VS_F16 || val_dtype == VS_BF16, VS_ERR_INVALID, "bad value dtype");
+        VS_REQUIRE(store_dtype == VS_F32 || store_dtype == VS_F16 || store_dtype == VS_BF16, VS_ERR_INVALID, "bad store dtype");
+    }
+    VS_CUDA(cudaSetDevice(device));
+    vs_index *idx = new (std::nothrow) vs_index();
+    VS_REQUIRE(idx != nullptr, VS_ERR_NOMEM, "out of host memory");
+    idx->device = device;
+    idx->kind = binary ? 2 : 1;
+    idx->store_dtype = binary ? VS_NONE : store_dtype;
+    idx->n_rows = n_rows; idx->n_cols = n_cols; idx->nnz = nnz;
+    if (const char *e = getenv("VSEARCH_B200_BANK_AWARE")) idx->bank_aware = (e[0] != '0');
+    if (cudaMalloc(&idx->d_last_mode, 256) != cudaSuccess) { delete idx; VS_REQUIRE(false, VS_ERR_NOMEM, "out of device memory"); }
+    cudaMemsetAsync(idx->d_last_mode, 0, 256, st);
+    int rc = build_ws_index(idx, d_crow, crow_dtype, d_col, col_dtype, binary ? nullptr : d_val, binary ? VS_NONE : val_dtype, st,
+                            col_shift);
+    cudaStreamSynchronize(st);
+    for (int i = 0; i < VS_TIMER_SLOTS && rc == VS_OK; ++i)
+        if (cudaEventCreate(&idx->ev0[i]) != cudaSuccess || cudaEventCreate(&idx->ev1[i]) != cudaSuccess) {
+            set_error("cudaEventCreate failed");
+            rc = VS_ERR_CUDA;
+        }
+    if (rc != VS_OK) { vs_index_destroy(idx); return rc; }
+    *out = idx;
+    return VS_OK;
+}
+
 }  // namespace vs
 
 using namespace vs;
@@ -173,48 +209,21 @@ int vs_index_create_csr(int device, int64_t n_rows, int64_t n_cols, int64_t nnz,
     VS_REQUIRE(n_rows >= 0 && n_cols >= 1 && nnz >= 0, VS_ERR_INVALID, "bad shape");
     VS_REQUIRE(n_cols <= 32767, VS_ERR_UNSUPPORTED,
                "n_cols=%lld does not fit the uint16 column format (15 bits + the row-end flag)", (long long)n_cols);
-    VS_REQUIRE(n_rows < 0xffffffffll, VS_ERR_UNSUPPORTED, "n_rows must be < 2^32 - 1 per shard");
     VS_REQUIRE(crow_dtype == VS_I32 || crow_dtype == VS_I64, VS_ERR_INVALID, "crow dtype must be int32/int64");
     VS_REQUIRE(col_dtype == VS_I32 || col_dtype == VS_I64, VS_ERR_INVALID, "col dtype must be int32/int64");
     const bool binary = (hd_val == nullptr || val_dtype == VS_NONE);
-    if (!binary) {
-        VS_REQUIRE(val_dtype == VS_F32 || val_dtype == VS_F16 || val_dtype == VS_BF16, VS_ERR_INVALID, "bad value dtype");
-        VS_REQUIRE(store_dtype == VS_F32 || store_dtype == VS_F16 || store_dtype == VS_BF16, VS_ERR_INVALID, "bad store dtype");
-    }
     VS_REQUIRE(hd_crow != nullptr && (nnz == 0 || hd_col != nullptr), VS_ERR_INVALID, "NULL CSR arrays");
     VS_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
-
-    vs_index *idx = new (std::nothrow) vs_index();
-    VS_REQUIRE(idx != nullptr, VS_ERR_NOMEM, "out of host memory");
-    idx->device = device;
-    idx->kind = binary ? 2 : 1;
-    idx->store_dtype = binary ? VS_NONE : store_dtype;
-    idx->n_rows = n_rows; idx->n_cols = n_cols; idx->nnz = nnz;
-    if (const char *e = getenv("VSEARCH_B200_BANK_AWARE")) idx->bank_aware = (e[0] != '0');
-    if (cudaMalloc(&idx->d_last_mode, 256) != cudaSuccess) { delete idx; VS_REQUIRE(false, VS_ERR_NOMEM, "out of device memory"); }
-    cudaMemsetAsync(idx->d_last_mode, 0, 256, st);
-
-    int rc;
-    {
-        Staged s_crow, s_col, s_val;
-        rc = s_crow.init(hd_crow, (size_t)(n_rows + 1) * dtype_size(crow_dtype), st);
-        if (rc == VS_OK) rc = s_col.init(hd_col, (size_t)nnz * dtype_size(col_dtype), st);
-        if (rc == VS_OK && !binary) rc = s_val.init(hd_val, (size_t)nnz * dtype_size(val_dtype), st);
-        if (rc == VS_OK) rc = build_ws_index(idx, s_crow.ptr, crow_dtype, s_col.ptr, col_dtype, binary ? nullptr : s_val.ptr,
-                                             binary ? VS_NONE : val_dtype, st);
-        cudaStreamSynchronize(st);
-    }
-    if (rc == VS_OK) {
-        for (int i = 0; i < VS_TIMER_SLOTS && rc == VS_OK; ++i)
-            if (cudaEventCreate(&idx->ev0[i]) != cudaSuccess || cudaEventCreate(&idx->ev1[i]) != cudaSuccess) {
-                set_error("cudaEventCreate failed");
-                rc = VS_ERR_CUDA;
-            }
-    }
-    if (rc != VS_OK) { vs_index_destroy(idx); return rc; }
-    *out = idx;
-    return VS_OK;
+    Staged s_crow, s_col, s_val;
+    int rc = s_crow.init(hd_crow, (size_t)(n_rows + 1) * dtype_size(crow_dtype), st);
+    if (rc == VS_OK) rc = s_col.init(hd_col, (size_t)nnz * dtype_size(col_dtype), st);
+    if (rc == VS_OK && !binary) rc = s_val.init(hd_val, (size_t)nnz * dtype_size(val_dtype), st);
+    if (rc == VS_OK)
+        rc = create_csr_from_device(device, n_rows, n_cols, nnz, s_crow.ptr, crow_dtype, s_col.ptr, col_dtype, binary ? nullptr : s_val.ptr,
+                                    binary ? VS_NONE : val_dtype, store_dtype, 0, st, out);
+    cudaStreamSynchronize(st);   // the staging copies are freed at scope exit
+    return rc;
 }
 
 int vs_index_create_dense(int device, int64_t n_rows, int64_t dim, const void *hd_x, int x_dtype, int64_t ld,

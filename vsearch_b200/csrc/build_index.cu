@@ -11,6 +11,7 @@ namespace vs {
 template <typename T>
 __device__ __forceinline__ int64_t load_idx(const void *p, int64_t i) { return (int64_t)((const T *)p)[i]; }
 __device__ __forceinline__ int64_t load_index(const void *p, int dtype, int64_t i) {
+    if (dtype == VS_U16) return load_idx<uint16_t>(p, i);   // columns straight from a loaded shard file (npz.cu)
     return dtype == VS_I32 ? load_idx<int32_t>(p, i) : load_idx<int64_t>(p, i);
 }
 __device__ __forceinline__ float load_value(const void *p, int dtype, int64_t i) {
@@ -19,16 +20,35 @@ __device__ __forceinline__ float load_value(const void *p, int dtype, int64_t i)
     return __bfloat162float(((const __nv_bfloat16 *)p)[i]);
 }
 
-// chunks per row (>= 1 so that every row, even an empty one, owns a tail bit)
-__global__ void row_chunks_kernel(const void *crow, int crow_dtype, int64_t n_rows, int64_t nnz, uint64_t *rc, int *err) {
+// chunks per row (>= 1 so that every row, even an empty one, owns a tail bit).  col_shift > 0 (upstream's
+// `mat[:, shift:]`, index.py:174): entries in columns < col_shift are dropped; the surviving entries are counted into
+// *kept_nnz (one atomic per CTA).
+__global__ void __launch_bounds__(256) row_chunks_kernel(const void *crow, int crow_dtype, const void *col, int col_dtype,
+                                                         int64_t col_shift, int64_t n_rows, int64_t nnz, uint64_t *rc,
+                                                         unsigned long long *kept_nnz, int *err) {
+    __shared__ unsigned long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > n_rows) return;
-    if (r == n_rows) { rc[r] = 0; return; }
-    int64_t a = load_index(crow, crow_dtype, r), e = load_index(crow, crow_dtype, r + 1);
-    if (a < 0 || e > nnz || (r == 0 && a != 0)) { atomicExch(err, 3); a = e = 0; }   // row pointers must stay inside col / val
-    if (e < a) { atomicExch(err, 1); e = a; }
-    uint64_t len = (uint64_t)(e - a);
-    rc[r] = len == 0 ? 1 : (len + 7) / 8;
+    uint64_t len = 0;
+    if (r < n_rows) {
+        int64_t a = load_index(crow, crow_dtype, r), e = load_index(crow, crow_dtype, r + 1);
+        if (a < 0 || e > nnz || (r == 0 && a != 0)) { atomicExch(err, 3); a = e = 0; }   // row pointers must stay inside col / val
+        if (e < a) { atomicExch(err, 1); e = a; }
+        len = (uint64_t)(e - a);
+        if (col_shift > 0) {
+            len = 0;
+            for (int64_t j = a; j < e; ++j) len += load_index(col, col_dtype, j) >= col_shift;
+        }
+        rc[r] = len == 0 ? 1 : (len + 7) / 8;
+    } else if (r == n_rows) {
+        rc[r] = 0;
+    }
+    if (kept_nnz != nullptr) {
+        if (len) atomicAdd(&s_sum, (unsigned long long)len);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_sum) atomicAdd(kept_nnz, s_sum);
+    }
 }
 
 // part p starts at the first row whose chunk offset is >= p/n_parts of the total
@@ -71,7 +91,7 @@ template <typename VT>
 __global__ void fill_rows_kernel(const void *crow, int crow_dtype, const void *col, int col_dtype, const void *val,
                                  int val_dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, const uint64_t *cptr,
                                  const uint32_t *part_row_begin, const uint32_t *part_win_begin, int n_parts, int cpl_shift,
-                                 uint16_t *cols16, VT *vals, uint32_t *tails, uint32_t *row_chunk, int *err) {
+                                 int64_t col_shift, uint16_t *cols16, VT *vals, uint32_t *tails, uint32_t *row_chunk, int *err) {
     int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (r >= n_rows) return;
@@ -87,10 +107,17 @@ __global__ void fill_rows_kernel(const void *crow, int crow_dtype, const void *c
     int64_t a = load_index(crow, crow_dtype, r), e = load_index(crow, crow_dtype, r + 1);
     if (a < 0 || e > nnz || (r == 0 && a != 0)) a = e = 0;   // same clamps as row_chunks_kernel (which raised the error)
     if (e < a) e = a;
-    for (int64_t j = a + lane; j < e; j += 32) {
-        int64_t c = load_index(col, col_dtype, j);
-        if (c < 0 || c >= n_cols) { atomicExch(err, 2); continue; }  // leaves the sentinel in place
-        const uint64_t ent = (uint64_t)(j - a);
+    uint64_t kept = 0;   // entries of this row written so far (columns < col_shift are dropped, the rest move up)
+    for (int64_t j0 = a; j0 < e; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const int64_t c = j < e ? load_index(col, col_dtype, j) - col_shift : -1;
+        const bool in = j < e && c >= 0;
+        if (in && c >= n_cols) atomicExch(err, 2);   // leaves a sentinel in place
+        if (j < e && c < 0 && c + col_shift < 0) atomicExch(err, 2);
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        const uint64_t ent = kept + (uint64_t)__popc(m & ((1u << lane) - 1u));
+        kept += (uint64_t)__popc(m);
+        if (!in || c >= n_cols) continue;
         const uint64_t o = ws_phys_chunk(dst + (ent >> 3), cpl_shift) * 8ull + (ent & 7ull);
         cols16[o] = (uint16_t)c;
         if constexpr (sizeof(VT) == 4) {
@@ -316,7 +343,7 @@ __global__ void mark_tails_kernel(uint16_t *cols16, const uint32_t *tails, uint6
 
 
 int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void *d_col, int col_dtype,
-                   const void *d_val, int val_dtype, cudaStream_t st) {
+                   const void *d_val, int val_dtype, cudaStream_t st, int64_t col_shift) {
     const int64_t N = idx->n_rows;
     cudaDeviceProp prop;
     VS_CUDA(cudaGetDeviceProperties(&prop, idx->device));
@@ -325,19 +352,22 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
     idx->n_parts = idx->n_ctas * idx->warps_per_cta;
     const int P = idx->n_parts;
 
-    uint64_t *d_cptr = nullptr, *d_nwin = nullptr;
+    uint64_t *d_cptr = nullptr, *d_nwin = nullptr;   // d_nwin[0] = windows, d_nwin[1] = entries kept by the column shift
     int *d_err = nullptr;
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
     auto cleanup = [&]() { cudaFree(d_cptr); cudaFree(d_nwin); cudaFree(d_err); cudaFree(d_tmp); };
 
     VS_CUDA(cudaMalloc(&d_cptr, sizeof(uint64_t) * (size_t)(N + 1)));
-    VS_CUDA(cudaMalloc(&d_nwin, sizeof(uint64_t)));
+    VS_CUDA(cudaMalloc(&d_nwin, 2 * sizeof(uint64_t)));
     VS_CUDA(cudaMalloc(&d_err, sizeof(int)));
     VS_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    VS_CUDA(cudaMemsetAsync(d_nwin, 0, 2 * sizeof(uint64_t), st));
+    const int64_t nnz_in = idx->nnz;   // entries of the input arrays (row pointers are checked against it)
     {
         int64_t n = N + 1;
-        row_chunks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_crow, crow_dtype, N, idx->nnz, d_cptr, d_err);
+        row_chunks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_crow, crow_dtype, d_col, col_dtype, col_shift, N, nnz_in, d_cptr,
+                                                                       col_shift > 0 ? (unsigned long long *)(d_nwin + 1) : nullptr, d_err);
     }
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cptr, d_cptr, (int64_t)(N + 1), st);
     VS_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16));
@@ -350,9 +380,11 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
     idx->cpl_shift = idx->kind == 2 ? 3 : (idx->store_dtype == VS_F32 ? 0 : 1);
     const int cpl_shift = idx->cpl_shift;
     part_windows_kernel<<<1, 32, 0, st>>>(d_cptr, idx->part_row_begin, P, cpl_shift, idx->part_win_begin, d_nwin);
-    uint64_t n_windows = 0;
-    VS_CUDA(cudaMemcpyAsync(&n_windows, d_nwin, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    uint64_t h_nwin[2] = {0, 0};
+    VS_CUDA(cudaMemcpyAsync(h_nwin, d_nwin, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     VS_CUDA(cudaStreamSynchronize(st));
+    const uint64_t n_windows = h_nwin[0];
+    if (col_shift > 0) idx->nnz = (int64_t)h_nwin[1];   // what survives `[:, shift:]`
     if (n_windows >= (1ull << 32)) { cleanup(); VS_REQUIRE(false, VS_ERR_UNSUPPORTED, "index too large for one shard: %llu windows", (unsigned long long)n_windows); }
     idx->n_windows = n_windows;
 
@@ -375,9 +407,9 @@ int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void
         unsigned blocks = (unsigned)((N * 32 + 255) / 256);
 #define VS_FILL(VT)                                                                                              \
     fill_rows_kernel<VT><<<blocks, 256, 0, st>>>(d_crow, crow_dtype, d_col, col_dtype, d_val, val_dtype, N,      \
-                                                 idx->n_cols, idx->nnz, d_cptr, idx->part_row_begin,             \
+                                                 idx->n_cols, nnz_in, d_cptr, idx->part_row_begin,               \
                                                  idx->part_win_begin,                                           \
-                                                 P, cpl_shift, (uint16_t *)idx->cols, (VT *)idx->vals, idx->tails, \
+                                                 P, cpl_shift, col_shift, (uint16_t *)idx->cols, (VT *)idx->vals, idx->tails, \
                                                  idx->row_chunk, d_err)
         if (idx->kind == 2) VS_FILL(NoVal);
         else if (idx->store_dtype == VS_F32) VS_FILL(float);

@@ -114,7 +114,12 @@ struct SparseQueries {
 
 namespace vs {
 int build_ws_index(vs_index *idx, const void *d_crow, int crow_dtype, const void *d_col, int col_dtype,
-                   const void *d_val, int val_dtype, cudaStream_t st);
+                   const void *d_val, int val_dtype, cudaStream_t st, int64_t col_shift = 0);
+// index from CSR arrays already on the device (col: VS_I32 | VS_I64 | VS_U16); columns < col_shift are dropped and the
+// rest renumbered (n_cols = width AFTER the shift).  SYNC.
+int create_csr_from_device(int device, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *d_crow, int crow_dtype,
+                           const void *d_col, int col_dtype, const void *d_val, int val_dtype, int store_dtype,
+                           int64_t col_shift, cudaStream_t st, vs_index **out);
 int export_ws_csr(const vs_index *idx, int64_t *d_crow, int64_t *d_col, float *d_val, cudaStream_t st);
 int build_inverted(vs_index *idx, cudaStream_t st);
 int debug_gather_wavefronts(const vs_index *idx, unsigned long long *d_out2, cudaStream_t st);

@@ -159,6 +159,7 @@ int parse_npy_header(const vs_npz *z, NpzMember &m) {
     else if (descr == "<u4") m.dtype = VS_U32;
     else if (descr == "<f4") m.dtype = VS_F32;
     else if (descr == "<f2") m.dtype = VS_F16;
+    else if (descr == "<f8") m.dtype = VS_F64;
     std::string sh = value_after("'shape'");
     size_t a = sh.find('('), b = sh.find(')');
     NPZ_REQUIRE(a != std::string::npos && b != std::string::npos, VS_ERR_INVALID, "%s: no shape in the header of %s", z->path.c_str(),
@@ -286,13 +287,86 @@ int npz_member_info_impl(vs_npz *z, const char *name, int *dtype, int *ndim, int
     return VS_OK;
 }
 
-int npz_read_impl(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t skip_elems, int64_t n_elems, int64_t add_offset) {
-    NPZ_REQUIRE(z && name && (dst || n_elems == 0), VS_ERR_INVALID, "vs_npz_read: NULL argument");
+// `n` elements of source dtype `sd` at p (aligned) -> dst[at ...] in dtype `dd`
+bool convert_any(int sd, const uint8_t *p, size_t n, void *dst, int dd, size_t at, int64_t add) {
+    switch (sd) {
+        case VS_I64: return convert_run((const int64_t *)p, n, dst, dd, at, add);
+        case VS_I32: return convert_run((const int32_t *)p, n, dst, dd, at, add);
+        case VS_U32: return convert_run((const uint32_t *)p, n, dst, dd, at, add);
+        case VS_U16: return convert_run((const uint16_t *)p, n, dst, dd, at, add);
+        case VS_F32: return convert_run((const float *)p, n, dst, dd, at, 0);
+        case VS_F64: return convert_run((const double *)p, n, dst, dd, at, 0);
+        default: return convert_run_half((const __half *)p, n, dst, dd, at);
+    }
+}
+
+size_t dtype_bytes(int dt) {
+    switch (dt) {
+        case VS_I64: case VS_F64: return 8;
+        case VS_I32: case VS_U32: case VS_F32: return 4;
+        default: return 2;
+    }
+}
+
+// converted elements go straight to their place in a host array
+struct HostSink {
+    void *dst; int dd; size_t written = 0;
+    bool put(int sd, const uint8_t *p, size_t n, int64_t add) {
+        const bool ok = convert_any(sd, p, n, dst, dd, written, add);
+        written += n;
+        return ok;
+    }
+    bool finish() { return true; }
+};
+
+// converted elements go through two pinned staging buffers to their place in a DEVICE array: while one buffer is on
+// its way (cudaMemcpyAsync on the sink's own stream) the inflating thread fills the other
+struct DeviceSink {
+    uint8_t *d_dst; int dd; cudaStream_t st;
+    uint8_t *buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    size_t cap = 0, fill = 0, d_off = 0, written = 0;
+    int cur = 0;
+    bool failed = false;
+    bool init(size_t bytes) {
+        cap = bytes;
+        for (int i = 0; i < 2; ++i)
+            if (cudaHostAlloc((void **)&buf[i], cap, cudaHostAllocDefault) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        return true;
+    }
+    ~DeviceSink() {
+        for (int i = 0; i < 2; ++i) { if (buf[i]) cudaFreeHost(buf[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+    }
+    bool flush() {
+        if (fill == 0) return true;
+        if (cudaMemcpyAsync(d_dst + d_off, buf[cur], fill, cudaMemcpyHostToDevice, st) != cudaSuccess) return !(failed = true);
+        if (cudaEventRecord(ev[cur], st) != cudaSuccess) return !(failed = true);
+        d_off += fill;
+        fill = 0;
+        cur ^= 1;
+        return cudaEventSynchronize(ev[cur]) == cudaSuccess || !(failed = true);   // the other buffer's last copy has left it
+    }
+    bool put(int sd, const uint8_t *p, size_t n, int64_t add) {
+        const size_t di = dtype_bytes(dd), si = dtype_bytes(sd);
+        while (n) {
+            const size_t room = (cap - fill) / di, c = room < n ? room : n;
+            if (!convert_any(sd, p, c, buf[cur], dd, fill / di, add)) return false;
+            fill += c * di; written += c; p += c * si; n -= c;
+            if (fill + di > cap && !flush()) return false;
+        }
+        return true;
+    }
+    bool finish() { return flush() && cudaStreamSynchronize(st) == cudaSuccess; }
+};
+
+template <typename Sink>
+int npz_read_core(vs_npz *z, const char *name, Sink &out, int dst_dtype, int64_t skip_elems, int64_t n_elems, int64_t add_offset) {
     NpzMember *m = find_member(z, name);
     NPZ_REQUIRE(m, VS_ERR_INVALID, "%s: no member %s", z->path.c_str(), name);
     int rc = parse_npy_header(z, *m);
     if (rc) return rc;
-    NPZ_REQUIRE(m->dtype != VS_NONE, VS_ERR_UNSUPPORTED, "%s: member %s has dtype %s (int32/int64/uint16/uint32/float32/float16 only)",
+    NPZ_REQUIRE(m->dtype != VS_NONE, VS_ERR_UNSUPPORTED, "%s: member %s has dtype %s (int32/int64/uint16/uint32/float16/float32/float64 only)",
                 z->path.c_str(), name, m->descr);
     int64_t total = 1;
     for (int i = 0; i < m->ndim; ++i) total *= m->shape[i];
@@ -308,19 +382,8 @@ int npz_read_impl(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t
     const uint64_t first = m->header_len + (uint64_t)skip_elems * item, last = first + (uint64_t)n_elems * item;
     uint8_t carry[8];
     size_t n_carry = 0;
-    size_t written = 0;
     bool ok = true;
-    auto emit = [&](const uint8_t *p, size_t n_el) {
-        switch (m->dtype) {
-            case VS_I64: ok = convert_run((const int64_t *)p, n_el, dst, dst_dtype, written, add_offset); break;
-            case VS_I32: ok = convert_run((const int32_t *)p, n_el, dst, dst_dtype, written, add_offset); break;
-            case VS_U32: ok = convert_run((const uint32_t *)p, n_el, dst, dst_dtype, written, add_offset); break;
-            case VS_U16: ok = convert_run((const uint16_t *)p, n_el, dst, dst_dtype, written, add_offset); break;
-            case VS_F32: ok = convert_run((const float *)p, n_el, dst, dst_dtype, written, 0); break;
-            default: ok = convert_run_half((const __half *)p, n_el, dst, dst_dtype, written); break;
-        }
-        written += n_el;
-    };
+    auto emit = [&](const uint8_t *p, size_t n_el) { ok = ok && out.put(m->dtype, p, n_el, add_offset); };
     rc = stream_member(z, *m, [&](const uint8_t *p, size_t n) {
         uint64_t lo = pos, hi = pos + n;
         pos = hi;
@@ -353,9 +416,30 @@ int npz_read_impl(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t
         return ok && pos < last;
     });
     if (rc) return rc;
-    NPZ_REQUIRE(ok, VS_ERR_INVALID, "%s: conversion of member %s failed", z->path.c_str(), name);
-    NPZ_REQUIRE((int64_t)written == n_elems, VS_ERR_INVALID, "%s: member %s ended after %lld of %lld elements", z->path.c_str(), name,
-                (long long)written, (long long)n_elems);
+    NPZ_REQUIRE(ok && out.finish(), VS_ERR_INVALID, "%s: conversion / transfer of member %s failed", z->path.c_str(), name);
+    NPZ_REQUIRE((int64_t)out.written == n_elems, VS_ERR_INVALID, "%s: member %s ended after %lld of %lld elements", z->path.c_str(), name,
+                (long long)out.written, (long long)n_elems);
+    return VS_OK;
+}
+
+int npz_read_impl(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t skip_elems, int64_t n_elems, int64_t add_offset) {
+    NPZ_REQUIRE(z && name && (dst || n_elems == 0), VS_ERR_INVALID, "vs_npz_read: NULL argument");
+    HostSink out{dst, dst_dtype};
+    return npz_read_core(z, name, out, dst_dtype, skip_elems, n_elems, add_offset);
+}
+
+// raw bytes of a small member's array data (format / shape / _is_array), at most `cap`
+int npz_read_small(vs_npz *z, const char *name, uint8_t *dst, size_t cap, size_t *got) {
+    NpzMember *m = find_member(z, name);
+    NPZ_REQUIRE(m, VS_ERR_INVALID, "%s: no member %s", z->path.c_str(), name);
+    int rc = parse_npy_header(z, *m);
+    if (rc) return rc;
+    std::vector<uint8_t> all;
+    rc = stream_member(z, *m, [&](const uint8_t *p, size_t n) { all.insert(all.end(), p, p + n); return all.size() < m->header_len + cap; });
+    if (rc) return rc;
+    const size_t n = all.size() > m->header_len ? all.size() - (size_t)m->header_len : 0;
+    *got = n < cap ? n : cap;
+    memcpy(dst, all.data() + m->header_len, *got);
     return VS_OK;
 }
 
@@ -391,6 +475,176 @@ int vs_npz_read(vs_npz *z, const char *name, void *dst, int dst_dtype, int64_t s
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Loader: shard files -> a device index, without a host copy of the index.  Upstream
+// (SparseIndex.init_index, index.py:163-179) inflates every shard on one Python thread into scipy matrices, slices,
+// vstacks, converts and only then copies to the device: minutes and more than twice the index in host memory at 21M
+// rows.  Here every (shard, member) pair is a job of a small thread pool: the member is inflated in 1 MB pieces,
+// narrowed on the fly (int64 / int32 columns -> uint16 when the vocabulary allows, float64 / float32 values ->
+// float16 when asked, row pointers + the shard's entry offset -> int64) into one of two pinned staging buffers and
+// sent to its final place in the device CSR arrays with cudaMemcpyAsync while the thread inflates the next piece.
+// The `[:, shift:]` column slice and the row concatenation cost nothing on the host: the shift is applied by the
+// index build on the GPU (build_index.cu drops and renumbers while it lays the rows out), concatenation is where the
+// pieces land.  Peak host memory: 2 x 4 MB pinned per thread.
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <thread>
+
+#include "index.cuh"
+
+namespace vs {
+__global__ void all_ones_kernel(const void *v, int dtype, uint64_t n, int *not_ones) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < n; i += stride) {
+        const float x = dtype == VS_F16 ? __half2float(((const __half *)v)[i]) : ((const float *)v)[i];
+        bad |= (x != 1.0f);
+    }
+    if (bad) atomicExch(not_ones, 1);
+}
+}  // namespace vs
+
+namespace {
+
+struct LoadJob {
+    int shard;
+    const char *member;
+    uint8_t *d_dst;
+    int dst_dtype;
+    int64_t skip, n, add;
+    uint64_t bytes;
+};
+
+int load_npz_impl(int device, const char *const *paths, int n_paths, int shift, int value_dtype, int binary_if_ones, int threads,
+                  void *stream, vs_index **out, int64_t *shard_rows) {
+    NPZ_REQUIRE(out != nullptr, VS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    NPZ_REQUIRE(paths != nullptr && n_paths >= 1 && shift >= 0, VS_ERR_INVALID, "vs_index_load_npz: bad argument");
+    NPZ_REQUIRE(value_dtype == VS_F32 || value_dtype == VS_F16 || value_dtype == VS_BF16, VS_ERR_INVALID, "value dtype must be f32 / f16 / bf16");
+    struct Shard { std::unique_ptr<vs_npz> z; int64_t rows = 0, nnz = 0, row_off = 0, nnz_off = 0; };
+    std::vector<Shard> sh((size_t)n_paths);
+    int64_t n_rows = 0, nnz = 0, n_cols_file = -1;
+    for (int i = 0; i < n_paths; ++i) {
+        vs_npz *z = nullptr;
+        int rc = npz_open_impl(paths[i], &z);
+        if (rc) return rc;
+        sh[i].z.reset(z);
+        uint8_t fmt[8] = {0};
+        size_t got = 0;
+        rc = npz_read_small(z, "format", fmt, 3, &got);
+        if (rc) return rc;
+        NPZ_REQUIRE(got == 3 && memcmp(fmt, "csr", 3) == 0, VS_ERR_INVALID, "%s: expected a CSR .npz (format member is not b'csr')", paths[i]);
+        int64_t shape[2] = {0, 0};
+        rc = npz_read_impl(z, "shape", shape, VS_I64, 0, 2, 0);
+        if (rc) return rc;
+        int64_t n_ptr = 0, n_idx = 0, n_dat = 0;
+        rc = npz_member_info_impl(z, "indptr", nullptr, nullptr, nullptr, &n_ptr);
+        if (rc == VS_OK) rc = npz_member_info_impl(z, "indices", nullptr, nullptr, nullptr, &n_idx);
+        if (rc == VS_OK) rc = npz_member_info_impl(z, "data", nullptr, nullptr, nullptr, &n_dat);
+        if (rc) return rc;
+        NPZ_REQUIRE(n_ptr == shape[0] + 1 && n_idx == n_dat && shape[0] >= 0 && shape[1] >= 1, VS_ERR_INVALID, "%s: inconsistent CSR members", paths[i]);
+        if (n_cols_file < 0) n_cols_file = shape[1];
+        NPZ_REQUIRE(shape[1] == n_cols_file, VS_ERR_INVALID, "%s: column count %lld differs from previous shards (%lld)", paths[i],
+                    (long long)shape[1], (long long)n_cols_file);
+        sh[i].rows = shape[0]; sh[i].nnz = n_idx; sh[i].row_off = n_rows; sh[i].nnz_off = nnz;
+        if (shard_rows) shard_rows[i] = shape[0];
+        n_rows += shape[0];
+        nnz += n_idx;
+    }
+    NPZ_REQUIRE(n_cols_file - shift >= 1, VS_ERR_INVALID, "shift=%d leaves no columns of %lld", shift, (long long)n_cols_file);
+    NPZ_REQUIRE(cudaSetDevice(device) == cudaSuccess, VS_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int col_dtype = n_cols_file <= 65535 ? VS_U16 : VS_I32;
+    const int stage_val = value_dtype == VS_F16 ? VS_F16 : VS_F32;   // upstream's fp16=True: astype(float16) while loading
+    const size_t csz = dtype_bytes(col_dtype), vsz = dtype_bytes(stage_val);
+    int64_t *d_crow = nullptr;
+    uint8_t *d_col = nullptr, *d_val = nullptr;
+    int *d_flag = nullptr;
+    auto cleanup = [&]() { cudaFree(d_crow); cudaFree(d_col); cudaFree(d_val); cudaFree(d_flag); };
+    if (cudaMalloc(&d_crow, (size_t)(n_rows + 1) * 8) != cudaSuccess || cudaMalloc(&d_col, nnz ? (size_t)nnz * csz : 16) != cudaSuccess ||
+        cudaMalloc(&d_val, nnz ? (size_t)nnz * vsz : 16) != cudaSuccess || cudaMalloc(&d_flag, 4) != cudaSuccess) {
+        cleanup();
+        NPZ_REQUIRE(false, VS_ERR_NOMEM, "out of device memory for the CSR staging arrays (%lld rows, %lld entries)", (long long)n_rows, (long long)nnz);
+    }
+    cudaMemsetAsync(d_crow, 0, 8, st);
+    cudaMemsetAsync(d_flag, 0, 4, st);
+    // ---- jobs, largest first
+    std::vector<LoadJob> jobs;
+    for (int i = 0; i < n_paths; ++i) {
+        jobs.push_back({i, "indices", d_col + (size_t)sh[i].nnz_off * csz, col_dtype, 0, sh[i].nnz, 0, (uint64_t)sh[i].nnz * 8});
+        jobs.push_back({i, "data", d_val + (size_t)sh[i].nnz_off * vsz, stage_val, 0, sh[i].nnz, 0, (uint64_t)sh[i].nnz * 4});
+        // drop each shard's leading 0, add the entries of the shards before it
+        jobs.push_back({i, "indptr", (uint8_t *)(d_crow + sh[i].row_off + 1), VS_I64, 1, sh[i].rows, sh[i].nnz_off, (uint64_t)sh[i].rows * 8});
+    }
+    std::sort(jobs.begin(), jobs.end(), [](const LoadJob &a, const LoadJob &b) { return a.bytes > b.bytes; });
+    int n_thr = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (n_thr < 1) n_thr = 1;
+    if (n_thr > (int)jobs.size()) n_thr = (int)jobs.size();
+    std::atomic<size_t> next{0};
+    std::mutex err_mu;
+    int first_rc = VS_OK;
+    std::string first_err;
+    auto worker = [&]() {
+        auto fail = [&](int rc, const char *msg) {
+            std::lock_guard<std::mutex> g(err_mu);
+            if (first_rc == VS_OK) { first_rc = rc; first_err = msg; }
+        };
+        if (cudaSetDevice(device) != cudaSuccess) { fail(VS_ERR_CUDA, "cudaSetDevice failed in a loader thread"); return; }
+        cudaStream_t cs = nullptr;
+        if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { fail(VS_ERR_CUDA, "cudaStreamCreate failed in a loader thread"); return; }
+        {
+            DeviceSink sink{nullptr, VS_I64, cs};
+            if (!sink.init(4u << 20)) fail(VS_ERR_NOMEM, "cannot allocate pinned staging buffers");
+            else
+                for (;;) {
+                    const size_t j = next.fetch_add(1);
+                    if (j >= jobs.size() || first_rc != VS_OK) break;
+                    const LoadJob &job = jobs[j];
+                    sink.d_dst = job.d_dst; sink.dd = job.dst_dtype; sink.fill = 0; sink.d_off = 0; sink.written = 0;
+                    int rc = VS_OK;
+                    try {
+                        rc = npz_read_core(sh[job.shard].z.get(), job.member, sink, job.dst_dtype, job.skip, job.n, job.add);
+                    } catch (...) {
+                        rc = VS_ERR_NOMEM;
+                        vs::set_error("out of host memory in a loader thread");
+                    }
+                    if (rc != VS_OK) fail(rc, vs_last_error());   // the message is thread-local: carry it over
+                }
+        }
+        cudaStreamSynchronize(cs);
+        cudaStreamDestroy(cs);
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_thr; ++t) pool.emplace_back(worker);
+        for (auto &t : pool) t.join();
+    }
+    if (first_rc != VS_OK) { cleanup(); NPZ_REQUIRE(false, first_rc, "%s", first_err.c_str()); }
+    // ---- bag-of-token files store a 1 per entry: keep column ids only
+    bool binary = false;
+    if (binary_if_ones) {
+        int h_flag = 0;
+        if (nnz) vs::all_ones_kernel<<<1024, 256, 0, st>>>(d_val, stage_val, (uint64_t)nnz, d_flag);
+        cudaError_t e = cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { cleanup(); NPZ_REQUIRE(false, VS_ERR_CUDA, "all-ones check failed: %s", cudaGetErrorString(e)); }
+        binary = h_flag == 0;
+    }
+    int rc = vs::create_csr_from_device(device, n_rows, n_cols_file - shift, nnz, d_crow, VS_I64, d_col, col_dtype, binary ? nullptr : d_val,
+                                        binary ? VS_NONE : stage_val, binary ? VS_NONE : value_dtype, shift, st, out);
+    cleanup();
+    return rc;
+}
+
+}  // namespace
+
+extern "C" int vs_index_load_npz(int device, const char *const *paths, int n_paths, int shift, int value_dtype, int binary_if_ones,
+                                 int threads, void *stream, vs_index **out, int64_t *shard_rows) {
+    NPZ_NOTHROW(load_npz_impl(device, paths, n_paths, shift, value_dtype, binary_if_ones, threads, stream, out, shard_rows))
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Writer: a zip of deflated `.npy` members (what scipy.sparse.save_npz / numpy.savez_compressed produce,

@@ -98,6 +98,27 @@ class _Engine:
         return cls(handle, device)
 
     @classmethod
+    def from_npz(cls, files, device, shift: int = 0, value_dtype=torch.float32, binary_if_ones: bool = False,
+                 threads: int = 0):
+        """Shard files -> device index without a host copy of the index (``vs_index_load_npz``).  Returns
+        ``(engine, rows_per_file)``."""
+        import os
+
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("vsearch_b200 searches on CUDA devices only (no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        paths = (ctypes.c_char_p * len(files))(*[os.fsencode(f) for f in files])
+        rows = (ctypes.c_int64 * len(files))()
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            rc = nat.LIB.vs_index_load_npz(device.index, paths, len(files), int(shift), _TORCH2VS[value_dtype], int(binary_if_ones),
+                                           int(threads), _stream_ptr(device), ctypes.byref(handle), rows)
+        nat.check(rc)
+        return cls(handle, device), [int(r) for r in rows]
+
+    @classmethod
     def from_dense(cls, x: torch.Tensor, device, store_dtype) -> "_Engine":
         device = torch.device(device)
         if device.type != "cuda":
@@ -419,10 +440,14 @@ class Index:
         v = self._vector
         if v.layout != torch.strided:
             raise TypeError("the dense Index needs a strided [N, D] vector; use SparseIndex / BoTIndex for CSR")
-        store = torch.float16 if v.dtype == torch.float16 else torch.bfloat16
         if v.dtype not in (torch.float16, torch.bfloat16):
-            logger.warning("dense index of dtype %s is stored as bfloat16 on the device (tensor-core path)", v.dtype)
-        self._engine = _Engine.from_dense(v.to(dev), dev, store)
+            # upstream's Index(fp16=False) searches an fp32 [N, D] matrix with an fp32 GEMM (index.py:36-44, 88-94).  The
+            # tcgen05 kernel stores bf16 / fp16 operands; narrowing an fp32 vector behind the caller's back would change
+            # near-tie ranks and scores, so it is refused until an fp32-accurate path exists.
+            raise NotImplementedError(
+                f"the dense index searches bf16 / fp16 vectors on the tensor cores; got {v.dtype}. Convert explicitly "
+                "(vector.to(torch.bfloat16) or Index(fp16=True)) to accept half-precision storage")
+        self._engine = _Engine.from_dense(v.to(dev), dev, v.dtype)
 
     def _require_engine(self) -> _Engine:
         if self._engine is None:
@@ -534,6 +559,16 @@ class SparseIndex(Index):
         if not files:
             raise FileNotFoundError(f"no index files match {index_file!r}")
         logger.info("***** Loading %s Index from %d files *****", self.index_type.value, len(files))
+        if _is_cuda(self.device):
+            # straight to the device (csrc/npz.cu): parallel inflate -> pinned staging -> the device CSR arrays -> index
+            # build, with the column shift applied on the GPU; no scipy matrices, no host copy of the index.  `.vector`
+            # is exported from the engine on demand (save, repr).
+            self._vector = None
+            self._engine, self.shard_rows = _Engine.from_npz(files, self._resolve(self.device), shift=max(self.shift, 0),
+                                                             value_dtype=torch.float16 if fp16 else torch.float32,
+                                                             binary_if_ones=self.index_type == IndexType.BAG_OF_TOKEN)
+            self._logical_dtype = torch.float16 if fp16 else torch.float32
+            return
         if self.shift <= 0:
             # native reader (csrc/npz.cu): all members of all shards inflated in parallel into the final arrays,
             # int64 -> int32 narrowing and astype(float16) on the fly

@@ -67,7 +67,7 @@ def load_csr_shards(files: Sequence[str], shift: int = 0) -> Tuple[np.ndarray, n
 
 # ---- native loader (csrc/npz.cu through the C ABI) ---------------------------------------------------------------
 _NP2VS = {np.dtype(np.int32): 3, np.dtype(np.int64): 4, np.dtype(np.float32): 0, np.dtype(np.float16): 1}
-_VS2NP = {0: np.float32, 1: np.float16, 3: np.int32, 4: np.int64, 5: np.uint16, 6: np.uint32}
+_VS2NP = {0: np.float32, 1: np.float16, 3: np.int32, 4: np.int64, 5: np.uint16, 6: np.uint32, 8: np.float64}
 
 
 class _NativeShard:
@@ -109,6 +109,18 @@ class _NativeShard:
             pass
 
 
+def shard_row_counts(files: Sequence[str]) -> List[int]:
+    """Rows of every shard file, from the .npy header of its ``indptr`` member (nothing is inflated beyond the header)."""
+    out = []
+    for f in files:
+        sh = _NativeShard(f)
+        try:
+            out.append(sh.info("indptr")[2] - 1)
+        finally:
+            sh.close()
+    return out
+
+
 def load_csr_shards_native(files: Sequence[str], fp16: bool = False, threads: int | None = None):
     """Row-concatenation of shard files like :func:`load_csr_shards` (``shift == 0``), but every big member of every
     shard is inflated by its own thread straight into its slice of the final arrays (ctypes releases the GIL), with
@@ -134,9 +146,11 @@ def load_csr_shards_native(files: Sequence[str], fp16: bool = False, threads: in
                 n_cols = shape[1]
             elif shape[1] != n_cols:
                 raise ValueError(f"{f}: column count {shape[1]} differs from previous shards ({n_cols})")
-            if ddt not in (0, 1):
-                raise ValueError(f"{f}: data must be float32 or float16")
-            data_np = _VS2NP[ddt] if data_np is None else np.result_type(data_np, _VS2NP[ddt])
+            if ddt not in (0, 1, 8):
+                raise ValueError(f"{f}: data must be float64, float32 or float16")
+            # float64 (scipy's default dtype) is narrowed to float32 while inflating: the engine searches f32 / f16 / bf16
+            ddt_np = np.float32 if ddt == 8 else _VS2NP[ddt]
+            data_np = ddt_np if data_np is None else np.result_type(data_np, ddt_np)
             metas.append((n_rows, nnz, shape[0], n_idx))
             n_rows += shape[0]
             nnz += n_idx
@@ -168,6 +182,7 @@ def save_csr_npz_native(path: str, indptr: np.ndarray, indices: np.ndarray, data
 
     from . import _native as nat
 
+    path = os.fspath(path)
     if not path.endswith(".npz"):
         path += ".npz"   # numpy / scipy append the suffix too
     arrays = [("indices", np.ascontiguousarray(indices)), ("indptr", np.ascontiguousarray(indptr)),
