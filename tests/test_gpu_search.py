@@ -799,3 +799,30 @@ def test_loader_direct_to_device_matches_reference_loader(shift, tmp_path, cuda_
     sp.save_npz(str(tmp_path / "ones.npz"), m)
     bot = vs.BoTIndex(str(tmp_path / "ones.npz"), device="cuda:0")
     assert bot._engine.kind == 2                                                             # all ones: column ids only
+
+
+@pytest.mark.gpu
+def test_sharded_index_from_shard_files(cuda_device):
+    """ShardedIndex.from_shard_files: the shard files are dealt to the ranks in contiguous groups of upstream's sorted-glob
+    order, each rank loads its own files onto its GPU and gets its global id offset from the headers of the files before
+    it.  Two virtual ranks on one GPU + the merge = the search of the whole index."""
+    import os
+
+    import vsearch_b200 as vs
+    from tests.util import GOLDEN
+    from vsearch_b200.index import merge_keys
+
+    pattern = os.path.join(GOLDEN, "shards", "index*.npz")
+    z = np.load(os.path.join(GOLDEN, "load_shift0.npz"))
+    X = ref_search.torch_csr(z["crow"], z["col"], z["val"], tuple(z["shape"]))
+    q = sparse_queries(3, int(z["shape"][1]), 40, seed=4)
+    whole = vs.ShardedIndex.from_shard_files(pattern, "cuda:0", fp16=False)
+    assert whole.row_offset == 0 and whole.n_rows_total == int(z["shape"][0])
+    assert ref_search.compare_results(whole.search(q, 6), ref_search.ref_scores(q, X), 6, rtol=1e-5, exact=False) is None
+    parts = [vs.ShardedIndex.from_shard_files(pattern, "cuda:0", world=2, rank=r, fp16=False) for r in range(2)]
+    assert parts[0].row_offset == 0 and parts[1].row_offset == parts[0].local._require_engine().n_rows
+    assert parts[1].row_offset + parts[1].local._require_engine().n_rows == int(z["shape"][0])
+    keys = torch.stack([p.local.search_keys(q, 6, id_offset=p.row_offset) for p in parts])
+    ids, sc = merge_keys(keys, 6)
+    msg = ref_search.compare_results(ref_search.SearchResults(ids, sc), ref_search.ref_scores(q, X), 6, rtol=1e-5, exact=False)
+    assert msg is None, msg

@@ -555,7 +555,8 @@ class SparseIndex(Index):
             return
         from .npz_io import load_csr_shards, load_csr_shards_native
 
-        files = sorted(glob.glob(index_file))
+        # a glob pattern like upstream's, or an explicit list of shard files in row order (a rank of the row-sharded layout)
+        files = sorted(glob.glob(index_file)) if isinstance(index_file, str) else [str(f) for f in index_file]
         if not files:
             raise FileNotFoundError(f"no index files match {index_file!r}")
         logger.info("***** Loading %s Index from %d files *****", self.index_type.value, len(files))

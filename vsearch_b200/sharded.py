@@ -44,6 +44,35 @@ class ShardedIndex:
         self.group = group
         self._merge = merge_fn or merge_keys  # tests on CPU/gloo inject the oracle merge here
 
+    @classmethod
+    def from_shard_files(cls, index_glob: str, device, index_cls=None, group=None, world: Optional[int] = None,
+                         rank: Optional[int] = None, **index_kwargs) -> "ShardedIndex":
+        """Row-sharded index straight from upstream's shard files (one ``index{i}.npz`` per build-time shard,
+        examples/inference_sparse/README.md:86-107): the files, in upstream's sorted-glob order, are dealt to the ranks in
+        contiguous groups; every rank loads ITS files directly onto ITS GPU (``vs_index_load_npz``: no host-side
+        concatenation), and the global id offset of a rank comes from the ``.npy`` headers of the files before it."""
+        import glob as _glob
+
+        from .index import SparseIndex
+        from .npz_io import shard_row_counts
+
+        files = sorted(_glob.glob(index_glob))
+        if not files:
+            raise FileNotFoundError(f"no index files match {index_glob!r}")
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if len(files) < world:
+            raise ValueError(f"{len(files)} shard files cannot be dealt to {world} ranks")
+        per = -(-len(files) // world)
+        lo, hi = min(len(files), rank * per), min(len(files), (rank + 1) * per)
+        if lo >= hi:
+            raise ValueError(f"rank {rank} of {world} gets no shard file ({len(files)} files, {per} per rank)")
+        rows = shard_row_counts(files)
+        local = (index_cls or SparseIndex)(files[lo:hi], device=device, **index_kwargs)
+        return cls(local, sum(rows[:lo]), sum(rows), group=group)
+
     def search(self, q_embs: torch.Tensor, k: int) -> SearchResults:
         if k > self.n_rows_total:
             raise RuntimeError(f"selected index k out of range (k={k} > N={self.n_rows_total})")
