@@ -72,7 +72,11 @@ int vs_index_create_csr(int device, int64_t n_rows, int64_t n_cols, int64_t nnz,
                         const void *hd_val, int val_dtype,     /* VS_F32 | VS_F16 | VS_BF16 | VS_NONE */
                         int store_dtype, void *stream, vs_index **out);
 
-/* Dense index: `Index.vector` strided [N, D] (index.py:25-44,88-94).  Stored bf16 or f32. */
+/* Dense index: `Index.vector` strided [N, D] (index.py:25-44,88-94).  store_dtype VS_BF16 | VS_F16: the vectors are
+ * scored as stored on the tensor cores (fp32 accumulate).  VS_F32 (upstream's Index(fp16=False): an fp32 matrix and an
+ * fp32 GEMM): fp32 semantics -- the tensor cores sweep a bf16 copy, every passage within the bf16 error bound
+ * 2 * 2^-7 * |q| * max|x| of the k-th score is re-scored exactly from its fp32 row, and those scores are ranked; the
+ * index keeps both copies (6 bytes per element).  SYNC. */
 int vs_index_create_dense(int device, int64_t n_rows, int64_t dim, const void *hd_x, int x_dtype,
                           int64_t ld, int store_dtype, void *stream, vs_index **out);
 

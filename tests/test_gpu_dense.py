@@ -111,15 +111,36 @@ def test_dense_continuous_ids_and_scores_at_2e3(cuda_device):
     assert msg is None, msg
 
 
-def test_dense_fp32_vector_is_refused_not_narrowed(cuda_device):
-    """upstream's Index(fp16=False) keeps an fp32 matrix and does an fp32 GEMM (index.py:36-44); the tensor-core kernel
-    stores bf16 / fp16, so an fp32 vector is refused (no silent narrowing) until an fp32-accurate path exists."""
+def test_dense_fp32_vector_keeps_fp32_semantics(cuda_device):
+    """upstream's Index(fp16=False) keeps an fp32 matrix and does an fp32 GEMM (index.py:36-44, 88-94).  Here the tensor
+    cores sweep a bf16 copy and every passage within the bf16 error bound of the k-th score is re-scored exactly from
+    its fp32 row: ids and scores must match the fp32 reference at 1e-5 (near-tie-aware), on data where a plain bf16
+    index ranks differently."""
     import vsearch_b200 as vs
 
-    idx = vs.Index(fp16=False)
-    idx.vector = torch.randn(100, 64)
-    with pytest.raises(NotImplementedError):
+    g = torch.Generator().manual_seed(21)
+    for n, d, B, k in ((150_000, 96, 37, 50), (1_100_000, 64, 9, 100), (3000, 200, 5, 100)):   # the last one: the sample sweep covers the whole index
+        x = torch.randn(n, d, generator=g)
+        q = torch.randn(B, d, generator=g)
+        idx = vs.Index(fp16=False)
+        idx.vector = x
         idx.move_to_device("cuda:0")
-    idx.vector = torch.randn(100, 64).to(torch.bfloat16)      # the explicit conversion works
+        assert idx._engine.store_dtype == 0
+        res = idx.search(q, k)
+        assert res.scores.dtype == torch.float32
+        ref = ref_search.ref_scores(q, x)
+        msg = ref_search.compare_results(res, ref, k, rtol=1e-5, exact=False)
+        assert msg is None, f"n={n}: {msg}"
+        if n == 150_000:   # the same vectors narrowed to bf16 do not reproduce the fp32 ranking: the re-score matters
+            narrow = vs.Index()
+            narrow.vector = x.to(torch.bfloat16)
+            narrow.move_to_device("cuda:0")
+            got = narrow.search(q, k)
+            assert ref_search.compare_results(ref_search.SearchResults(got.ids, got.scores.float()), ref, k, rtol=1e-5, exact=False) is not None
+    # grid data: exact in every precision -> bit-equal ids and scores, fp16 queries against an fp32 index
+    xg, qg = _grid((40_000, 128), 5), _grid((6, 128), 6)
+    idx = vs.Index(fp16=False)
+    idx.vector = xg
     idx.move_to_device("cuda:0")
-    assert idx.search(torch.randn(2, 64), 5).scores.dtype == torch.bfloat16
+    res = idx.search(qg.to(torch.float16), 20)
+    assert ref_search.compare_results(res, ref_search.ref_scores(qg, xg), 20, exact=True) is None

@@ -232,8 +232,7 @@ int vs_index_create_dense(int device, int64_t n_rows, int64_t dim, const void *h
     *out = nullptr;
     VS_REQUIRE(n_rows >= 0 && dim >= 1 && ld >= dim && hd_x != nullptr, VS_ERR_INVALID, "bad dense shape");
     VS_REQUIRE(x_dtype == VS_F32 || x_dtype == VS_F16 || x_dtype == VS_BF16, VS_ERR_INVALID, "bad dense dtype");
-    VS_REQUIRE(store_dtype == VS_F16 || store_dtype == VS_BF16, VS_ERR_UNSUPPORTED,
-               "the dense index is stored as bf16 or fp16 (tcgen05 kind::f16); fp32 storage is not built");
+    VS_REQUIRE(store_dtype == VS_F16 || store_dtype == VS_BF16 || store_dtype == VS_F32, VS_ERR_INVALID, "bad dense store dtype");
     VS_REQUIRE(n_rows < 0x7fffff00ll, VS_ERR_UNSUPPORTED, "n_rows must be < 2^31 per shard");
     VS_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -266,7 +265,7 @@ int vs_index_destroy(vs_index *idx) {
     cudaFree(idx->d_last_mode);
     cudaFree(idx->cols); cudaFree(idx->vals); cudaFree(idx->tails);
     cudaFree(idx->part_win_begin); cudaFree(idx->part_row_begin); cudaFree(idx->row_chunk);
-    cudaFree(idx->dense);
+    cudaFree(idx->dense); cudaFree(idx->dense32);
     cudaFree(idx->post_ptr); cudaFree(idx->blk_ptr); cudaFree(idx->blk_base); cudaFree(idx->post_row); cudaFree(idx->post_val);
     for (int i = 0; i < VS_TIMER_SLOTS; ++i) {
         if (idx->ev0[i]) cudaEventDestroy(idx->ev0[i]);

@@ -556,6 +556,87 @@ __global__ void dense_seed_lists_kernel(const uint64_t *sorted_keys, int k, uint
     }
 }
 
+// ---- fp32 storage (upstream's Index(fp16=False): an fp32 [N, D] matrix and an fp32 GEMM, index.py:36-44, 88-94) ----------
+// The tensor cores score a bf16 copy; the fp32 matrix stays beside it.  Rounding both operands to bf16 (unit roundoff
+// u = 2^-8) changes a score by at most (2u + u^2) * sum_i |q_i x_i| <= E = 2^-7 * |q| * |x| (Cauchy-Schwarz; the fp32
+// accumulation errors of either side are three orders below).  With s_k = the k-th best bf16 score, every row of the
+// true fp32 top-k has a bf16 score >= s_k - 2E: one more filtered sweep with that threshold collects a superset of the
+// true top-k, its members are re-scored exactly from the fp32 rows on the CUDA cores, and the merge ranks those.
+constexpr float kBf16PairErr = 1.02f * 0.0078125f;   // 2^-7 with a 2 % margin for the second-order terms
+
+__global__ void row_norm_max_kernel(const float *x, int64_t n_rows, int64_t dim, unsigned int *max_norm_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float best = 0.f;
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+        float s = 0.f;
+        for (int64_t c = lane; c < dim; c += 32) { const float v = x[r * dim + c]; s = fmaf(v, v, s); }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        best = fmaxf(best, s);
+    }
+    if (lane == 0) atomicMax(max_norm_bits, __float_as_uint(sqrtf(best) * 1.000001f));   // non-negative floats order like their bits
+}
+
+__global__ void copy_f32_kernel(const void *in, int in_dtype, int64_t rows, int64_t dim, int64_t ld, float *out) {
+    const int64_t total = rows * dim;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / dim, c = i - r * dim;
+        float v;
+        if (in_dtype == VS_F32) v = ((const float *)in)[r * ld + c];
+        else if (in_dtype == VS_F16) v = __half2float(((const __half *)in)[r * ld + c]);
+        else v = __bfloat162float(((const __nv_bfloat16 *)in)[r * ld + c]);
+        out[i] = v;
+    }
+}
+
+__device__ __forceinline__ float load_q(const void *q, int dtype, int64_t i) {
+    if (dtype == VS_F32) return ((const float *)q)[i];
+    if (dtype == VS_F16) return __half2float(((const __half *)q)[i]);
+    return __bfloat162float(((const __nv_bfloat16 *)q)[i]);
+}
+
+// one block per query: threshold key of the superset sweep = (k-th best bf16 score - 2E, lowest rank for that score)
+__global__ void dense_relax_kernel(const uint64_t *sorted_keys, int k, const void *q, int q_dtype, int64_t ldq, int64_t dim,
+                                   float max_norm, uint64_t *tau, uint32_t *cnt) {
+    __shared__ float s_part[8];
+    const int64_t b = blockIdx.x;
+    float s = 0.f;
+    for (int64_t c = threadIdx.x; c < dim; c += blockDim.x) { const float v = load_q(q, q_dtype, b * ldq + c); s = fmaf(v, v, s); }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += s_part[i];
+        const float E = kBf16PairErr * sqrtf(tot) * 1.000001f * max_norm;
+        const uint64_t kth = sorted_keys[b * k + (k - 1)];
+        // fewer than k rows in the index cannot happen (k <= N is checked); kth == 0 would mean an empty list
+        const float thr = kth ? key_score(kth) - 2.0f * E : -INFINITY;
+        // the sweep appends keys > tau: take the predecessor of the lowest key with score `thr`
+        tau[b] = make_key(thr, 0xffffffffu) - 1ull;
+        cnt[b] = 0u;
+    }
+}
+
+// exact fp32 scores of the candidates: one warp per (query, candidate), the candidate's fp32 row gathered from HBM
+__global__ void __launch_bounds__(256) dense_rescore_kernel(const float *x32, int64_t dim, const void *q, int q_dtype, int64_t ldq,
+                                                            uint64_t *cand, const uint32_t *cnt, int64_t cap) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = blockIdx.x;
+    const uint32_t n = min(cnt[b], (uint32_t)cap);
+    for (uint32_t j = blockIdx.y * 8 + (threadIdx.x >> 5); j < n; j += gridDim.y * 8) {
+        const uint32_t id = key_id(cand[b * cap + j]);
+        const float *row = x32 + (int64_t)id * dim;
+        float s = 0.f;
+        for (int64_t c = lane; c < dim; c += 32) s = fmaf(load_q(q, q_dtype, b * ldq + c), row[c], s);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) cand[b * cap + j] = make_key(s, id);
+    }
+}
+
 static PFN_cuTensorMapEncodeTiled get_encode_fn() {
     static PFN_cuTensorMapEncodeTiled fn = nullptr;
     if (!fn) {
@@ -587,15 +668,31 @@ int build_dense_index(vs_index *idx, const void *d_x, int x_dtype, int64_t ld, c
     idx->d_pad = (idx->dim + kBK - 1) / kBK * kBK;
     idx->n_pad = (idx->n_rows + kBN - 1) / kBN * kBN;
     if (idx->n_pad == 0) idx->n_pad = kBN;
+    idx->mma_dtype = idx->store_dtype == VS_F32 ? VS_BF16 : idx->store_dtype;   // what the tensor cores read
     VS_CUDA(cudaMalloc(&idx->dense, (size_t)idx->n_pad * idx->d_pad * 2));
     dense_convert_kernel<<<2048, 256, 0, st>>>(d_x, x_dtype, idx->n_rows, idx->dim, ld, (uint16_t *)idx->dense,
-                                               idx->store_dtype, idx->n_pad, idx->d_pad);
+                                               idx->mma_dtype, idx->n_pad, idx->d_pad);
     VS_CUDA(cudaGetLastError());
+    idx->device_bytes = idx->n_pad * idx->d_pad * 2;
+    if (idx->store_dtype == VS_F32) {   // fp32 semantics: the exact rows for the re-score, and the largest row norm
+        unsigned int *d_bits = nullptr;
+        VS_CUDA(cudaMalloc(&idx->dense32, idx->n_rows ? (size_t)idx->n_rows * idx->dim * 4 : 16));
+        VS_CUDA(cudaMalloc(&d_bits, 4));
+        VS_CUDA(cudaMemsetAsync(d_bits, 0, 4, st));
+        copy_f32_kernel<<<2048, 256, 0, st>>>(d_x, x_dtype, idx->n_rows, idx->dim, ld, idx->dense32);
+        row_norm_max_kernel<<<1024, 256, 0, st>>>(idx->dense32, idx->n_rows, idx->dim, d_bits);
+        unsigned int h_bits = 0;
+        cudaError_t e = cudaMemcpyAsync(&h_bits, d_bits, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(d_bits);
+        VS_CUDA(e);
+        memcpy(&idx->max_row_norm, &h_bits, 4);
+        idx->device_bytes += idx->n_rows * idx->dim * 4;
+    }
     VS_CUDA(cudaStreamSynchronize(st));
     cudaDeviceProp prop;
     VS_CUDA(cudaGetDeviceProperties(&prop, idx->device));
     idx->n_ctas = prop.multiProcessorCount;
-    idx->device_bytes = idx->n_pad * idx->d_pad * 2;
     idx->stream_bytes = idx->device_bytes;
     return VS_OK;
 }
@@ -686,11 +783,18 @@ int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t
                  int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, void *d_ws, cudaStream_t st) {
     VS_REQUIRE(idx->n_rows + id_offset < 0xffffffffll, VS_ERR_UNSUPPORTED, "global ids must fit 32 bits");
     CUtensorMap tx, tx_half;
-    int rc = make_tmap(&tx, idx->dense, idx->store_dtype, idx->n_pad, idx->d_pad, kBN);
+    int rc = make_tmap(&tx, idx->dense, idx->mma_dtype, idx->n_pad, idx->d_pad, kBN);
     if (rc) return rc;
-    rc = make_tmap(&tx_half, idx->dense, idx->store_dtype, idx->n_pad, idx->d_pad, kBN / 2);   // CTA-pair kernel: B halves
+    rc = make_tmap(&tx_half, idx->dense, idx->mma_dtype, idx->n_pad, idx->d_pad, kBN / 2);   // CTA-pair kernel: B halves
     if (rc) return rc;
-    const uint32_t fmt = idx->store_dtype == VS_F16 ? 0u : 1u;
+    const uint32_t fmt = idx->mma_dtype == VS_F16 ? 0u : 1u;
+    const bool exact32 = idx->store_dtype == VS_F32;   // bf16 sweep -> superset with an error margin -> exact fp32 re-score
+    // in that mode the bf16 pipeline below delivers its top-k as keys (local ids) into w.tau_sorted
+    int64_t *const out_ids = d_ids;
+    float *const out_scores = d_scores;
+    uint64_t *const out_keys = d_keys;
+    const int64_t out_offset = id_offset;
+    if (exact32) { d_ids = nullptr; d_scores = nullptr; id_offset = 0; score_round = VS_F32; }
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     void *ws_base = (void *)(((uintptr_t)d_ws + 1023) / 1024 * 1024);
     for (int64_t b0 = 0; b0 < B; b0 += kDenseQueryChunk) {
@@ -698,10 +802,40 @@ int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t
         const int64_t b_pad = (Bc + 2 * kBM - 1) / (2 * kBM) * (2 * kBM);
         DenseWs w = carve_dense(idx, ws_base, Bc, k);
         const uint8_t *qsrc = (const uint8_t *)d_q + (size_t)b0 * ldq * (q_dtype == VS_F32 ? 4 : 2);
-        dense_convert_kernel<<<1024, 256, 0, st>>>(qsrc, q_dtype, Bc, idx->dim, ldq, w.q16, idx->store_dtype, b_pad, idx->d_pad);
+        dense_convert_kernel<<<1024, 256, 0, st>>>(qsrc, q_dtype, Bc, idx->dim, ldq, w.q16, idx->mma_dtype, b_pad, idx->d_pad);
         CUtensorMap tq;
-        rc = make_tmap(&tq, w.q16, idx->store_dtype, b_pad, idx->d_pad, kBM);
+        rc = make_tmap(&tq, w.q16, idx->mma_dtype, b_pad, idx->d_pad, kBM);
         if (rc) return rc;
+        if (exact32) d_keys = w.tau_sorted - b0 * k;   // (the merges below write d_keys + b0 * k)
+        // ---- fp32 storage: superset sweep + exact re-score, run after the bf16 top-k of this chunk is in w.tau_sorted
+        auto finish_exact32 = [&]() -> int {
+            dense_relax_kernel<<<(unsigned)Bc, 256, 0, st>>>(w.tau_sorted, k, qsrc, q_dtype, ldq, idx->dim, idx->max_row_norm, w.tau, w.cnt);
+            DenseArgs e = {};
+            e.n_tiles_m = (int)((Bc + kBM - 1) / kBM);
+            e.k_blocks = (int)(idx->d_pad / kBK);
+            e.n_rows = idx->n_rows; e.n_queries = Bc; e.row_offset = 0;
+            e.score_round = VS_F32; e.idesc = idesc;
+            e.sample_keys = w.sample; e.sample_ld = 0; e.tau = w.tau; e.cand = w.cand; e.cand_cnt = w.cnt; e.cand_cap = kDenseCandCap;
+            e.work_counter = w.work_counter; e.dbg = 0;
+            e.mode = 1; e.n_tiles_n = (int)(idx->n_pad / kBN);
+            int r2 = launch_dense(idx, tq, tx, tx_half, e, st);
+            if (r2) return r2;
+            std::vector<uint32_t> h_cnt((size_t)Bc);
+            VS_CUDA(cudaMemcpyAsync(h_cnt.data(), w.cnt, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
+            VS_CUDA(cudaStreamSynchronize(st));
+            uint32_t mx = 0;
+            for (int64_t i = 0; i < Bc; ++i) mx = h_cnt[i] > mx ? h_cnt[i] : mx;
+            VS_REQUIRE(mx <= (uint32_t)kDenseCandCap, VS_ERR_UNSUPPORTED,
+                       "fp32 dense search: %u passages lie within the bf16 error bound of a query's k-th score (limit %lld)", mx,
+                       (long long)kDenseCandCap);
+            unsigned gy = (mx + 7) / 8;
+            gy = gy < 1 ? 1 : (gy > 64 ? 64 : gy);
+            dense_rescore_kernel<<<dim3((unsigned)Bc, gy), 256, 0, st>>>(idx->dense32, idx->dim, qsrc, q_dtype, ldq, w.cand, w.cnt, kDenseCandCap);
+            VS_CUDA(cudaGetLastError());
+            return launch_merge_counted(w.cand, w.cnt, 1, 0, kDenseCandCap, Bc, (int)kDenseCandCap, k, out_offset,
+                                        out_ids ? out_ids + b0 * k : nullptr, out_scores ? out_scores + b0 * k : nullptr,
+                                        out_keys ? out_keys + b0 * k : nullptr, st);
+        };
         DenseArgs a;
         a.n_tiles_m = (int)((Bc + kBM - 1) / kBM);
         a.k_blocks = (int)(idx->d_pad / kBK);
@@ -725,6 +859,7 @@ int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t
             rc = launch_merge(w.sample, 1, 0, s1, Bc, (int)s1, k, id_offset, d_ids ? d_ids + b0 * k : nullptr,
                               d_scores ? d_scores + b0 * k : nullptr, d_keys ? d_keys + b0 * k : nullptr, st);
             if (rc) return rc;
+            if (exact32 && (rc = finish_exact32()) != VS_OK) return rc;
             continue;
         }
         rc = launch_merge(w.sample, 1, 0, s1, Bc, (int)s1, k, 0, nullptr, nullptr, w.tau_sorted, st);
@@ -771,6 +906,7 @@ int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t
                                   d_ids ? d_ids + b0 * k : nullptr, d_scores ? d_scores + b0 * k : nullptr,
                                   d_keys ? d_keys + b0 * k : nullptr, st);
         if (rc) return rc;
+        if (exact32 && (rc = finish_exact32()) != VS_OK) return rc;
     }
     return VS_OK;
 }

@@ -70,6 +70,9 @@ struct vs_index {
     // ---- dense
     int64_t dim = 0, d_pad = 0, n_pad = 0;   // logical width; width / rows padded to the GEMM tile
     void *dense = nullptr;                   // [n_pad, d_pad] bf16 or fp16, K-major
+    int mma_dtype = VS_BF16;                 // dtype of `dense` (store_dtype, or bf16 when the index keeps fp32 semantics)
+    float *dense32 = nullptr;                // store_dtype == VS_F32: the exact rows [n_rows, dim] for the re-score
+    float max_row_norm = 0.f;                // ... and the largest row L2 norm (error bound of the bf16 sweep)
 
     int64_t device_bytes = 0;
     int64_t stream_bytes = 0;

@@ -440,13 +440,11 @@ class Index:
         v = self._vector
         if v.layout != torch.strided:
             raise TypeError("the dense Index needs a strided [N, D] vector; use SparseIndex / BoTIndex for CSR")
-        if v.dtype not in (torch.float16, torch.bfloat16):
-            # upstream's Index(fp16=False) searches an fp32 [N, D] matrix with an fp32 GEMM (index.py:36-44, 88-94).  The
-            # tcgen05 kernel stores bf16 / fp16 operands; narrowing an fp32 vector behind the caller's back would change
-            # near-tie ranks and scores, so it is refused until an fp32-accurate path exists.
-            raise NotImplementedError(
-                f"the dense index searches bf16 / fp16 vectors on the tensor cores; got {v.dtype}. Convert explicitly "
-                "(vector.to(torch.bfloat16) or Index(fp16=True)) to accept half-precision storage")
+        if v.dtype not in (torch.float16, torch.bfloat16, torch.float32):
+            v = v.to(torch.float32)
+        # bf16 / fp16 vectors are scored as they are on the tensor cores.  An fp32 vector (upstream's Index(fp16=False):
+        # an fp32 GEMM, index.py:36-44, 88-94) keeps fp32 semantics: the tensor cores sweep a bf16 copy, every passage
+        # within the bf16 error bound of the k-th score is re-scored exactly from its fp32 row (csrc/dense.cu).
         self._engine = _Engine.from_dense(v.to(dev), dev, v.dtype)
 
     def _require_engine(self) -> _Engine:
