@@ -473,11 +473,11 @@ def sparse_extra(ctx, name, batches):
             m["mode_used"] = used
             m["e2e"].update({"h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": bq * K_CFG3 * 12})
             if used == "scan":
-                kms = m["kernel_ms_per_launch"]
-                ach = bq * bytes_pass / (kms * 1e-3) / 1e9 if kms > 0 else None
+                kms, launches = m["kernel_ms_per_launch"], max(1.0, m["kernel_launches_per_step"])   # the ABI cuts large batches
+                ach = bq * bytes_pass / launches / (kms * 1e-3) / 1e9 if kms > 0 else None
                 m["roofline"] = {"bound": "hbm", "achieved": ach, "peak": ctx.peaks["hbm"], "unit": "GB/s",
                                  "frac": ach / ctx.peaks["hbm"] if ach else None, "traffic": None,
-                                 "kernel": "vs::scan_topk_kernel<1, 2, 0, 0, 0>", "algorithmic_bytes_per_launch": bq * bytes_pass,
+                                 "kernel": "vs::scan_topk_kernel<1, 2, 0, 0, 0>", "algorithmic_bytes_per_launch": bq * bytes_pass / launches,
                                  "peak_source": ctx.peaks["src"] + " hbm_gbs"}
             res[mode] = m
         out[f"{name}_b{bq}"] = res

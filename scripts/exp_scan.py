@@ -91,7 +91,9 @@ if args.prof and index.last_mode() == "inverted":
     nat.check(nat.LIB.vs_debug_scan_profile(eng.handle, None))
     t = buf.view(args.batch, n_ctas, 8).double() / 1e3   # us per (query, CTA)
     names = ["setup", "zero", "accumulate", "first_block_histogram", "block_select", "refresh_compact", "final_write", "total"]
-    out["phases_us_per_query_cta"] = {n: round(float(t[:, :, i].mean()), 2) for i, n in enumerate(names)}
+    live = t[:, :, 7].sum(dim=0) > 0   # CTAs that own row blocks (a small index launches fewer than n_ctas)
+    out["phases_us_per_query_cta"] = {n: round(float(t[:, live, i].mean()), 2) for i, n in enumerate(names)}
+    out["ctas_per_query"] = int(live.sum())
 wf = torch.zeros(2, dtype=torch.int64, device=dev)
 nat.check(nat.LIB.vs_debug_gather_wavefronts(eng.handle, ctypes.c_void_p(wf.data_ptr()), None))
 torch.cuda.synchronize()

@@ -37,7 +37,8 @@ constexpr int kInvWarps = kInvThreads / 32;
 constexpr int kInvBuildThreads = 1024;
 constexpr int kMaxQueryNnz = 4096;    // queries denser than this are served by the scan kernels
 constexpr int kBlockRowsMax = 37120;  // accumulator rows per block: 145 KB of the 227 KB
-constexpr int kInvAppend = 5120;      // keys in the CTA-wide append region (>= one replay step of kInvThreads * 4 rows)
+constexpr int kInvAppend = 4096;      // keys in the CTA-wide append region (>= one replay step of kInvThreads * 4 rows)
+constexpr int kInvQueue = 64;         // per-warp queue of accumulator float4s that passed the pre-filter (drained 32 at a time)
 static_assert(kInvAppend >= kInvThreads * 4, "a replay step must fit the append region");
 constexpr int kTokTile = 512;         // query tokens staged per pass over a block
 
@@ -361,7 +362,10 @@ struct InvSearchParams {
     int64_t n_rows;
     uint64_t *cand;      // [B, gridDim.x, cand_stride]: up to kout keys per list, zero padded
     int k, kout, score_round, cand_stride;
-    int flags;           // experiment switches (VSEARCH_B200_K3_FLAGS): 2 = L2 prefetch of the next block's lists
+    int n_queries;
+    int n_lists;         // candidate lists per query the merge reads (= CTAs of the scan grid); this kernel's grid may be
+                         // narrower (only CTAs that own row blocks are launched) and zero-fills the lists nobody writes
+    int flags;           // experiment switch (VSEARCH_B200_K3_FLAGS): 2 = L2 prefetch of the next block's lists
     const int *use_inv;  // device flag written by inv_decide_kernel: 0 = the scan serves this chunk, this kernel exits
     unsigned long long *prof;   // diagnostic (vs_debug_scan_profile): per (query, CTA) nanoseconds spent per phase, or nullptr
 };
@@ -408,11 +412,12 @@ __device__ __forceinline__ void hist_count_plain(uint32_t *coarse, uint32_t *fin
 
 constexpr uint32_t kLongList = 1024;   // postings; longer (block, token) lists are shared by all warps of the CTA
 
-// Add w * value at every posting of one list slice: offsets begin, begin + stride, ... < end; kInvUnroll loads in
-// flight per lane.  All lanes of a warp work on the SAME list, so their rows are distinct (no intra-warp conflicts)
-// and the token's weight / list start are warp-uniform registers.
-__device__ __forceinline__ void accumulate_slice(float *acc, const uint16_t *rows, const void *vals, int val_kind,
-                                                 uint64_t pos0, uint32_t begin, uint32_t end, uint32_t stride, float w) {
+// Add w * value at every posting of one list slice: offsets begin, begin + stride, ... < end of the list at `rows`
+// (`vals`: its values, in the index dtype); kInvUnroll loads in flight per lane.  All lanes of a warp work on the SAME
+// list, so their rows are distinct (no intra-warp conflicts) and the token's weight / list start are warp-uniform.
+template <int VK>
+__device__ __forceinline__ void accumulate_slice(float *acc, const uint16_t *__restrict__ rows, const void *__restrict__ vals,
+                                                 uint32_t begin, uint32_t end, uint32_t stride, float w) {
     for (uint32_t off = begin; off < end; off += stride * kInvUnroll) {
         uint32_t row[kInvUnroll];
         float v[kInvUnroll];
@@ -422,8 +427,10 @@ __device__ __forceinline__ void accumulate_slice(float *acc, const uint16_t *row
             row[u] = 0xffffffffu;
             v[u] = w;
             if (o < end) {
-                row[u] = rows[pos0 + o];
-                if (val_kind) v[u] *= posting_value(vals, val_kind, pos0 + o);
+                row[u] = rows[o];
+                if constexpr (VK == 1) v[u] *= ((const float *)vals)[o];
+                else if constexpr (VK == 2) v[u] *= __half2float(((const __half *)vals)[o]);
+                else if constexpr (VK == 3) v[u] *= __bfloat162float(((const __nv_bfloat16 *)vals)[o]);
             }
         }
 #pragma unroll
@@ -432,8 +439,28 @@ __device__ __forceinline__ void accumulate_slice(float *acc, const uint16_t *row
     }
 }
 
+// Drop the keys of the append region that fell below the histogram bound `ob` (ordered score bits): called by all
+// threads of the CTA with the same (n_app, ob), nobody appending meanwhile.  Ends with a barrier.
+static __device__ __noinline__ void compact_appended(uint64_t *app, CtaState *st, const uint32_t n_app, const uint32_t ob) {
+    constexpr int NT = kInvThreads, PER = (kInvAppend + NT - 1) / NT;
+    const int tid = threadIdx.x;
+    uint64_t keep[PER];
+    const uint64_t tmin = (uint64_t)ob << 32;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { const int i = tid + j * NT; keep[j] = (i < (int)n_app) ? app[i] : 0ull; }
+    __syncthreads();
+    if (tid == 0) st->n_app = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        if (keep[j] != 0ull && keep[j] >= tmin) app[atom_shared_add(&st->n_app, 1u)] = keep[j];
+    __syncthreads();
+}
+
+template <int VK, bool ROUND>
 __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSearchParams p) {
     constexpr int NT = kInvThreads, NW = kInvWarps;
+    constexpr int vbytes = VK == 0 ? 0 : (VK == 1 ? 4 : 2);
     extern __shared__ __align__(128) uint8_t ssmem[];
     // the score histogram and the exact fallback's shared top-k set share their memory: a query that has to fall back
     // to exact CTA-wide selections (masses of equal scores, adversarial row order) stops using the histogram
@@ -446,19 +473,22 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     float *s_w = reinterpret_cast<float *>(s_tok + kTokTile);
     uint32_t *s_beg = reinterpret_cast<uint32_t *>(s_w + kTokTile);
     uint32_t *s_len = s_beg + kTokTile;
-    float *acc = reinterpret_cast<float *>(s_len + kTokTile);                   // rows_per_block
+    uint16_t *s_queue = reinterpret_cast<uint16_t *>(s_len + kTokTile);         // kInvWarps x kInvQueue
+    float *acc = reinterpret_cast<float *>(s_queue + kInvWarps * kInvQueue);    // rows_per_block
     __shared__ CtaState st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (*p.use_inv == 0) return;
-    const int q = blockIdx.y;
+    // persistent over the queries: CTA (x, y) scores queries y, y + gridDim.y, ... against its row blocks (a fresh CTA
+    // with 227 KB of shared memory per (query, block group) left the SMs idle half the time on a 71-block shard)
+    for (int q = blockIdx.y; q < p.n_queries; q += gridDim.y) {
     const int cnt = (int)min(p.L.cnt[q], (uint32_t)kMaxQueryNnz);
     const uint32_t *tok = p.L.tok + (size_t)q * kMaxQueryNnz;
     const float *w = p.L.w + (size_t)q * kMaxQueryNnz;
     const int R = p.rows_per_block;
     const int blk0 = blockIdx.x * p.blocks_per_cta, blk1 = min(p.n_blocks, blk0 + p.blocks_per_cta);
     const bool cached = cnt <= kTokTile;   // the whole token list stays in shared memory across blocks
-    const int vbytes = p.val_kind == 0 ? 0 : (p.val_kind == 1 ? 4 : 2);
     const size_t nb = (size_t)p.n_blocks;
+    __shared__ uint32_t s_ob;
     InvProf prof;
     prof.start(p.prof != nullptr && tid == 0);
     if (tid == 0) cta_state_reset(&st);
@@ -475,41 +505,84 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     bool booted = false;                   // the CTA's first block has set the pre-filter
     bool exact = false;                    // exact fallback engaged: histogram memory now holds the shared top-k set
 
-    // one pass over rows [r_begin, rows_b) of the block's accumulator: rows at or above the pre-filter (and above the exact
-    // threshold, if any) are counted in the histogram (rows >= count_from only) and appended.  STEP = rows per thread.
-    auto select_rows = [&](const int rb, const int rows_b, const int64_t row0, const uint64_t tau, const int count_from) {
-        const int r = rb + tid * 4;
-        if (r < rows_b) {
-            const float4 v = acc4[r >> 2];
-            const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-            if (round_score(mx, p.score_round) >= tau_s) {   // rounding is monotonic
-                const float sc[4] = {v.x, v.y, v.z, v.w};
-                uint64_t key[4];
-                uint32_t n = 0;
+    auto rnd = [&](float x) -> float { if constexpr (ROUND) return round_score(x, p.score_round); else return x; };
+    // The slow path of the select, for up to 32 accumulator float4s at once (lane < n_q takes queue entry `lane`): rows at
+    // or above the pre-filter and above the exact threshold (if any) are counted in the histogram (rows >= count_from
+    // only) and appended -- one ATOMS.ADD per warp for the slots.  Called by all 32 lanes.
+    auto take_rows = [&](const uint16_t *qw, const int n_q, const int rows_b, const int64_t row0, const uint64_t tau, const int count_from) {
+        uint64_t key[4] = {0ull, 0ull, 0ull, 0ull};
+        uint32_t n = 0;
+        if (lane < n_q) {
+            const int i = qw[lane], r = i * 4;
+            const float4 v = acc4[i];
+            const float sc[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float se = round_score(sc[e], p.score_round);
-                    key[e] = 0ull;
-                    if (r + e < rows_b && se >= tau_s) {
-                        const uint64_t ke = make_key(se, (uint32_t)(row0 + r + e));
-                        if (ke > tau) {
-                            key[e] = ke; ++n;
-                            if (!exact && r + e >= count_from) hist_count_plain(coarse, fine, (uint32_t)(ke >> 32));
-                        }
+            for (int e = 0; e < 4; ++e) {
+                const float se = rnd(sc[e]);
+                if (r + e < rows_b && se >= tau_s) {
+                    const uint64_t ke = make_key(se, (uint32_t)(row0 + r + e));
+                    if (ke > tau) {
+                        key[e] = ke; ++n;
+                        if (!exact && r + e >= count_from) hist_count_plain(coarse, fine, (uint32_t)(ke >> 32));
                     }
-                }
-                if (n) {
-                    uint32_t slot = atom_shared_add(&st.n_app, n);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (key[e] != 0ull) { if (slot < (uint32_t)kInvAppend) app[slot] = key[e]; ++slot; }
                 }
             }
         }
+        uint32_t incl = n;   // slots: exclusive prefix over the lanes, one atomic for the warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) return;
+        uint32_t base_slot = 0;
+        if (lane == 0) base_slot = atom_shared_add(&st.n_app, total);
+        uint32_t slot = __shfl_sync(0xffffffffu, base_slot, 0) + incl - n;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (key[e] != 0ull) { if (slot < (uint32_t)kInvAppend) app[slot] = key[e]; ++slot; }
     };
-    // raise the pre-filter to the histogram's k-th bucket (all warps compute the same bound)
+    // float4 indices [i_lo, i_hi) of the block's accumulator through the pre-filter: the loop the select spends its time in.
+    // Hits (one float4 in ~60 at best, so some lane of most warp iterations has one) are not handled where they occur --
+    // a divergent slow path per hit -- but queued per warp and taken 32 at a time with all lanes busy.
+    auto select_range = [&](const int i_lo, const int i_hi, const int rows_b, const int64_t row0, const uint64_t tau, const int count_from) {
+        uint16_t *qw = s_queue + warp * kInvQueue;
+        int qn = 0;
+        for (int i0 = i_lo; i0 < i_hi; i0 += NT) {
+            const int i = i0 + tid;
+            bool hit = false;
+            if (i < i_hi) {
+                const float4 v = acc4[i];
+                hit = rnd(fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w))) >= tau_s;   // rounding is monotonic
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                if (hit) qw[qn + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+                qn += __popc(m);
+                if (qn >= 32) {
+                    __syncwarp();
+                    take_rows(qw, 32, rows_b, row0, tau, count_from);
+                    const uint16_t rest = lane < qn - 32 ? qw[32 + lane] : (uint16_t)0;
+                    __syncwarp();
+                    if (lane < qn - 32) qw[lane] = rest;
+                    qn -= 32;
+                }
+            }
+        }
+        if (qn) { __syncwarp(); take_rows(qw, qn, rows_b, row0, tau, count_from); __syncwarp(); }
+    };
+    // raise the pre-filter to the histogram's k-th bucket: one warp asks the histogram, everybody reads the answer.
+    // Called by all threads; a barrier before the call makes the counts of the rows processed so far visible.
+    uint32_t n_app_seen = 0;   // the append count at the last refresh (the same value in every thread)
     auto refresh = [&]() -> uint32_t {
-        const uint32_t ob = hist_threshold(coarse, fine, p.k);
+        if (warp == 0) {
+            const uint32_t ob = hist_threshold(coarse, fine, p.k);
+            if (lane == 0) s_ob = ob;
+        }
+        n_app_seen = *(volatile uint32_t *)&st.n_app;   // nobody appends between the caller's barrier and this one
+        __syncthreads();
+        const uint32_t ob = s_ob;
         if (ob) tau_s = fmaxf(tau_s, key_score((uint64_t)ob << 32));
         return ob;
     };
@@ -547,7 +620,8 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                 const uint32_t len = s_len[ti];
                 if (len - 1u < kLongList) {
                     const uint32_t lo = (len * pc) >> psh, hi = (len * (pc + 1u)) >> psh;
-                    accumulate_slice(acc, p.post_row, p.post_val, p.val_kind, base + s_beg[ti], lo + lane, hi, 32u, s_w[ti]);
+                    const uint64_t at = base + s_beg[ti];
+                    accumulate_slice<VK>(acc, p.post_row + at, (const uint8_t *)p.post_val + at * vbytes, lo + lane, hi, 32u, s_w[ti]);
                 }
             }
             // long lists (heavy-tailed token popularity): every warp takes a share
@@ -556,8 +630,9 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                 uint32_t longm = __ballot_sync(0xffffffffu, ti_l < tn && s_len[ti_l] > kLongList);
                 for (; longm; longm &= longm - 1) {
                     const int ti = tb + __ffs(longm) - 1;
-                    accumulate_slice(acc, p.post_row, p.post_val, p.val_kind, base + s_beg[ti], (uint32_t)tid, s_len[ti],
-                                     (uint32_t)NT, s_w[ti]);
+                    const uint64_t at = base + s_beg[ti];
+                    accumulate_slice<VK>(acc, p.post_row + at, (const uint8_t *)p.post_val + at * vbytes, (uint32_t)tid, s_len[ti],
+                                         (uint32_t)NT, s_w[ti]);
                 }
             }
         }
@@ -600,28 +675,51 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
         // append region overflows (masses of equal scores, adversarial order) the query switches to the exact machinery:
         // the block is replayed in steps of NT*4 rows with a CTA-wide re-selection whenever the next step might not fit.
         const uint32_t app0 = *(volatile uint32_t *)&st.n_app;
-        for (;;) {
-            uint64_t tau = *(volatile uint64_t *)&st.tau;   // exact k-th key of the last re-selection (0: none yet)
-            int it = 0;
-            for (int rb = 0; rb < rows_b; rb += NT * 4, ++it) {
-                if (exact) {
-                    // the thread that appended last reads the final count, so the OR is exact
-                    if (__syncthreads_or(*(volatile uint32_t *)&st.n_app + NT * 4 > (uint32_t)kInvAppend)) {
-                        cta_join_flat<NT, kInvAppend>(shset, app, p.k, hist, &st);
-                        tau_s = fmaxf(tau_s, gate_tau_score(gate_load(&st)));
-                        tau = *(volatile uint64_t *)&st.tau;
+        const int n4 = (rows_b + 3) >> 2;   // float4s of the block's accumulator (the tail beyond rows_b is masked in take_rows)
+        if (!exact) {
+            const uint64_t tau = *(volatile uint64_t *)&st.tau;
+            if (!booted) {   // the pre-filter of the first block tightens as its rows are counted: after NT*4, 3x and 7x that many
+                // (small k: the first refresh already leaves few enough survivors for the append region, and every
+                // refresh costs two barriers; large k needs the tighter bounds, and drops what fell below them whenever
+                // the region is half full, to stay out of the exact fallback)
+                const bool more = p.k > 128;
+                int i_done = min(n4, NT);
+                select_range(0, i_done, rows_b, row0, tau, count_from);
+#pragma unroll 1
+                for (int i_next = 3 * NT; i_done < n4; i_next = 2 * i_next + NT) {
+                    if (more || i_done == NT) {
+                        __syncthreads();
+                        const uint32_t ob = refresh();
+                        // (a count beyond the region is an overflow: left alone, the check after the block sees it)
+                        if (n_app_seen > (uint32_t)(kInvAppend / 2) && n_app_seen <= (uint32_t)kInvAppend && ob)
+                            compact_appended(app, &st, n_app_seen, ob);
                     }
-                } else if (!booted && (it == 1 || it == 3 || it == 7)) {
-                    __syncthreads();   // the pre-filter of the first block tightens as its rows are counted
-                    refresh();
+                    const int i_hi = (more || i_next < 7 * NT) ? min(n4, i_next) : n4;
+                    select_range(i_done, i_hi, rows_b, row0, tau, count_from);
+                    i_done = i_hi;
                 }
-                select_rows(rb, rows_b, row0, tau, count_from);
+            } else {
+                select_range(0, n4, rows_b, row0, tau, count_from);
             }
             __syncthreads();
-            if (exact || *(volatile uint32_t *)&st.n_app <= (uint32_t)kInvAppend) break;
-            __syncthreads();
-            if (tid == 0) { st.n_app = app0 <= (uint32_t)kInvAppend ? app0 : 0u; st.cnt = 0; }
-            exact = true;   // from here on the histogram memory holds the shared top-k set
+            if (*(volatile uint32_t *)&st.n_app > (uint32_t)kInvAppend) {   // overflow: drop this block's appends, go exact
+                __syncthreads();
+                if (tid == 0) { st.n_app = app0 <= (uint32_t)kInvAppend ? app0 : 0u; st.cnt = 0; }
+                exact = true;   // from here on the histogram memory holds the shared top-k set
+                __syncthreads();
+            }
+        }
+        if (exact) {   // replay / later blocks of an exact-mode query: steps of NT*4 rows, re-selections whenever a step might not fit
+            uint64_t tau = *(volatile uint64_t *)&st.tau;
+            for (int i0 = 0; i0 < n4; i0 += NT) {
+                // the thread that appended last reads the final count, so the OR is exact
+                if (__syncthreads_or(*(volatile uint32_t *)&st.n_app + NT * 4 > (uint32_t)kInvAppend)) {
+                    cta_join_flat<NT, kInvAppend>(shset, app, p.k, hist, &st);
+                    tau_s = fmaxf(tau_s, gate_tau_score(gate_load(&st)));
+                    tau = *(volatile uint64_t *)&st.tau;
+                }
+                select_range(i0, min(n4, i0 + NT), rows_b, row0, tau, count_from);
+            }
             __syncthreads();
         }
         booted = true;
@@ -629,20 +727,8 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
         // ---- raise the pre-filter for the next block; when the region is half full, drop what fell below it
         if (!exact && b + 1 < blk1) {
             const uint32_t ob = refresh();
-            const uint32_t n_app = *(volatile uint32_t *)&st.n_app;
-            if (n_app > (uint32_t)(kInvAppend / 2)) {
-                constexpr int PER = (kInvAppend + NT - 1) / NT;
-                uint64_t keep[PER];
-                const uint64_t tmin = (uint64_t)ob << 32;
-#pragma unroll
-                for (int j = 0; j < PER; ++j) { const int i = tid + j * NT; keep[j] = (i < (int)n_app) ? app[i] : 0ull; }
-                __syncthreads();
-                if (tid == 0) st.n_app = 0;
-                __syncthreads();
-#pragma unroll
-                for (int j = 0; j < PER; ++j)
-                    if (keep[j] != 0ull && keep[j] >= tmin) app[atom_shared_add(&st.n_app, 1u)] = keep[j];
-                __syncthreads();
+            if (n_app_seen > (uint32_t)(kInvAppend / 2)) {
+                compact_appended(app, &st, n_app_seen, ob);
                 if (*(volatile uint32_t *)&st.n_app > (uint32_t)(kInvAppend / 2)) {   // a bucket full of equal scores: go exact
                     if (tid == 0) st.cnt = 0;
                     exact = true;
@@ -661,12 +747,21 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     // ---- end of query: everything at or above the final histogram bound goes to the merge kernel (k .. kout keys);
     // more than kout (a bucket full of equal scores), or a query in exact mode -> the exact CTA-wide select
     {
-        uint64_t *out = p.cand + ((size_t)q * gridDim.x + blockIdx.x) * (size_t)p.cand_stride;
+        uint64_t *out = p.cand + ((size_t)q * p.n_lists + blockIdx.x) * (size_t)p.cand_stride;
+        for (int l = blockIdx.x + gridDim.x; l < p.n_lists; l += gridDim.x) {   // lists of CTAs that were not launched
+            uint64_t *z = p.cand + ((size_t)q * p.n_lists + l) * (size_t)p.cand_stride;
+            for (int i = tid; i < p.kout; i += NT) z[i] = 0ull;
+        }
         if (tid == 0) st.scratch = 0;
         __syncthreads();
         bool use_exact = exact;
         if (!exact) {
-            const uint64_t tmin = (uint64_t)hist_threshold(coarse, fine, p.k) << 32;
+            if (warp == 0) {
+                const uint32_t ob = hist_threshold(coarse, fine, p.k);
+                if (lane == 0) s_ob = ob;
+            }
+            __syncthreads();
+            const uint64_t tmin = (uint64_t)s_ob << 32;
             const int n_app = (int)min(*(volatile uint32_t *)&st.n_app, (uint32_t)kInvAppend);
             for (int i = tid; i < n_app; i += NT) {
                 const uint64_t x = app[i];
@@ -690,8 +785,11 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     if (prof.on) {
         prof.lap(6);
         prof.acc[7] = prof.t - prof.acc[7];
-        for (int i = 0; i < 8; ++i) p.prof[((size_t)q * gridDim.x + blockIdx.x) * 8 + i] = prof.acc[i];
+        for (int i = 0; i < 8; ++i) p.prof[((size_t)q * p.n_lists + blockIdx.x) * 8 + i] = prof.acc[i];
     }
+    __syncthreads();   // the next query resets the CTA state and the histogram
+
+    }   // queries
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -743,9 +841,8 @@ int launch_inverted(vs_index *idx, int64_t Bc, int k, int cand_stride, int score
     QueryLists L = carve_lists((uint8_t *)d_ws, Bc, &end);
     static_assert(kHistFine * 4 >= kSharedKeys * 8, "the exact fallback's top-k set lives in the histogram's memory");
     const size_t smem = (size_t)(kHistFine + kHistCoarse + 256) * 4 + (size_t)kInvAppend * 8 + (size_t)kTokTile * 4 * 4 +
-                        (size_t)idx->blk_rows * 4;
+                        (size_t)kInvWarps * kInvQueue * 2 + (size_t)idx->blk_rows * 4;
     VS_REQUIRE(smem <= 227 * 1024, VS_ERR_UNSUPPORTED, "inverted-list search needs %zu bytes of shared memory", smem);
-    VS_CUDA(cudaFuncSetAttribute(inv_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     InvSearchParams p;
     p.L = L; p.blk_rng = (const uint2 *)idx->blk_ptr; p.blk_base = idx->blk_base; p.post_row = idx->post_row; p.post_val = idx->post_val;
     p.val_kind = idx->kind == 1 ? (idx->store_dtype == VS_F32 ? 1 : (idx->store_dtype == VS_F16 ? 2 : 3)) : 0;
@@ -755,9 +852,29 @@ int launch_inverted(vs_index *idx, int64_t Bc, int k, int cand_stride, int score
     p.flags = k3_flags;
     p.use_inv = d_flag;
     p.prof = idx->scan_prof;
-    inv_search_kernel<<<dim3(idx->n_ctas, (unsigned)Bc), kInvThreads, smem, st>>>(p);
-    VS_CUDA(cudaGetLastError());
-    return VS_OK;
+    p.n_lists = idx->n_ctas;
+    p.n_queries = (int)Bc;
+    // a CTA with 227 KB of shared memory costs microseconds to launch even when it owns no row block (a shard of 71
+    // blocks on 148 SMs spent half its time there): launch only the CTAs that have blocks
+    const unsigned grid_x = (unsigned)((idx->n_blocks + idx->blocks_per_cta - 1) / idx->blocks_per_cta);
+    auto launch = [&](auto kern) -> int {
+        VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // grid: every CTA that owns row blocks, times as many query lanes as fit the SMs in ONE wave
+        static const int k3_waves = getenv("VSEARCH_B200_K3_GRIDY") ? atoi(getenv("VSEARCH_B200_K3_GRIDY")) : 0;
+        unsigned grid_y = k3_waves > 0 ? (unsigned)k3_waves : (unsigned)(idx->n_ctas / grid_x);
+        if (grid_y < 1) grid_y = 1;
+        if (grid_y > (unsigned)Bc) grid_y = (unsigned)Bc;
+        kern<<<dim3(grid_x, grid_y), kInvThreads, smem, st>>>(p);
+        VS_CUDA(cudaGetLastError());
+        return VS_OK;
+    };
+    const bool rnd = score_round != VS_F32;
+    switch (p.val_kind) {
+        case 0: return rnd ? launch(inv_search_kernel<0, true>) : launch(inv_search_kernel<0, false>);
+        case 1: return rnd ? launch(inv_search_kernel<1, true>) : launch(inv_search_kernel<1, false>);
+        case 2: return rnd ? launch(inv_search_kernel<2, true>) : launch(inv_search_kernel<2, false>);
+        default: return rnd ? launch(inv_search_kernel<3, true>) : launch(inv_search_kernel<3, false>);
+    }
 }
 
 }  // namespace vs
