@@ -164,7 +164,10 @@ int vs_kernel_timer(vs_index *idx, int reset, float *total_ms, int *launches);
 /* Diagnostic: while d_buf != NULL the binary scan kernel (K2) stores %globaltimer at its phase boundaries,
  * d_buf[(cta * B + query) * 8 + slot] (slots: 0 pass start, 1 query vector staged, 2 sampling streamed, 3 threshold
  * selected, 4 warp 0 finished streaming, 5 all warps finished, 6 top-k written); the buffer must hold
- * n_ctas * B * 8 entries for every search issued while it is set.  NULL switches it off. */
+ * n_ctas * B * 8 entries for every search issued while it is set.  The inverted-list kernel (K3) stores phase DURATIONS
+ * instead, d_buf[(query * n_ctas + cta) * 16 + slot] in ns (slots: 0 setup, 1 zero the accumulator, 2 accumulate, 3
+ * first-block histogram, 4 block select, 5 refresh/compact, 6 final write, 7 total, 8-10 the first block's select split
+ * into first rows / refreshes / rest), so the buffer must hold n_ctas * B * 16 entries there.  NULL switches it off. */
 int vs_debug_scan_profile(vs_index *idx, unsigned long long *d_buf);
 
 /* Diagnostic: what the bank-aware entry placement achieved on this sparse / binary index.  d_out2[0] = shared-memory

@@ -67,7 +67,7 @@ out = {"rows": args.rows, "batch": args.batch, "k": args.k, "mode": index.last_m
        "GBps_algorithmic": args.batch * bytes_pass / (kms * 1e-3) / 1e9, "qps": args.batch / (call_ms * 1e-3),
        "stream_bytes": eng.stream_bytes}
 if args.prof and index.last_mode() == "scan":
-    buf = torch.zeros(n_ctas * args.batch * 8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(n_ctas * args.batch * 16, dtype=torch.int64, device=dev)
     nat.check(nat.LIB.vs_debug_scan_profile(eng.handle, ctypes.c_void_p(buf.data_ptr())))
     index.search(q, args.k)
     torch.cuda.synchronize()
@@ -84,13 +84,14 @@ if args.prof and index.last_mode() == "scan":
     ph["pass_total_min_cta_mean"] = round(float(tot.mean(dim=1).min()), 2)
     out["phases_us"] = ph
 if args.prof and index.last_mode() == "inverted":
-    buf = torch.zeros(n_ctas * args.batch * 8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(n_ctas * args.batch * 16, dtype=torch.int64, device=dev)
     nat.check(nat.LIB.vs_debug_scan_profile(eng.handle, ctypes.c_void_p(buf.data_ptr())))
     index.search(q, args.k)
     torch.cuda.synchronize()
     nat.check(nat.LIB.vs_debug_scan_profile(eng.handle, None))
-    t = buf.view(args.batch, n_ctas, 8).double() / 1e3   # us per (query, CTA)
-    names = ["setup", "zero", "accumulate", "first_block_histogram", "block_select", "refresh_compact", "final_write", "total"]
+    t = buf.view(args.batch, n_ctas, 16).double() / 1e3   # us per (query, CTA)
+    names = ["setup", "zero", "accumulate", "first_block_histogram", "block_select", "refresh_compact", "final_write", "total",
+             "first_block_select_first_rows", "first_block_select_refreshes", "first_block_select_rest"]
     live = t[:, :, 7].sum(dim=0) > 0   # CTAs that own row blocks (a small index launches fewer than n_ctas)
     out["phases_us_per_query_cta"] = {n: round(float(t[:, live, i].mean()), 2) for i, n in enumerate(names)}
     out["ctas_per_query"] = int(live.sum())

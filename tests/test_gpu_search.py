@@ -302,6 +302,36 @@ def test_inverted_heavy_ties_and_continuous(cuda_device):
     assert msg is None, msg
 
 
+def test_inverted_binary_index_fixed_point_and_fp32_queries(cuda_device):
+    """K3 on a binary index accumulates in 32-bit fixed point when every query weight is positive and keeps >= 17 bits
+    under the scale of the weights' total (native integer shared-memory adds), in fp32 otherwise: grid weights must come
+    out bit-exact, continuous ones within the 1e-5 contract, and queries that cannot go to fixed point (a negative
+    weight, a 2^20 dynamic range) must take the fp32 path with the same guarantees -- all in one batch."""
+    n = 150_000
+    crow, col, val = stratified_csr(n, V, 60, seed=23, binary=True, jitter=30)
+    X = ref_search.torch_csr(crow, col, val, (n, V))
+    idx = _mk("BoTIndex", crow, col, val, (n, V))
+    idx.search_mode = "inverted"
+    q = sparse_queries(4, V, 64, seed=5)                         # multiples of 1/64: exact in either arithmetic
+    for k in (10, 300):
+        msg = ref_search.compare_results(idx.search(q, k), ref_search.ref_scores(q, X), k, exact=True)
+        assert msg is None, f"grid weights, k={k}: {msg}"
+    q = sparse_queries(6, V, 64, seed=6, grid=False)             # U(0.01, 3): fixed point
+    q[1] = sparse_queries(1, V, 64, seed=7, grid=False, neg=True)[0]      # mixed signs: fp32
+    nz = q[2].nonzero().flatten()
+    q[2, nz[0]] = 3.0e-6                                         # 2^20 below the largest weight: fp32
+    q[3] = sparse_queries(1, V, 500, seed=8, grid=False)[0]      # a long query, still one token tile
+    assert idx.last_mode() == "inverted"
+    for k in (10, 300):
+        res = idx.search(q, k)
+        msg = ref_search.compare_results(res, ref_search.ref_scores(q, X), k, rtol=1e-5)
+        assert msg is None, f"continuous weights, k={k}: {msg}"
+    # the same batch through the scan: same ids wherever the reference scores are not near-ties
+    idx.search_mode = "scan"
+    msg = ref_search.compare_results(idx.search(q, 300), ref_search.ref_scores(q, X), 300, rtol=1e-5)
+    assert msg is None, msg
+
+
 def test_inverted_ascending_scores_replay_path(cuda_device):
     """K3 worst case: scores increase with the row id, so after the sampling phase EVERY row beats the threshold;
     the optimistic whole-block pass overflows the append region and each block is replayed stepwise with joins.

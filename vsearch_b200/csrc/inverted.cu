@@ -208,7 +208,9 @@ struct QueryLists {
     uint32_t *pref;    // [B, kMaxQueryNnz + 1]
     uint32_t *cnt;     // [B]   number of non-zero tokens (may exceed kMaxQueryNnz: then lists are truncated, unusable)
     uint64_t *total;   // [B]   total postings of the query
+    int *fx;           // [B]   binary index: fixed-point exponent of the query's weights, or kNoFixed (inv_fixed_point_kernel)
 };
+constexpr int kNoFixed = 0x7fffffff;
 
 __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t *s_warp, uint32_t &block_total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -315,6 +317,29 @@ __global__ void __launch_bounds__(256) inv_lists_from_csr_kernel(const void *q_p
     }
 }
 
+// Binary index, all query weights positive: a row's score is a sum of query weights, bounded by their total.  The weights
+// go to 32-bit fixed point (scale 2^e, total <= 2^31) and K3's accumulator holds integers -- native shared-memory adds
+// instead of CAS loops -- when that is at least as exact as the 1e-5 contract asks: every weight keeps >= 17 bits below
+// its leading one, so each term, hence the sum, is within 2^-18 of its real value (the integer adds are exact; fp32
+// accumulation itself drifts by ~n * 2^-24).  Otherwise (fx = kNoFixed) the query is accumulated in fp32.  A warp per query.
+__global__ void __launch_bounds__(256) inv_fixed_point_kernel(QueryLists L, int Bc) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= Bc) return;
+    const uint32_t cnt = L.cnt[q];
+    const float *w = L.w + (size_t)q * kMaxQueryNnz;
+    float tot = 0.f, mn = INFINITY;
+    if (cnt <= (uint32_t)kTokTile)
+        for (uint32_t i = lane; i < cnt; i += 32) { const float x = w[i]; tot += x; mn = fminf(mn, x); }   // a NaN weight makes tot NaN
+    for (int d = 16; d; d >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, d); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d)); }
+    int e = kNoFixed;
+    if (cnt > 0 && cnt <= (uint32_t)kTokTile && mn > 0.f && tot < 1e30f && tot > 1e-30f) {
+        int x;
+        (void)frexpf(tot * 1.0001f, &x);      // tot (whatever the summation order) < 2^x
+        if (ldexpf(mn, 31 - x) >= 131072.f) e = 31 - x;
+    }
+    if (lane == 0) L.fx[q] = e;
+}
+
 // scan or inverted lists?  One CTA looks at the extracted queries of the chunk and writes the decision where the two
 // scoring kernels and the merge read it -- the host never waits for it.  mode: VS_MODE_AUTO applies the cost model
 // (seconds per query, constants measured on B200), VS_MODE_INVERTED takes the lists whenever they can serve the chunk
@@ -365,13 +390,15 @@ struct InvSearchParams {
     int n_queries;
     int n_lists;         // candidate lists per query the merge reads (= CTAs of the scan grid); this kernel's grid may be
                          // narrower (only CTAs that own row blocks are launched) and zero-fills the lists nobody writes
-    int flags;           // experiment switch (VSEARCH_B200_K3_FLAGS): 2 = L2 prefetch of the next block's lists
+    int flags;           // experiment switches (VSEARCH_B200_K3_FLAGS): 1 = L1 prefetch of a tile's list heads, 2 = L2 prefetch of the
+                         // next block's lists, 16 = no fixed-point accumulation on binary indices
     const int *use_inv;  // device flag written by inv_decide_kernel: 0 = the scan serves this chunk, this kernel exits
     unsigned long long *prof;   // diagnostic (vs_debug_scan_profile): per (query, CTA) nanoseconds spent per phase, or nullptr
 };
-// phases: 0 setup, 1 zero, 2 accumulate, 3 first-block histogram, 4 block select, 5 refresh / compaction, 6 final write, 7 total
+// phases: 0 setup, 1 zero, 2 accumulate, 3 first-block histogram, 4 block select, 5 refresh / compaction, 6 final write, 7 total,
+// 8-10 the first block's select: first rows / refreshes / rest
 struct InvProf {
-    unsigned long long t, acc[8];
+    unsigned long long t, acc[16];
     bool on;
     __device__ __forceinline__ static unsigned long long now() {
         unsigned long long t;
@@ -380,7 +407,7 @@ struct InvProf {
     }
     __device__ __forceinline__ void start(bool enabled) {
         on = enabled;
-        if (on) { for (int i = 0; i < 8; ++i) acc[i] = 0; t = now(); acc[7] = t; }
+        if (on) { for (int i = 0; i < 16; ++i) acc[i] = 0; t = now(); acc[7] = t; }
     }
     __device__ __forceinline__ void lap(int phase) {
         if (on) { const unsigned long long n = now(); acc[phase] += n - t; t = n; }
@@ -396,6 +423,7 @@ __device__ __forceinline__ float posting_value(const void *vals, int kind, uint6
 constexpr int kInvUnroll = 8;          // posting loads in flight per lane
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t atom_shared_add(uint32_t *p, uint32_t v) {  // plain ATOMS.ADD (no compiler-made warp aggregation)
     uint32_t old;
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
@@ -436,6 +464,24 @@ __device__ __forceinline__ void accumulate_slice(float *acc, const uint16_t *__r
 #pragma unroll
         for (int u = 0; u < kInvUnroll; ++u)
             if (row[u] != 0xffffffffu) atomicAdd(&acc[row[u]], v[u]);
+    }
+}
+
+// The same for a binary index whose query weights went to fixed point (see `fx` in inv_search_kernel): every posting of
+// the list adds the token's integer weight, and 32-bit integer adds ARE native on shared memory (ATOMS.ADD, no CAS loop:
+// three times the CAS ceiling in scripts/micro/smem_atomics.cu).
+__device__ __forceinline__ void accumulate_slice_fixed(uint32_t *acc, const uint16_t *__restrict__ rows, uint32_t begin, uint32_t end,
+                                                       uint32_t stride, uint32_t wq) {
+    for (uint32_t off = begin; off < end; off += stride * kInvUnroll) {
+        uint32_t row[kInvUnroll];
+#pragma unroll
+        for (int u = 0; u < kInvUnroll; ++u) {
+            const uint32_t o = off + (uint32_t)u * stride;
+            row[u] = o < end ? (uint32_t)rows[o] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < kInvUnroll; ++u)
+            if (row[u] != 0xffffffffu) atomicAdd(&acc[row[u]], wq);
     }
 }
 
@@ -488,13 +534,29 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     const int blk0 = blockIdx.x * p.blocks_per_cta, blk1 = min(p.n_blocks, blk0 + p.blocks_per_cta);
     const bool cached = cnt <= kTokTile;   // the whole token list stays in shared memory across blocks
     const size_t nb = (size_t)p.n_blocks;
-    __shared__ uint32_t s_ob;
+    __shared__ uint32_t s_ob, s_qn[kInvWarps];
     InvProf prof;
     prof.start(p.prof != nullptr && tid == 0);
     if (tid == 0) cta_state_reset(&st);
     for (int i = tid; i < kHistFine + kHistCoarse; i += NT) fine[i] = 0u;   // coarse follows fine
     if (cached && tid < cnt) { s_tok[tid] = tok[tid]; s_w[tid] = w[tid]; }
     __syncthreads();
+    bool fixed = false;
+    float fx_scale = 1.f, fx_inv = 1.f;
+    if constexpr (VK == 0) {   // fixed-point weights (inv_fixed_point_kernel)
+        const int e = p.L.fx[q];
+        if (e != kNoFixed && !(p.flags & 16)) { fixed = true; fx_scale = ldexpf(1.f, e); fx_inv = ldexpf(1.f, -e); }
+    }
+    uint32_t *accu = reinterpret_cast<uint32_t *>(acc);
+    const uint4 *acc4u = reinterpret_cast<const uint4 *>(acc);
+    // the largest integer pre-filter that still lets through every row whose (rounded) float score can reach t
+    auto fx_floor = [&](const float t) -> uint32_t {
+        if (!(t > 0.f)) return 0u;
+        float lo = t;
+        if constexpr (ROUND) lo = t * (1.f - 0.0078125f) - 6e-8f;
+        const float x = lo * fx_scale * (1.f - 1e-6f) - 1.f;
+        return x > 0.f ? (uint32_t)x : 0u;
+    };
     // list bounds of token `tid` in the NEXT block to score: loaded one block ahead, and the lists themselves are
     // pulled into L2 while the previous block is being selected
     uint2 nrng = make_uint2(0u, 0u);
@@ -506,15 +568,19 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     bool exact = false;                    // exact fallback engaged: histogram memory now holds the shared top-k set
 
     auto rnd = [&](float x) -> float { if constexpr (ROUND) return round_score(x, p.score_round); else return x; };
-    // The slow path of the select, for up to 32 accumulator float4s at once (lane < n_q takes queue entry `lane`): rows at
+    // The slow path of the select, for up to 32 accumulator float4s at once (a lane with `have` takes float4 `i`): rows at
     // or above the pre-filter and above the exact threshold (if any) are counted in the histogram (rows >= count_from
     // only) and appended -- one ATOMS.ADD per warp for the slots.  Called by all 32 lanes.
-    auto take_rows = [&](const uint16_t *qw, const int n_q, const int rows_b, const int64_t row0, const uint64_t tau, const int count_from) {
+    auto take_rows = [&](const bool have, const int i, const int rows_b, const int64_t row0, const uint64_t tau, const int count_from) {
         uint64_t key[4] = {0ull, 0ull, 0ull, 0ull};
         uint32_t n = 0;
-        if (lane < n_q) {
-            const int i = qw[lane], r = i * 4;
-            const float4 v = acc4[i];
+        if (have) {
+            const int r = i * 4;
+            float4 v = acc4[i];
+            if (fixed) {
+                const uint4 u = acc4u[i];
+                v = make_float4(__uint2float_rn(u.x) * fx_inv, __uint2float_rn(u.y) * fx_inv, __uint2float_rn(u.z) * fx_inv, __uint2float_rn(u.w) * fx_inv);
+            }
             const float sc[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -545,16 +611,23 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     };
     // float4 indices [i_lo, i_hi) of the block's accumulator through the pre-filter: the loop the select spends its time in.
     // Hits (one float4 in ~60 at best, so some lane of most warp iterations has one) are not handled where they occur --
-    // a divergent slow path per hit -- but queued per warp and taken 32 at a time with all lanes busy.
+    // a divergent slow path per hit -- but queued per warp and taken 32 at a time with all lanes busy.  What is left in
+    // the queues (`qn` entries) stays there across calls; flush_cta() / flush_own() take it at the end of the block.
+    uint16_t *const qw = s_queue + warp * kInvQueue;
+    int qn = 0;
     auto select_range = [&](const int i_lo, const int i_hi, const int rows_b, const int64_t row0, const uint64_t tau, const int count_from) {
-        uint16_t *qw = s_queue + warp * kInvQueue;
-        int qn = 0;
+        const uint32_t tau_u = fx_floor(tau_s);
         for (int i0 = i_lo; i0 < i_hi; i0 += NT) {
             const int i = i0 + tid;
             bool hit = false;
             if (i < i_hi) {
-                const float4 v = acc4[i];
-                hit = rnd(fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w))) >= tau_s;   // rounding is monotonic
+                if (fixed) {
+                    const uint4 u = acc4u[i];
+                    hit = max(max(u.x, u.y), max(u.z, u.w)) >= tau_u;
+                } else {
+                    const float4 v = acc4[i];
+                    hit = rnd(fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w))) >= tau_s;   // rounding is monotonic
+                }
             }
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
             if (m) {
@@ -562,7 +635,7 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                 qn += __popc(m);
                 if (qn >= 32) {
                     __syncwarp();
-                    take_rows(qw, 32, rows_b, row0, tau, count_from);
+                    take_rows(true, qw[lane], rows_b, row0, tau, count_from);
                     const uint16_t rest = lane < qn - 32 ? qw[32 + lane] : (uint16_t)0;
                     __syncwarp();
                     if (lane < qn - 32) qw[lane] = rest;
@@ -570,7 +643,38 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                 }
             }
         }
-        if (qn) { __syncwarp(); take_rows(qw, qn, rows_b, row0, tau, count_from); __syncwarp(); }
+    };
+    auto flush_own = [&](const int rows_b, const int64_t row0, const uint64_t tau, const int count_from) {
+        __syncwarp();
+        if (qn) take_rows(lane < qn, qw[lane < qn ? lane : 0], rows_b, row0, tau, count_from);
+        __syncwarp();
+        qn = 0;
+    };
+    // The leftovers of all warps' queues (a handful per warp at the end of a block) taken together: 24 warps running the
+    // slow path for five entries each cost as much as for 32 each, so the entries are dealt to the first
+    // ceil(total / 32) warps instead.  Called by all threads; contains one barrier, the caller adds the one after.
+    auto flush_cta = [&](const int rows_b, const int64_t row0, const uint64_t tau, const int count_from) {
+        if (lane == 0) s_qn[warp] = (uint32_t)qn;
+        __syncthreads();
+        const uint32_t c = lane < NW ? s_qn[lane] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        qn = 0;
+        if ((uint32_t)warp * 32u >= total) return;
+        const uint32_t g = min((uint32_t)warp * 32u + (uint32_t)lane, total - 1u);
+        int lo = 0, hi = NW - 1;   // the warp whose queue holds entry g: the first one with incl > g
+#pragma unroll
+        for (int s5 = 0; s5 < 5; ++s5) {
+            const int mid = (lo + hi) >> 1;
+            if (__shfl_sync(0xffffffffu, incl, mid) > g) hi = mid; else lo = mid + 1;
+        }
+        const uint32_t first = __shfl_sync(0xffffffffu, incl, lo) - __shfl_sync(0xffffffffu, c, lo);
+        take_rows((uint32_t)warp * 32u + (uint32_t)lane < total, s_queue[lo * kInvQueue + (int)(g - first)], rows_b, row0, tau, count_from);
     };
     // raise the pre-filter to the histogram's k-th bucket: one warp asks the histogram, everybody reads the answer.
     // Called by all threads; a barrier before the call makes the counts of the rows processed so far visible.
@@ -611,6 +715,20 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
             if (tid < tn) { s_beg[tid] = rng.x; s_len[tid] = rng.y - rng.x; }
             __syncthreads();  // also orders the zeroing above before the first atomic
             prof.lap(1);
+            if (p.flags & 1) {   // the heads of this tile's lists -> L1 (a warp walks its lists one after the other)
+                for (int i = tid; i < tn * 8; i += NT) {
+                    const int ti = i >> 3;
+                    const uint32_t ln = (uint32_t)(i & 7), len = min(s_len[ti], kLongList);
+                    const uint64_t at = base + s_beg[ti];
+                    const uintptr_t r0 = reinterpret_cast<uintptr_t>(p.post_row + at);
+                    if (((r0 & ~(uintptr_t)127) + ln * 128u) < r0 + len * 2u) prefetch_l1(reinterpret_cast<const void *>((r0 & ~(uintptr_t)127) + ln * 128u));
+                    if (vbytes) {
+                        const uintptr_t v0 = reinterpret_cast<uintptr_t>(p.post_val) + at * vbytes;
+                        for (uint32_t l2 = ln; ((v0 & ~(uintptr_t)127) + l2 * 128u) < v0 + (uint64_t)len * vbytes; l2 += 8u)
+                            prefetch_l1(reinterpret_cast<const void *>((v0 & ~(uintptr_t)127) + l2 * 128u));
+                    }
+                }
+            }
             // short lists: one warp per list piece, round robin; few tokens -> lists are cut in 2 or 4 pieces so that
             // every warp gets about the same number of postings
             const int psh = tn >= 2 * NW ? 0 : (tn >= NW ? 1 : 2);   // 1, 2 or 4 pieces per list
@@ -621,7 +739,8 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                 if (len - 1u < kLongList) {
                     const uint32_t lo = (len * pc) >> psh, hi = (len * (pc + 1u)) >> psh;
                     const uint64_t at = base + s_beg[ti];
-                    accumulate_slice<VK>(acc, p.post_row + at, (const uint8_t *)p.post_val + at * vbytes, lo + lane, hi, 32u, s_w[ti]);
+                    if (fixed) accumulate_slice_fixed(accu, p.post_row + at, lo + lane, hi, 32u, __float2uint_rn(s_w[ti] * fx_scale));
+                    else accumulate_slice<VK>(acc, p.post_row + at, (const uint8_t *)p.post_val + at * vbytes, lo + lane, hi, 32u, s_w[ti]);
                 }
             }
             // long lists (heavy-tailed token popularity): every warp takes a share
@@ -631,8 +750,9 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                 for (; longm; longm &= longm - 1) {
                     const int ti = tb + __ffs(longm) - 1;
                     const uint64_t at = base + s_beg[ti];
-                    accumulate_slice<VK>(acc, p.post_row + at, (const uint8_t *)p.post_val + at * vbytes, (uint32_t)tid, s_len[ti],
-                                         (uint32_t)NT, s_w[ti]);
+                    if (fixed) accumulate_slice_fixed(accu, p.post_row + at, (uint32_t)tid, s_len[ti], (uint32_t)NT, __float2uint_rn(s_w[ti] * fx_scale));
+                    else accumulate_slice<VK>(acc, p.post_row + at, (const uint8_t *)p.post_val + at * vbytes, (uint32_t)tid, s_len[ti],
+                                              (uint32_t)NT, s_w[ti]);
                 }
             }
         }
@@ -655,7 +775,11 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
             const int r = tid * 4;
             uint32_t zeros = 0;
             if (r < rows_b) {
-                const float4 v = acc4[r >> 2];
+                float4 v = acc4[r >> 2];
+                if (fixed) {
+                    const uint4 u = acc4u[r >> 2];
+                    v = make_float4(__uint2float_rn(u.x) * fx_inv, __uint2float_rn(u.y) * fx_inv, __uint2float_rn(u.z) * fx_inv, __uint2float_rn(u.w) * fx_inv);
+                }
                 const float sc[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
@@ -685,6 +809,7 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                 const bool more = p.k > 128;
                 int i_done = min(n4, NT);
                 select_range(0, i_done, rows_b, row0, tau, count_from);
+                prof.lap(8);
 #pragma unroll 1
                 for (int i_next = 3 * NT; i_done < n4; i_next = 2 * i_next + NT) {
                     if (more || i_done == NT) {
@@ -693,14 +818,17 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                         // (a count beyond the region is an overflow: left alone, the check after the block sees it)
                         if (n_app_seen > (uint32_t)(kInvAppend / 2) && n_app_seen <= (uint32_t)kInvAppend && ob)
                             compact_appended(app, &st, n_app_seen, ob);
+                        prof.lap(9);
                     }
                     const int i_hi = (more || i_next < 7 * NT) ? min(n4, i_next) : n4;
                     select_range(i_done, i_hi, rows_b, row0, tau, count_from);
+                    prof.lap(10);
                     i_done = i_hi;
                 }
             } else {
                 select_range(0, n4, rows_b, row0, tau, count_from);
             }
+            flush_cta(rows_b, row0, tau, count_from);
             __syncthreads();
             if (*(volatile uint32_t *)&st.n_app > (uint32_t)kInvAppend) {   // overflow: drop this block's appends, go exact
                 __syncthreads();
@@ -719,6 +847,7 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                     tau = *(volatile uint64_t *)&st.tau;
                 }
                 select_range(i0, min(n4, i0 + NT), rows_b, row0, tau, count_from);
+                flush_own(rows_b, row0, tau, count_from);
             }
             __syncthreads();
         }
@@ -785,7 +914,7 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     if (prof.on) {
         prof.lap(6);
         prof.acc[7] = prof.t - prof.acc[7];
-        for (int i = 0; i < 8; ++i) p.prof[((size_t)q * p.n_lists + blockIdx.x) * 8 + i] = prof.acc[i];
+        for (int i = 0; i < 16; ++i) p.prof[((size_t)q * p.n_lists + blockIdx.x) * 16 + i] = prof.acc[i];
     }
     __syncthreads();   // the next query resets the CTA state and the histogram
 
@@ -795,7 +924,7 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
 // ------------------------------------------------------------------------------------------- host side
 size_t inverted_workspace_bytes(const vs_index *idx, int64_t Bc, int group) {
     (void)idx; (void)group;
-    size_t lists = (size_t)Bc * ((size_t)kMaxQueryNnz * 8 + ((size_t)kMaxQueryNnz + 1) * 4 + 4 + 8);
+    size_t lists = (size_t)Bc * ((size_t)kMaxQueryNnz * 8 + ((size_t)kMaxQueryNnz + 1) * 4 + 4 + 4 + 8);
     return (lists + 255) / 256 * 256 + 1024;
 }
 
@@ -807,6 +936,7 @@ static QueryLists carve_lists(uint8_t *base, int64_t Bc, uint8_t **end) {
     L.w = (float *)(base + o); o += (size_t)Bc * kMaxQueryNnz * 4;
     L.pref = (uint32_t *)(base + o); o += (size_t)Bc * (kMaxQueryNnz + 1) * 4;
     L.cnt = (uint32_t *)(base + o); o += (size_t)Bc * 4;
+    L.fx = (int *)(base + o); o += (size_t)Bc * 4;
     *end = base + (o + 255) / 256 * 256;
     return L;
 }
@@ -829,6 +959,7 @@ int inverted_prepare(vs_index *idx, const float *d_qprep, int vpad, const void *
     else
         inv_extract_kernel<<<(unsigned)Bc, 256, 0, st>>>(d_qprep, vpad, (int)idx->n_cols, idx->post_ptr, L);
     VS_CUDA(cudaGetLastError());
+    if (idx->kind != 1) inv_fixed_point_kernel<<<(unsigned)((Bc + 7) / 8), 256, 0, st>>>(L, (int)Bc);   // binary index
     inv_decide_kernel<<<1, 256, 0, st>>>(L, (int)Bc, mode, t_scan, postings_per_sec, t_rows_fixed, d_flag, idx->d_last_mode);
     VS_CUDA(cudaGetLastError());
     return VS_OK;
