@@ -322,6 +322,25 @@ def sharded_parity(ctx):
             if msg is not None:
                 fails.append(f"binary={binary} n={n} k={k} mode={mode}: {msg}")
         del idx
+    # dense index, thresholds pooled between the ranks (vs_search_dense_step), and the one-all-gather path beside it
+    for steps in (True, False):
+        n, d, B, k = 1_000_003, 64, 6, 100
+        g = torch.Generator().manual_seed(21)
+        x = torch.randint(-8, 9, (n, d), generator=g).float() / 4.0
+        q = torch.randint(-8, 9, (B, d), generator=g).float() / 4.0
+        lo, hi = vs.row_partition(n, ctx.world, ctx.rank)
+        idx = vs.Index()
+        idx.vector = x[lo:hi].to(torch.bfloat16)
+        idx.move_to_device(ctx.dev)
+        sh = vs.ShardedIndex(idx, lo, n)
+        sh.dense_steps = steps
+        res = sh.search(q, k)
+        torch.cuda.synchronize()
+        if ctx.rank == 0:
+            canon = ref_search.canonical_topk(ref_search.quantize_like(ref_search.ref_scores(q, x), torch.bfloat16), k)
+            if not (torch.equal(res.ids.cpu(), canon.ids) and torch.equal(res.scores.float().cpu(), canon.scores)):
+                fails.append(f"dense n={n} k={k} stepwise={steps}: ids / scores differ from the reference's")
+        del idx, sh
     flag = torch.tensor([len(fails)], device=ctx.dev)
     dist.broadcast(flag, 0)
     if int(flag.item()):
@@ -540,6 +559,15 @@ def dense_extra(ctx):
                      "note": "achieved = 2*B*N_shard*D / device time of the sweeps of one call (sample + filtered sweeps, "
                              "CUDA events inside the ABI); peak = sustained cuBLAS bf16 rate, frac_of_burst vs the burst rate",
                      "peak_source": ctx.peaks["src"]}
+    if sharded is not None:   # the same through the one-all-gather path (every rank finds its thresholds alone)
+        sharded.dense_steps = False
+        m1 = ctx.measure(step_resident, step_e2e, eng, B_CFG4, 5, 2, e2e_steps=2)
+        sharded.dense_steps = True
+        k1 = flops / (m1["kernel_ms_per_launch"] * m1["kernel_launches_per_step"] * 1e-3) / 1e12 if m1["kernel_ms_per_launch"] else None
+        m["without_threshold_sharing"] = {"value": m1["value"], "ms_per_step": m1["ms_per_step"], "sweeps_tflops_per_gpu": k1,
+                                          "whole_call_tflops_per_gpu": flops / (m1["ms_per_step"] * 1e-3) / 1e12}
+        m["roofline"]["note"] += "; N > 1: thresholds pooled between the ranks after every sweep (vs_search_dense_step), the " \
+                                 "timed sweeps include the two key all-gathers in between"
     m["workload"] = f"cfg4: dense bf16 index {N_CFG4:,} x {D_CFG4}, B={B_CFG4}, k={K}"
     m["parallelism"] = f"row-shard x{world}" if world > 1 else "single GPU"
     m["index_build_s"] = round(build_s, 2)

@@ -102,8 +102,9 @@ int vs_index_export_csr(const vs_index *idx, int64_t *d_crow, int64_t *d_col, fl
  *   d_workspace  >= vs_search_workspace_bytes(idx, B, k) bytes, 256-byte aligned
  * The [B, N] score matrix is never written. */
 /* Synchronisation: sparse / bag-of-token indices -- none (the first auto / inverted search on a handle builds the
- * inverted lists once: SYNC that one time).  Dense index -- SYNC: the filtered sweeps read back one overflow counter
- * per sweep. */
+ * inverted lists once: SYNC that one time).  Dense index -- the whole call is enqueued without reading anything back,
+ * then SYNC once at its end: one status word says whether a survivor list overflowed (adversarial row order), in which
+ * case the call is redone with per-sweep checks. */
 #define VS_MAX_K 2048
 size_t vs_search_workspace_bytes(const vs_index *idx, int64_t B, int k);
 int vs_search(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int k, int mode,
@@ -116,6 +117,21 @@ int vs_search(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int
 int vs_search_keys(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B, int64_t ldq, int k, int mode,
                    int score_round, int64_t id_offset, uint64_t *d_keys,
                    void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Row-sharded DENSE search, one rank's part, in three steps with an all-gather of the [B, k] keys after each (no
+ * reference counterpart: upstream searches one device, index.py:179; sharded.py drives it).  A rank on its own learns
+ * its thresholds from its own rows only; pooled, the ranks get the thresholds of the whole index from a sample 1/n_ranks
+ * the size each:
+ *   step 0  sample sweep over this rank's share of the sample prefix   -> d_keys: its top-k (global ids)
+ *   step 1  d_gathered_keys = all ranks' step-0 keys [n_ranks, B, k]; filtered sweep over the next 64 x share rows
+ *                                                                      -> d_keys: top-k of what this rank has seen
+ *   step 2  the same with the step-1 keys, over the rest of the rows   -> d_keys: this rank's final top-k;
+ *           *d_status (device uint32, may be NULL) != 0: a survivor list overflowed, redo the search through vs_search_keys.
+ * Same workspace pointer (vs_search_workspace_bytes(idx, B, k)) in all three steps: it carries the state.  Device
+ * queries, B <= 4096, 16-bit index.  No synchronisation. */
+int vs_search_dense_step(const vs_index *idx, int step, const void *d_q, int q_dtype, int64_t B, int64_t ldq, int k,
+                         int score_round, int64_t id_offset, int n_ranks, const uint64_t *d_gathered_keys, uint64_t *d_keys,
+                         uint32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Same search for SPARSE queries given as CSR-style (token, weight) lists -- what the reference's query sparsifier
  * produces (utils/sparse.py:8-19: the a=768 activation budget, encoder/vdr.py:159-169) -- without the dense [B, V]

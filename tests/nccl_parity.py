@@ -40,6 +40,26 @@ for binary, n, m, k, mode in [(True, 300_001, 60, 100, "scan"), (False, 120_000,
         msg = ref_search.compare_results(res, ref_search.ref_scores(q, X), k, exact=True)
         print(f"world={world} binary={binary} n={n} k={k} mode={mode}:", "OK" if msg is None else msg, flush=True)
         ok = ok and msg is None
+# dense index: thresholds pooled between the ranks after every sweep (vs_search_dense_step); grid values, massive ties
+for n, d, B, k, dtype, steps in [(1_000_003, 64, 6, 100, torch.bfloat16, True), (1_000_003, 64, 6, 100, torch.bfloat16, False),
+                                 (300_000, 128, 260, 10, torch.float16, True)]:
+    g = torch.Generator().manual_seed(21)
+    x = torch.randint(-8, 9, (n, d), generator=g).float() / 4.0
+    q = torch.randint(-8, 9, (B, d), generator=g).float() / 4.0
+    lo, hi = vs.row_partition(n, world, rank)
+    idx = vs.Index()
+    idx.vector = x[lo:hi].to(dtype)
+    idx.move_to_device(dev)
+    sh = vs.ShardedIndex(idx, lo, n)
+    sh.dense_steps = steps
+    assert sh._dense_steps_apply(idx._require_engine(), q, k) == (steps and world > 1)
+    res = sh.search(q, k)
+    torch.cuda.synchronize()
+    if rank == 0:
+        canon = ref_search.canonical_topk(ref_search.quantize_like(ref_search.ref_scores(q, x), dtype), k)
+        good = torch.equal(res.ids.cpu(), canon.ids) and torch.equal(res.scores.float().cpu(), canon.scores)
+        print(f"world={world} dense n={n} d={d} B={B} k={k} {dtype} stepwise={steps}:", "OK" if good else "MISMATCH", flush=True)
+        ok = ok and good
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -144,3 +144,54 @@ def test_dense_fp32_vector_keeps_fp32_semantics(cuda_device):
     idx.move_to_device("cuda:0")
     res = idx.search(qg.to(torch.float16), 20)
     assert ref_search.compare_results(res, ref_search.ref_scores(qg, xg), 20, exact=True) is None
+
+
+@pytest.mark.parametrize("n,d,B,k,world,dtype", [
+    (1_300_000, 64, 5, 100, 2, torch.bfloat16),   # all three steps sweep rows on both ranks
+    (400_000, 64, 300, 10, 4, torch.float16),     # CTA-pair kernel; last rank shorter
+    (40_000, 96, 9, 100, 3, torch.bfloat16),      # step 1 ends the rows of a rank: step 2 sweeps nothing
+    (260_000, 64, 4, 1000, 1, torch.bfloat16),    # one rank: the steps alone
+])
+def test_dense_stepwise_simulated_ranks(n, d, B, k, world, dtype, cuda_device):
+    """vs_search_dense_step (the row-sharded dense path: thresholds pooled between the ranks after every sweep), with the
+    ranks played one after the other on one GPU and torch.stack standing in for the all-gather; grid values, so ids and
+    scores must equal the reference's bit for bit.  Massive ties at the k-th score included (integer grid)."""
+    import vsearch_b200 as vs
+
+    x, q = _grid((n, d), 11, scale=4.0, lim=8), _grid((B, d), 12, scale=4.0, lim=8)
+    parts = [vs.row_partition(n, world, r) for r in range(world)]
+    shards = [_dense_index(x[lo:hi], dtype) for lo, hi in parts]
+    engines = [s._require_engine() for s in shards]
+    rnd = shards[0]._score_round()   # scores are ranked after rounding to the index dtype (index.py:89)
+    qd = engines[0]._prep_q(q)
+    keys = [torch.empty((B, k), dtype=torch.int64, device="cuda:0") for _ in range(world)]
+    status = [torch.zeros(1, dtype=torch.int32, device="cuda:0") for _ in range(world)]
+    gathered = None
+    for step in range(3):
+        for r, eng in enumerate(engines):
+            eng.search_dense_step(step, qd, k, world, gathered, keys[r], status[r], score_round=rnd, id_offset=parts[r][0])
+        gathered = torch.stack(keys).contiguous()
+    assert all(int(s.item()) == 0 for s in status)
+    ids, scores = vs.merge_keys(gathered, k)
+    canon = ref_search.canonical_topk(ref_search.quantize_like(ref_search.ref_scores(q, x), dtype), k)
+    assert torch.equal(ids.cpu(), canon.ids), (ids.cpu() != canon.ids).nonzero()[:5]
+    assert torch.equal(ref_search.quantize_like(scores.cpu(), dtype), canon.scores)
+
+
+def test_dense_overflowing_lists_take_the_checked_fallback(cuda_device):
+    """The dense call enqueues all its sweeps without reading anything back and polls one status word at the end.  Rows
+    that beat everything the sample saw, 100,000 of them in the second sweep's range (the survivor lists hold 65,536),
+    raise it, and the call must still come out exact through the checked, retrying path."""
+    n, d, B, k = 1_200_000, 64, 4, 10
+    g = torch.Generator().manual_seed(5)
+    x = torch.zeros(n, d)
+    x[:16384, 0] = 1.0
+    hot = 20_000 + torch.randperm(900_000, generator=g)[:100_000]
+    x[hot, 0] = 2.0 + (torch.arange(100_000) % 200).float()          # integers <= 201: exact in bf16
+    q = torch.zeros(B, d)
+    q[:, 0] = torch.tensor([1.0, 2.0, 0.5, 4.0])
+    idx = _dense_index(x)
+    res = idx.search(q, k)
+    canon = ref_search.canonical_topk(ref_search.quantize_like(ref_search.ref_scores(q, x), torch.bfloat16), k)
+    assert torch.equal(res.ids.cpu(), canon.ids)
+    assert torch.equal(res.scores.float().cpu(), canon.scores)

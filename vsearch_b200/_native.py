@@ -27,7 +27,7 @@ SYMBOLS = [
     "vs_scores", "vs_merge_keys", "vs_kernel_timer", "vs_index_last_mode",
     "vs_npz_open", "vs_npz_close", "vs_npz_member_info", "vs_npz_read", "vs_bot_from_tokens", "vs_score_rows", "vs_npz_write", "vs_sparsify_topk",
     "vs_debug_scan_profile", "vs_debug_gather_wavefronts", "vs_search_sparse", "vs_score_rows_workspace_bytes",
-    "vs_dense_to_csr", "vs_index_load_npz",
+    "vs_dense_to_csr", "vs_index_load_npz", "vs_search_dense_step",
 ]
 
 
@@ -63,6 +63,8 @@ def _load() -> ctypes.CDLL:
                               c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.vs_search_keys.argtypes = [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int64,
                                    c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.vs_search_dense_step.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int64, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.vs_search_sparse.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.vs_score_rows_workspace_bytes.argtypes = [c_void_p, c_int64]

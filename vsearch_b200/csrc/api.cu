@@ -32,6 +32,9 @@ int inverted_prepare(vs_index *idx, const float *d_qprep, int vpad, const void *
 int launch_inverted(vs_index *idx, int64_t Bc, int k, int cand_stride, int score_round, void *d_ws, uint64_t *d_cand,
                     const int *d_flag, cudaStream_t st);
 size_t dense_workspace_bytes(const vs_index *idx, int64_t B, int k);
+int search_dense_step(vs_index *idx, int step, const void *d_q, int q_dtype, int64_t B, int64_t ldq, int k, int score_round,
+                      int64_t id_offset, int n_ranks, const uint64_t *d_gathered, uint64_t *d_keys_out, uint32_t *d_status,
+                      void *d_ws, cudaStream_t st);
 int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t ldq, int k, int score_round,
                  int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, void *d_ws, cudaStream_t st);
 int launch_merge(const uint64_t *d_in, int64_t P, int64_t stride_p, int64_t stride_b, int64_t B, int k_in, int k_out,
@@ -338,7 +341,7 @@ static int search_impl(const vs_index *cidx, const QueryInput &in, int64_t B, in
     const int vpad = vpad_for(idx->n_cols);
     uint8_t *ws_base = (uint8_t *)(((uintptr_t)d_workspace + 255) / 256 * 256);
 
-    if (idx->kind == 0) {  // dense index: K4 (tcgen05 GEMM + fused top-k).  SYNC (candidate-list overflow checks)
+    if (idx->kind == 0) {  // dense index: K4 (tcgen05 GEMM + fused top-k).  SYNC once, at the end (overflow status word)
         VS_REQUIRE(d_scores_full == nullptr, VS_ERR_UNSUPPORTED, "vs_scores is a sparse-path diagnostic");
         const void *dq = in.q;
         size_t ws_off = 0;
@@ -452,6 +455,27 @@ int vs_search_keys(const vs_index *idx, const void *hd_q, int q_dtype, int64_t B
     in.q = hd_q; in.q_dtype = q_dtype; in.ldq = ldq;
     return search_impl(idx, in, B, k, mode, score_round, id_offset, nullptr, nullptr, d_keys, nullptr, d_workspace,
                        workspace_bytes, stream);
+}
+
+int vs_search_dense_step(const vs_index *cidx, int step, const void *d_q, int q_dtype, int64_t B, int64_t ldq, int k,
+                         int score_round, int64_t id_offset, int n_ranks, const uint64_t *d_gathered_keys, uint64_t *d_keys,
+                         uint32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream) {
+    vs_index *idx = const_cast<vs_index *>(cidx);
+    VS_REQUIRE(idx != nullptr, VS_ERR_INVALID, "index is NULL");
+    VS_REQUIRE(idx->kind == 0, VS_ERR_UNSUPPORTED, "vs_search_dense_step needs a dense index");
+    VS_REQUIRE(d_q != nullptr && d_keys != nullptr, VS_ERR_INVALID, "queries / output keys are NULL");
+    VS_REQUIRE(q_dtype == VS_F32 || q_dtype == VS_F16 || q_dtype == VS_BF16, VS_ERR_INVALID, "bad query dtype");
+    VS_REQUIRE(ldq >= idx->n_cols, VS_ERR_INVALID, "query leading dimension %lld < dim %lld", (long long)ldq, (long long)idx->n_cols);
+    VS_REQUIRE(k >= 1 && (int64_t)k <= idx->n_rows && k <= VS_MAX_K, VS_ERR_INVALID, "k=%d out of range (rows %lld, VS_MAX_K %d)", k,
+               (long long)idx->n_rows, VS_MAX_K);
+    VS_REQUIRE(score_round == VS_F32 || score_round == VS_F16 || score_round == VS_BF16, VS_ERR_INVALID, "bad score_round");
+    VS_REQUIRE(B >= 1 && workspace_bytes >= vs_search_workspace_bytes(idx, B, k), VS_ERR_INVALID, "bad batch / workspace too small");
+    VS_REQUIRE(is_device_ptr(d_q), VS_ERR_INVALID, "vs_search_dense_step takes device queries");
+    VS_CUDA(cudaSetDevice(idx->device));
+    uint8_t *ws_base = (uint8_t *)(((uintptr_t)d_workspace + 255) / 256 * 256);
+    idx->last_mode = VS_MODE_SCAN; idx->last_mode_on_device = false;
+    return search_dense_step(idx, step, d_q, q_dtype, B, ldq, k, score_round, id_offset, n_ranks, d_gathered_keys, d_keys, d_status,
+                             ws_base, (cudaStream_t)stream);
 }
 
 int vs_search_sparse(const vs_index *idx, const void *hd_qptr, int ptr_dtype, const int32_t *hd_qtok, const float *hd_qw,

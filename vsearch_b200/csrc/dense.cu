@@ -544,16 +544,33 @@ __global__ void dense_convert_kernel(const void *in, int in_dtype, int64_t rows,
 // Every sweep starts from the top-k of the rows BEFORE it (`sorted_keys`) and their k-th key as the threshold.  A retry
 // after an overflow keeps those seeds -- seeding rows of the sweep itself would append them a second time -- and only
 // raises the threshold to the k-th best of what the failed attempt had stored (`retry_keys`).
+// tau_ext: [B] thresholds from elsewhere (the other ranks of a row-sharded index, search_dense_step), or nullptr
 __global__ void dense_seed_lists_kernel(const uint64_t *sorted_keys, int k, uint64_t *cand, int64_t cap, uint32_t *cnt,
-                                        uint64_t *tau, const uint64_t *retry_keys) {
+                                        uint64_t *tau, const uint64_t *retry_keys, const uint64_t *tau_ext = nullptr) {
     const int64_t q = blockIdx.x;
     for (int i = threadIdx.x; i < k; i += blockDim.x) cand[q * cap + i] = sorted_keys[q * k + i];
     if (threadIdx.x == 0) {
         cnt[q] = (uint32_t)k;
         uint64_t t = sorted_keys[q * k + (k - 1)];
         if (retry_keys && retry_keys[q * k + (k - 1)] > t) t = retry_keys[q * k + (k - 1)];
+        if (tau_ext && tau_ext[q] > t) t = tau_ext[q];
         tau[q] = t;
     }
+}
+
+// status word of a call that does not stop to look at its survivor counts: bit `bit` is set when a list went past its
+// capacity (the caller polls the word once, at the end)
+__global__ void dense_overflow_kernel(const uint32_t *cnt, int64_t n, uint32_t cap, uint32_t *status, uint32_t bit) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && cnt[i] > cap) atomicOr(status, bit);
+}
+
+// merged [B, k] keys of all ranks (global ids) -> per-query threshold: every row that scores at least as much as the
+// k-th best of the union can still make the global top-k; ids are left out of the comparison (local and global ids
+// do not compare), so rows that tie with the k-th score pass
+__global__ void dense_tau_from_keys_kernel(const uint64_t *merged, int k, int64_t n, uint64_t *tau_ext) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) tau_ext[q] = merged[q * k + (k - 1)] & 0xffffffff00000000ull;
 }
 
 // ---- fp32 storage (upstream's Index(fp16=False): an fp32 [N, D] matrix and an fp32 GEMM, index.py:36-44, 88-94) ----------
@@ -690,6 +707,10 @@ int build_dense_index(vs_index *idx, const void *d_x, int x_dtype, int64_t ld, c
         idx->device_bytes += idx->n_rows * idx->dim * 4;
     }
     VS_CUDA(cudaStreamSynchronize(st));
+    int rc = make_tmap(reinterpret_cast<CUtensorMap *>(idx->tmap_x), idx->dense, idx->mma_dtype, idx->n_pad, idx->d_pad, kBN);
+    if (rc) return rc;
+    rc = make_tmap(reinterpret_cast<CUtensorMap *>(idx->tmap_x_half), idx->dense, idx->mma_dtype, idx->n_pad, idx->d_pad, kBN / 2);   // CTA-pair kernel: B halves
+    if (rc) return rc;
     cudaDeviceProp prop;
     VS_CUDA(cudaGetDeviceProperties(&prop, idx->device));
     idx->n_ctas = prop.multiProcessorCount;
@@ -703,13 +724,14 @@ int launch_merge_counted(const uint64_t *d_in, const uint32_t *d_counts, int64_t
                          int64_t B, int k_in, int k_out, int64_t id_offset, int64_t *d_ids, float *d_scores,
                          uint64_t *d_keys, cudaStream_t st, const int *d_alt_flag = nullptr, int k_in_alt = 0);
 
-// workspace carve for one query chunk
+// workspace carve for one query chunk (behind the call's 1 KB status block)
 struct DenseWs {
     uint16_t *q16;        // [b_pad, d_pad]
     uint64_t *sample;     // [Bc, sample_rows]
     uint64_t *tau;        // [Bc]
+    uint64_t *tau_ext;    // [Bc]     thresholds learnt from the other ranks (search_dense_step)
     uint64_t *tau_sorted; // [Bc, k]  top-k of the rows before the current sweep
-    uint64_t *tau_retry;  // [Bc, k]  top-k of what an overflowed attempt stored
+    uint64_t *tau_retry;  // [Bc, k]  top-k of what an overflowed attempt stored / merged keys of all ranks
     uint32_t *cnt;        // [Bc]
     unsigned long long *work_counter;
     uint64_t *cand;       // [Bc, cap]
@@ -717,11 +739,16 @@ struct DenseWs {
 };
 constexpr int64_t kDenseQueryChunk = 4096;
 constexpr int64_t kDenseCandCap = 1 << 16;   // per-query survivor list (keys)
+constexpr size_t kDenseStatusBytes = 1024;   // head of the workspace: the call's status word
+constexpr uint32_t kDenseListOverflow = 1u, kDenseSupersetOverflow = 2u;
 
-static int64_t dense_sample_rows(const vs_index *idx, int k) {
-    // sample prefix: ~64*k rows (>= 16 K), a whole number of tiles, at most the index
+static int64_t dense_sample_rows(const vs_index *idx, int k, int n_ranks = 1) {
+    // sample prefix: ~64*k rows (>= 16 K) -- of the whole index: a rank of a row-sharded index sweeps its share and the
+    // ranks pool what they found --, at least k rows, a whole number of tiles, at most the index
     int64_t s = (int64_t)k * 64;
     if (s < 16384) s = 16384;
+    s = (s + n_ranks - 1) / n_ranks;
+    if (s < k) s = k;
     s = (s + kBN - 1) / kBN * kBN;
     return s < idx->n_pad ? s : idx->n_pad;
 }
@@ -730,11 +757,12 @@ static DenseWs carve_dense(const vs_index *idx, void *base, int64_t Bc, int k) {
     DenseWs w;
     auto al = [](size_t x) { return (x + 1023) / 1024 * 1024; };
     const int64_t b_pad = (Bc + 2 * kBM - 1) / (2 * kBM) * (2 * kBM);   // whole 256-query pair tiles
-    size_t o = 0;
+    size_t o = kDenseStatusBytes;
     uint8_t *p = (uint8_t *)base;
     w.q16 = (uint16_t *)(p + o); o += al((size_t)b_pad * idx->d_pad * 2);
     w.sample = (uint64_t *)(p + o); o += al((size_t)Bc * dense_sample_rows(idx, k) * 8);
     w.tau = (uint64_t *)(p + o); o += al((size_t)Bc * 8);
+    w.tau_ext = (uint64_t *)(p + o); o += al((size_t)Bc * 8);
     w.tau_sorted = (uint64_t *)(p + o); o += al((size_t)Bc * k * 8);
     w.tau_retry = (uint64_t *)(p + o); o += al((size_t)Bc * k * 8);
     w.cnt = (uint32_t *)(p + o); o += al((size_t)Bc * 4);
@@ -778,136 +806,267 @@ static int launch_dense(const vs_index *idx, const CUtensorMap &tq, const CUtens
     return VS_OK;
 }
 
-// d_q: device queries [B, ldq]; outputs like the sparse path (ids/scores or keys).  SYNC (reads survivor counts).
-int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t ldq, int k, int score_round,
-                 int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, void *d_ws, cudaStream_t st) {
-    VS_REQUIRE(idx->n_rows + id_offset < 0xffffffffll, VS_ERR_UNSUPPORTED, "global ids must fit 32 bits");
-    CUtensorMap tx, tx_half;
-    int rc = make_tmap(&tx, idx->dense, idx->mma_dtype, idx->n_pad, idx->d_pad, kBN);
-    if (rc) return rc;
-    rc = make_tmap(&tx_half, idx->dense, idx->mma_dtype, idx->n_pad, idx->d_pad, kBN / 2);   // CTA-pair kernel: B halves
-    if (rc) return rc;
-    const uint32_t fmt = idx->mma_dtype == VS_F16 ? 0u : 1u;
-    const bool exact32 = idx->store_dtype == VS_F32;   // bf16 sweep -> superset with an error margin -> exact fp32 re-score
-    // in that mode the bf16 pipeline below delivers its top-k as keys (local ids) into w.tau_sorted
-    int64_t *const out_ids = d_ids;
-    float *const out_scores = d_scores;
-    uint64_t *const out_keys = d_keys;
-    const int64_t out_offset = id_offset;
-    if (exact32) { d_ids = nullptr; d_scores = nullptr; id_offset = 0; score_round = VS_F32; }
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-    void *ws_base = (void *)(((uintptr_t)d_ws + 1023) / 1024 * 1024);
-    for (int64_t b0 = 0; b0 < B; b0 += kDenseQueryChunk) {
-        const int64_t Bc = (B - b0) < kDenseQueryChunk ? (B - b0) : kDenseQueryChunk;
-        const int64_t b_pad = (Bc + 2 * kBM - 1) / (2 * kBM) * (2 * kBM);
-        DenseWs w = carve_dense(idx, ws_base, Bc, k);
-        const uint8_t *qsrc = (const uint8_t *)d_q + (size_t)b0 * ldq * (q_dtype == VS_F32 ? 4 : 2);
-        dense_convert_kernel<<<1024, 256, 0, st>>>(qsrc, q_dtype, Bc, idx->dim, ldq, w.q16, idx->mma_dtype, b_pad, idx->d_pad);
-        CUtensorMap tq;
-        rc = make_tmap(&tq, w.q16, idx->mma_dtype, b_pad, idx->d_pad, kBM);
+// ---- one chunk (<= kDenseQueryChunk queries) of a dense search: the pieces both drivers below are made of
+struct DenseRun {
+    vs_index *idx;
+    cudaStream_t st;
+    int k;
+    int64_t Bc;
+    DenseWs w;
+    DenseArgs a;
+    const CUtensorMap *tq, *tx, *tx_half;
+    const uint8_t *qsrc;
+    int q_dtype;
+    int64_t ldq;
+    uint32_t *status;
+};
+
+static int dense_begin(DenseRun &r, vs_index *idx, const uint8_t *qsrc, int q_dtype, int64_t Bc, int64_t ldq, int k, int score_round,
+                       void *ws_base, bool convert, cudaStream_t st) {
+    r.idx = idx; r.st = st; r.k = k; r.Bc = Bc; r.qsrc = qsrc; r.q_dtype = q_dtype; r.ldq = ldq;
+    r.status = (uint32_t *)ws_base;
+    r.w = carve_dense(idx, ws_base, Bc, k);
+    const int64_t b_pad = (Bc + 2 * kBM - 1) / (2 * kBM) * (2 * kBM);
+    if (convert) {
+        dense_convert_kernel<<<1024, 256, 0, st>>>(qsrc, q_dtype, Bc, idx->dim, ldq, r.w.q16, idx->mma_dtype, b_pad, idx->d_pad);
+        VS_CUDA(cudaGetLastError());
+    }
+    if (idx->tmap_q_ptr != (const void *)r.w.q16 || idx->tmap_q_rows != b_pad) {   // a new workspace or batch height
+        int rc = make_tmap(reinterpret_cast<CUtensorMap *>(idx->tmap_q), r.w.q16, idx->mma_dtype, b_pad, idx->d_pad, kBM);
         if (rc) return rc;
-        if (exact32) d_keys = w.tau_sorted - b0 * k;   // (the merges below write d_keys + b0 * k)
-        // ---- fp32 storage: superset sweep + exact re-score, run after the bf16 top-k of this chunk is in w.tau_sorted
-        auto finish_exact32 = [&]() -> int {
-            dense_relax_kernel<<<(unsigned)Bc, 256, 0, st>>>(w.tau_sorted, k, qsrc, q_dtype, ldq, idx->dim, idx->max_row_norm, w.tau, w.cnt);
-            DenseArgs e = {};
-            e.n_tiles_m = (int)((Bc + kBM - 1) / kBM);
-            e.k_blocks = (int)(idx->d_pad / kBK);
-            e.n_rows = idx->n_rows; e.n_queries = Bc; e.row_offset = 0;
-            e.score_round = VS_F32; e.idesc = idesc;
-            e.sample_keys = w.sample; e.sample_ld = 0; e.tau = w.tau; e.cand = w.cand; e.cand_cnt = w.cnt; e.cand_cap = kDenseCandCap;
-            e.work_counter = w.work_counter; e.dbg = 0;
-            e.mode = 1; e.n_tiles_n = (int)(idx->n_pad / kBN);
-            int r2 = launch_dense(idx, tq, tx, tx_half, e, st);
-            if (r2) return r2;
+        idx->tmap_q_ptr = r.w.q16; idx->tmap_q_rows = b_pad;
+    }
+    r.tq = reinterpret_cast<const CUtensorMap *>(idx->tmap_q);
+    r.tx = reinterpret_cast<const CUtensorMap *>(idx->tmap_x);
+    r.tx_half = reinterpret_cast<const CUtensorMap *>(idx->tmap_x_half);
+    const uint32_t fmt = idx->mma_dtype == VS_F16 ? 0u : 1u;
+    DenseArgs &a = r.a;
+    a = DenseArgs{};
+    a.n_tiles_m = (int)((Bc + kBM - 1) / kBM);
+    a.k_blocks = (int)(idx->d_pad / kBK);
+    a.n_rows = idx->n_rows; a.n_queries = Bc; a.row_offset = 0;
+    a.score_round = score_round;
+    a.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    a.sample_keys = r.w.sample; a.tau = r.w.tau; a.cand = r.w.cand; a.cand_cnt = r.w.cnt; a.cand_cap = kDenseCandCap;
+    a.work_counter = r.w.work_counter;
+    a.dbg = getenv("VSEARCH_B200_DENSE_DBG") ? atoi(getenv("VSEARCH_B200_DENSE_DBG")) : 0;
+    return VS_OK;
+}
+
+// sample sweep: every score of rows [0, s_rows) becomes a key, their exact top-k goes to the given outputs
+static int dense_sample_pass(DenseRun &r, int64_t s_rows, int64_t id_offset, int64_t *ids, float *scores, uint64_t *keys) {
+    DenseArgs a = r.a;
+    a.mode = 0; a.n_tiles_n = (int)(s_rows / kBN); a.sample_ld = s_rows; a.row_offset = 0;
+    int rc = launch_dense(r.idx, *r.tq, *r.tx, *r.tx_half, a, r.st);
+    if (rc) return rc;
+    return launch_merge(r.w.sample, 1, 0, s_rows, r.Bc, (int)s_rows, r.k, id_offset, ids, scores, keys, r.st);
+}
+
+// filtered sweep over rows [row, row + rows): every list starts with the current top-k (w.tau_sorted), rows at or above the
+// threshold (its k-th key, raised by `retry` / `tau_ext` where given) are appended
+static int dense_filtered_pass(DenseRun &r, int64_t row, int64_t rows, const uint64_t *retry, const uint64_t *tau_ext) {
+    dense_seed_lists_kernel<<<(unsigned)r.Bc, 128, 0, r.st>>>(r.w.tau_sorted, r.k, r.w.cand, kDenseCandCap, r.w.cnt, r.w.tau, retry, tau_ext);
+    VS_CUDA(cudaGetLastError());
+    if (rows <= 0) return VS_OK;
+    DenseArgs a = r.a;
+    a.mode = 1; a.row_offset = row; a.n_tiles_n = (int)(rows / kBN);
+    return launch_dense(r.idx, *r.tq, *r.tx, *r.tx_half, a, r.st);
+}
+
+static int dense_flag_overflow(DenseRun &r, uint32_t bit) {
+    dense_overflow_kernel<<<(unsigned)((r.Bc + 255) / 256), 256, 0, r.st>>>(r.w.cnt, r.Bc, (uint32_t)kDenseCandCap, r.status, bit);
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+static int dense_survivor_topk(DenseRun &r, int64_t id_offset, int64_t *ids, float *scores, uint64_t *keys) {
+    return launch_merge_counted(r.w.cand, r.w.cnt, 1, 0, kDenseCandCap, r.Bc, (int)kDenseCandCap, r.k, id_offset, ids, scores, keys, r.st);
+}
+
+// fp32 storage: superset sweep + exact re-score, run after the bf16 top-k of the chunk is in w.tau_sorted.  `checked`:
+// stop and read the survivor counts (the fallback driver); otherwise they only raise the status word.
+static int dense_finish_exact32(DenseRun &r, bool checked, int64_t id_offset, int64_t *ids, float *scores, uint64_t *keys) {
+    vs_index *idx = r.idx;
+    dense_relax_kernel<<<(unsigned)r.Bc, 256, 0, r.st>>>(r.w.tau_sorted, r.k, r.qsrc, r.q_dtype, r.ldq, idx->dim, idx->max_row_norm, r.w.tau, r.w.cnt);
+    DenseArgs e = r.a;
+    e.score_round = VS_F32; e.sample_ld = 0; e.dbg = 0;
+    e.mode = 1; e.row_offset = 0; e.n_tiles_n = (int)(idx->n_pad / kBN);
+    int rc = launch_dense(idx, *r.tq, *r.tx, *r.tx_half, e, r.st);
+    if (rc) return rc;
+    unsigned gy = 16;
+    if (checked) {
+        std::vector<uint32_t> h_cnt((size_t)r.Bc);
+        VS_CUDA(cudaMemcpyAsync(h_cnt.data(), r.w.cnt, (size_t)r.Bc * 4, cudaMemcpyDeviceToHost, r.st));
+        VS_CUDA(cudaStreamSynchronize(r.st));
+        uint32_t mx = 0;
+        for (int64_t i = 0; i < r.Bc; ++i) mx = h_cnt[i] > mx ? h_cnt[i] : mx;
+        VS_REQUIRE(mx <= (uint32_t)kDenseCandCap, VS_ERR_UNSUPPORTED,
+                   "fp32 dense search: %u passages lie within the bf16 error bound of a query's k-th score (limit %lld)", mx,
+                   (long long)kDenseCandCap);
+        gy = (mx + 7) / 8;
+        gy = gy < 1 ? 1 : (gy > 64 ? 64 : gy);
+    } else if ((rc = dense_flag_overflow(r, kDenseSupersetOverflow)) != VS_OK) {
+        return rc;
+    }
+    dense_rescore_kernel<<<dim3((unsigned)r.Bc, gy), 256, 0, r.st>>>(idx->dense32, idx->dim, r.qsrc, r.q_dtype, r.ldq, r.w.cand, r.w.cnt, kDenseCandCap);
+    VS_CUDA(cudaGetLastError());
+    return dense_survivor_topk(r, id_offset, ids, scores, keys);
+}
+
+// One chunk, start to finish.  checked = false: nothing is read back -- a survivor list that ran past its capacity only
+// raises the status word, which search_dense polls once at the end of the call.  checked = true (the fallback for such
+// a call: adversarial row order): every sweep's counts are read (SYNC) and an overflowed sweep is redone with the
+// k-th best of what it stored as the new, strictly tighter threshold.
+static int dense_chunk(vs_index *idx, const uint8_t *qsrc, int q_dtype, int64_t Bc, int64_t ldq, int k, int score_round,
+                       int64_t id_offset, int64_t *ids, float *scores, uint64_t *keys, void *ws_base, bool checked, cudaStream_t st) {
+    const bool exact32 = idx->store_dtype == VS_F32;   // bf16 sweep -> superset with an error margin -> exact fp32 re-score
+    DenseRun r;
+    int rc = dense_begin(r, idx, qsrc, q_dtype, Bc, ldq, k, exact32 ? VS_F32 : score_round, ws_base, true, st);
+    if (rc) return rc;
+    // in exact32 mode the bf16 pipeline delivers its top-k as keys (local ids) into w.tau_sorted
+    int64_t *const p_ids = exact32 ? nullptr : ids;
+    float *const p_scores = exact32 ? nullptr : scores;
+    uint64_t *const p_keys = exact32 ? r.w.tau_sorted : keys;
+    const int64_t p_off = exact32 ? 0 : id_offset;
+
+    // ---- pass 1 (sample sweep): exact top-k of the first S1 rows -> threshold tau1
+    const int64_t s1 = dense_sample_rows(idx, k);
+    const int slot = idx->timer_n < VS_TIMER_SLOTS ? idx->timer_n : -1;
+    if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev0[slot], st));
+    if (s1 >= idx->n_rows) {   // the sample IS the index (small index): its top-k is the answer
+        rc = dense_sample_pass(r, s1, p_off, p_ids, p_scores, p_keys);
+        if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
+        idx->timer_n += 1;
+        if (rc) return rc;
+        return exact32 ? dense_finish_exact32(r, checked, id_offset, ids, scores, keys) : VS_OK;
+    }
+    rc = dense_sample_pass(r, s1, 0, nullptr, nullptr, r.w.tau_sorted);
+    if (rc) return rc;
+    // ---- passes 2 and 3 (filtered sweeps).  Pass 2 covers the next ~64 x S1 rows with tau1 and tightens the
+    // threshold to the k-th best of everything seen so far; pass 3 covers the rest of the index with that
+    // threshold, so only ~k * N / (65 * S1) rows per query survive it.
+    int64_t row = s1;
+    for (int pass = 2; row < idx->n_pad; ++pass) {
+        int64_t rows = (pass == 2) ? 64 * s1 : idx->n_pad - row;
+        if (rows > idx->n_pad - row) rows = idx->n_pad - row;
+        for (int attempt = 0;; ++attempt) {
+            rc = dense_filtered_pass(r, row, rows, attempt ? r.w.tau_retry : nullptr, nullptr);
+            if (rc) return rc;
+            if (!checked) {
+                if ((rc = dense_flag_overflow(r, kDenseListOverflow)) != VS_OK) return rc;
+                break;
+            }
             std::vector<uint32_t> h_cnt((size_t)Bc);
-            VS_CUDA(cudaMemcpyAsync(h_cnt.data(), w.cnt, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
+            VS_CUDA(cudaMemcpyAsync(h_cnt.data(), r.w.cnt, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
             VS_CUDA(cudaStreamSynchronize(st));
             uint32_t mx = 0;
             for (int64_t i = 0; i < Bc; ++i) mx = h_cnt[i] > mx ? h_cnt[i] : mx;
-            VS_REQUIRE(mx <= (uint32_t)kDenseCandCap, VS_ERR_UNSUPPORTED,
-                       "fp32 dense search: %u passages lie within the bf16 error bound of a query's k-th score (limit %lld)", mx,
-                       (long long)kDenseCandCap);
-            unsigned gy = (mx + 7) / 8;
-            gy = gy < 1 ? 1 : (gy > 64 ? 64 : gy);
-            dense_rescore_kernel<<<dim3((unsigned)Bc, gy), 256, 0, st>>>(idx->dense32, idx->dim, qsrc, q_dtype, ldq, w.cand, w.cnt, kDenseCandCap);
-            VS_CUDA(cudaGetLastError());
-            return launch_merge_counted(w.cand, w.cnt, 1, 0, kDenseCandCap, Bc, (int)kDenseCandCap, k, out_offset,
-                                        out_ids ? out_ids + b0 * k : nullptr, out_scores ? out_scores + b0 * k : nullptr,
-                                        out_keys ? out_keys + b0 * k : nullptr, st);
-        };
-        DenseArgs a;
-        a.n_tiles_m = (int)((Bc + kBM - 1) / kBM);
-        a.k_blocks = (int)(idx->d_pad / kBK);
-        a.n_rows = idx->n_rows; a.n_queries = Bc; a.row_offset = 0;
-        a.score_round = score_round; a.idesc = idesc;
-        a.sample_keys = w.sample; a.tau = w.tau; a.cand = w.cand; a.cand_cnt = w.cnt; a.cand_cap = kDenseCandCap;
-        a.work_counter = w.work_counter;
-        a.dbg = getenv("VSEARCH_B200_DENSE_DBG") ? atoi(getenv("VSEARCH_B200_DENSE_DBG")) : 0;
+            if (mx <= (uint32_t)kDenseCandCap) break;
+            VS_REQUIRE(attempt < 8, VS_ERR_UNSUPPORTED, "dense candidate lists keep overflowing");
+            // (lists that did not overflow keep their own count: only their first cnt[q] entries are valid)
+            rc = dense_survivor_topk(r, 0, nullptr, nullptr, r.w.tau_retry);
+            if (rc) return rc;
+        }
+        row += rows;
+        if (row < idx->n_pad && (rc = dense_survivor_topk(r, 0, nullptr, nullptr, r.w.tau_sorted)) != VS_OK) return rc;
+    }
+    if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
+    idx->timer_n += 1;
+    // exact top-k of the survivors (only the first cnt[q] entries of each list are valid)
+    rc = dense_survivor_topk(r, p_off, p_ids, p_scores, p_keys);
+    if (rc) return rc;
+    return exact32 ? dense_finish_exact32(r, checked, id_offset, ids, scores, keys) : VS_OK;
+}
 
-        // ---- pass 1 (sample sweep): exact top-k of the first S1 rows -> threshold tau1
-        const int64_t s1 = dense_sample_rows(idx, k);
-        a.mode = 0; a.n_tiles_n = (int)(s1 / kBN); a.sample_ld = s1; a.row_offset = 0;
-        const int slot = idx->timer_n < VS_TIMER_SLOTS ? idx->timer_n : -1;
-        if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev0[slot], st));
-        rc = launch_dense(idx, tq, tx, tx_half, a, st);
+static int dense_all_chunks(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t ldq, int k, int score_round,
+                            int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, void *ws_base, bool checked,
+                            cudaStream_t st) {
+    for (int64_t b0 = 0; b0 < B; b0 += kDenseQueryChunk) {
+        const int64_t Bc = (B - b0) < kDenseQueryChunk ? (B - b0) : kDenseQueryChunk;
+        const uint8_t *qsrc = (const uint8_t *)d_q + (size_t)b0 * ldq * (q_dtype == VS_F32 ? 4 : 2);
+        int rc = dense_chunk(idx, qsrc, q_dtype, Bc, ldq, k, score_round, id_offset, d_ids ? d_ids + b0 * k : nullptr,
+                             d_scores ? d_scores + b0 * k : nullptr, d_keys ? d_keys + b0 * k : nullptr, ws_base, checked, st);
         if (rc) return rc;
-        if (s1 >= idx->n_rows) {
-            // the sample IS the index (small index): its top-k is the answer
+    }
+    return VS_OK;
+}
+
+// d_q: device queries [B, ldq]; outputs like the sparse path (ids/scores or keys).  The whole call is enqueued without
+// looking at intermediate results; SYNC once at the end (the status word: did any survivor list overflow?).
+int search_dense(vs_index *idx, const void *d_q, int q_dtype, int64_t B, int64_t ldq, int k, int score_round,
+                 int64_t id_offset, int64_t *d_ids, float *d_scores, uint64_t *d_keys, void *d_ws, cudaStream_t st) {
+    VS_REQUIRE(idx->n_rows + id_offset < 0xffffffffll, VS_ERR_UNSUPPORTED, "global ids must fit 32 bits");
+    void *ws_base = (void *)(((uintptr_t)d_ws + 1023) / 1024 * 1024);
+    VS_CUDA(cudaMemsetAsync(ws_base, 0, 4, st));
+    int rc = dense_all_chunks(idx, d_q, q_dtype, B, ldq, k, score_round, id_offset, d_ids, d_scores, d_keys, ws_base, false, st);
+    if (rc) return rc;
+    uint32_t status = 0;
+    VS_CUDA(cudaMemcpyAsync(&status, ws_base, 4, cudaMemcpyDeviceToHost, st));
+    VS_CUDA(cudaStreamSynchronize(st));
+    VS_REQUIRE(!(status & kDenseSupersetOverflow), VS_ERR_UNSUPPORTED,
+               "fp32 dense search: more than %lld passages lie within the bf16 error bound of a query's k-th score",
+               (long long)kDenseCandCap);
+    if (status & kDenseListOverflow)   // adversarial row order: redo the call with per-sweep checks and retries
+        return dense_all_chunks(idx, d_q, q_dtype, B, ldq, k, score_round, id_offset, d_ids, d_scores, d_keys, ws_base, true, st);
+    return VS_OK;
+}
+
+// keys with local ids -> global ids (empty keys stay empty)
+__global__ void dense_keys_offset_kernel(const uint64_t *in, uint64_t *out, int64_t n, uint32_t id_offset) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const uint64_t x = in[i]; out[i] = x ? ((x & 0xffffffff00000000ull) | (uint64_t)(uint32_t)~(key_id(x) + id_offset)) : 0ull; }
+}
+
+// Row-sharded dense search, one rank's part in three steps with an all-gather of [B, k] keys after each (sharded.py):
+//   step 0  sample sweep over this rank's share of the sample prefix        -> d_keys_out: its top-k (global ids)
+//   step 1  d_gathered = every rank's step-0 keys [n_ranks, B, k]: their merged k-th score is a threshold no rank could
+//           have found alone; filtered sweep over the next 64 x share rows   -> d_keys_out: top-k of what this rank has seen
+//   step 2  the same with the step-1 keys, over the rest of the rows         -> d_keys_out: this rank's final top-k;
+//           *d_status (device) != 0 when a survivor list overflowed: the caller redoes the search through vs_search.
+// The workspace (same pointer in all three steps) carries the state.  B <= 4096, 16-bit index.  Nothing is read back.
+int search_dense_step(vs_index *idx, int step, const void *d_q, int q_dtype, int64_t B, int64_t ldq, int k, int score_round,
+                      int64_t id_offset, int n_ranks, const uint64_t *d_gathered, uint64_t *d_keys_out, uint32_t *d_status,
+                      void *d_ws, cudaStream_t st) {
+    VS_REQUIRE(idx->kind == 0 && idx->store_dtype != VS_F32, VS_ERR_UNSUPPORTED, "stepwise search is for 16-bit dense indices");
+    VS_REQUIRE(B >= 1 && B <= kDenseQueryChunk, VS_ERR_INVALID, "stepwise search takes 1..%lld queries per call", (long long)kDenseQueryChunk);
+    VS_REQUIRE(step >= 0 && step <= 2 && n_ranks >= 1, VS_ERR_INVALID, "bad step / n_ranks");
+    VS_REQUIRE(idx->n_rows + id_offset < 0xffffffffll, VS_ERR_UNSUPPORTED, "global ids must fit 32 bits");
+    VS_REQUIRE(step == 0 || d_gathered != nullptr, VS_ERR_INVALID, "steps 1 and 2 need the gathered keys");
+    void *ws_base = (void *)(((uintptr_t)d_ws + 1023) / 1024 * 1024);
+    DenseRun r;
+    int rc = dense_begin(r, idx, (const uint8_t *)d_q, q_dtype, B, ldq, k, score_round, ws_base, step == 0, st);
+    if (rc) return rc;
+    const int64_t s_loc = dense_sample_rows(idx, k, n_ranks);
+    int64_t r2 = 64 * s_loc;
+    if (r2 > idx->n_pad - s_loc) r2 = idx->n_pad - s_loc;
+    const int slot = idx->timer_n < VS_TIMER_SLOTS ? idx->timer_n : -1;
+    const unsigned nblk = (unsigned)((B * k + 255) / 256);
+    if (step == 0) {
+        VS_CUDA(cudaMemsetAsync(ws_base, 0, 4, st));
+        if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev0[slot], st));
+        rc = dense_sample_pass(r, s_loc, 0, nullptr, nullptr, r.w.tau_sorted);
+        if (rc) return rc;
+    } else {
+        // the k-th best of all ranks' keys -> external threshold
+        rc = launch_merge(d_gathered, n_ranks, B * k, k, B, k, k, 0, nullptr, nullptr, r.w.tau_retry, st);
+        if (rc) return rc;
+        dense_tau_from_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(r.w.tau_retry, k, B, r.w.tau_ext);
+        VS_CUDA(cudaGetLastError());
+        const int64_t row = step == 1 ? s_loc : s_loc + r2;
+        const int64_t rows = step == 1 ? r2 : idx->n_pad - row;
+        rc = dense_filtered_pass(r, row, rows, nullptr, r.w.tau_ext);
+        if (rc) return rc;
+        if ((rc = dense_flag_overflow(r, kDenseListOverflow)) != VS_OK) return rc;
+        if (step == 2) {
             if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
             idx->timer_n += 1;
-            rc = launch_merge(w.sample, 1, 0, s1, Bc, (int)s1, k, id_offset, d_ids ? d_ids + b0 * k : nullptr,
-                              d_scores ? d_scores + b0 * k : nullptr, d_keys ? d_keys + b0 * k : nullptr, st);
-            if (rc) return rc;
-            if (exact32 && (rc = finish_exact32()) != VS_OK) return rc;
-            continue;
         }
-        rc = launch_merge(w.sample, 1, 0, s1, Bc, (int)s1, k, 0, nullptr, nullptr, w.tau_sorted, st);
+        rc = dense_survivor_topk(r, 0, nullptr, nullptr, r.w.tau_sorted);
         if (rc) return rc;
-
-        // ---- passes 2 and 3 (filtered sweeps).  Pass 2 covers the next ~64 x S1 rows with tau1 and tightens the
-        // threshold to the k-th best of everything seen so far; pass 3 covers the rest of the index with that
-        // threshold, so only ~k * N / (65 * S1) rows per query survive it.  Every list starts with the current top-k.
-        int64_t row = s1;
-        for (int pass = 2; row < idx->n_pad; ++pass) {
-            int64_t rows = (pass == 2) ? 64 * s1 : idx->n_pad - row;
-            if (rows > idx->n_pad - row) rows = idx->n_pad - row;
-            for (int attempt = 0;; ++attempt) {
-                dense_seed_lists_kernel<<<(unsigned)Bc, 128, 0, st>>>(w.tau_sorted, k, w.cand, kDenseCandCap, w.cnt, w.tau,
-                                                                      attempt ? w.tau_retry : nullptr);
-                a.mode = 1; a.row_offset = row; a.n_tiles_n = (int)(rows / kBN);
-                rc = launch_dense(idx, tq, tx, tx_half, a, st);
-                if (rc) return rc;
-                std::vector<uint32_t> h_cnt((size_t)Bc);
-                VS_CUDA(cudaMemcpyAsync(h_cnt.data(), w.cnt, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
-                VS_CUDA(cudaStreamSynchronize(st));
-                uint32_t mx = 0;
-                for (int64_t i = 0; i < Bc; ++i) mx = h_cnt[i] > mx ? h_cnt[i] : mx;
-                if (mx <= (uint32_t)kDenseCandCap) break;
-                VS_REQUIRE(attempt < 8, VS_ERR_UNSUPPORTED, "dense candidate lists keep overflowing");
-                // overflow (adversarial row order): the k-th best of the kDenseCandCap stored candidates is a valid,
-                // strictly tighter threshold; redo this sweep with it
-                // (lists that did not overflow keep their own count: only their first cnt[q] entries are valid)
-                rc = launch_merge_counted(w.cand, w.cnt, 1, 0, kDenseCandCap, Bc, (int)kDenseCandCap, k, 0, nullptr, nullptr,
-                                          w.tau_retry, st);
-                if (rc) return rc;
-            }
-            row += rows;
-            if (row < idx->n_pad) {  // tighten for the next sweep: top-k of everything seen so far
-                rc = launch_merge_counted(w.cand, w.cnt, 1, 0, kDenseCandCap, Bc, (int)kDenseCandCap, k, 0, nullptr, nullptr,
-                                          w.tau_sorted, st);
-                if (rc) return rc;
-            }
-        }
-        if (slot >= 0) VS_CUDA(cudaEventRecord(idx->ev1[slot], st));
-        idx->timer_n += 1;
-        // exact top-k of the survivors (only the first cnt[q] entries of each list are valid)
-        rc = launch_merge_counted(w.cand, w.cnt, 1, 0, kDenseCandCap, Bc, (int)kDenseCandCap, k, id_offset,
-                                  d_ids ? d_ids + b0 * k : nullptr, d_scores ? d_scores + b0 * k : nullptr,
-                                  d_keys ? d_keys + b0 * k : nullptr, st);
-        if (rc) return rc;
-        if (exact32 && (rc = finish_exact32()) != VS_OK) return rc;
     }
+    dense_keys_offset_kernel<<<nblk, 256, 0, st>>>(r.w.tau_sorted, d_keys_out, B * k, (uint32_t)id_offset);
+    VS_CUDA(cudaGetLastError());
+    if (step == 2 && d_status) VS_CUDA(cudaMemcpyAsync(d_status, ws_base, 4, cudaMemcpyDeviceToDevice, st));
     return VS_OK;
 }
 

@@ -73,6 +73,12 @@ struct vs_index {
     int mma_dtype = VS_BF16;                 // dtype of `dense` (store_dtype, or bf16 when the index keeps fp32 semantics)
     float *dense32 = nullptr;                // store_dtype == VS_F32: the exact rows [n_rows, dim] for the re-score
     float max_row_norm = 0.f;                // ... and the largest row L2 norm (error bound of the bf16 sweep)
+    // TMA descriptors (CUtensorMap, kept as bytes: this header does not see the driver API) of `dense` with full- and
+    // half-height boxes, encoded once at build; the one of the converted query block is re-encoded only when the
+    // caller's workspace or the batch height changes
+    alignas(64) unsigned char tmap_x[128] = {}, tmap_x_half[128] = {}, tmap_q[128] = {};
+    const void *tmap_q_ptr = nullptr;
+    int64_t tmap_q_rows = 0;
 
     int64_t device_bytes = 0;
     int64_t stream_bytes = 0;

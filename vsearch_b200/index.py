@@ -219,6 +219,20 @@ class _Engine:
         nat.check(rc)
         return ids, scores
 
+    def search_dense_step(self, step: int, q: torch.Tensor, k: int, n_ranks: int, gathered: Optional[torch.Tensor],
+                          keys_out: torch.Tensor, status: Optional[torch.Tensor], score_round: int = nat.VS_F32,
+                          id_offset: int = 0) -> None:
+        """One step of the row-sharded dense search (``vs_search_dense_step``); ``q`` prepared ``[B <= 4096, dim]`` on
+        this device, ``gathered`` ``[n_ranks, B, k]`` int64 keys of all ranks (steps 1, 2), ``keys_out`` ``[B, k]``."""
+        B = q.shape[0]
+        with torch.cuda.device(self.device):
+            ws = self.workspace(B, k)
+            rc = nat.LIB.vs_search_dense_step(self.handle, step, q.data_ptr(), _TORCH2VS[q.dtype], B, q.stride(0), k, score_round,
+                                              id_offset, n_ranks, None if gathered is None else gathered.data_ptr(),
+                                              keys_out.data_ptr(), None if status is None else status.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
+        nat.check(rc)
+
     def scores(self, q: torch.Tensor, score_round: int = nat.VS_F32) -> torch.Tensor:
         """Diagnostic: the full [B, N] score matrix (upstream index.py:91)."""
         q = self._prep_q(q)

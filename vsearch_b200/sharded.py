@@ -73,6 +73,46 @@ class ShardedIndex:
         local = (index_cls or SparseIndex)(files[lo:hi], device=device, **index_kwargs)
         return cls(local, sum(rows[:lo]), sum(rows), group=group)
 
+    # ---- dense index: thresholds shared between the ranks (vs_search_dense_step) -------------------------------------
+    dense_steps = True   # class-wide switch (benchmarks compare against the one-all-gather path)
+
+    def _dense_steps_apply(self, eng, q: torch.Tensor, k: int) -> bool:
+        """The same answer on every rank (it decides which collectives follow): a 16-bit dense index, more than one
+        rank, and even the shortest shard holds the k rows and the sample share the stepwise search starts from."""
+        if not (self.dense_steps and eng.kind == 0 and dist.is_initialized() and q.layout == torch.strided):
+            return False
+        world = dist.get_world_size(self.group)
+        if world < 2 or self.local._value_dtype() == torch.float32:
+            return False
+        per = -(-self.n_rows_total // world)
+        shortest = self.n_rows_total - (world - 1) * per
+        return shortest >= max(k, 4096)
+
+    def _dense_stepwise(self, eng, q: torch.Tensor, k: int):
+        """Three sweeps with the ranks' top-k keys pooled after each: the sample every rank sweeps is 1/W of what a lone
+        GPU needs, and the filtered sweeps run with the thresholds of the WHOLE index, so a rank keeps ~W times fewer
+        survivors.  Returns the gathered final keys ``[W, B, k]``, or None when a survivor list overflowed on some rank
+        (adversarial row order: every rank then falls back to the one-all-gather path)."""
+        world = dist.get_world_size(self.group)
+        q = eng._prep_q(q)
+        rnd = self.local._score_round()
+        status = torch.zeros(1, dtype=torch.int32, device=eng.device)
+        chunks = []
+        for b0 in range(0, q.shape[0], 4096):
+            qc = q[b0:b0 + 4096]
+            keys = torch.empty((qc.shape[0], k), dtype=torch.int64, device=eng.device)
+            st = torch.zeros(1, dtype=torch.int32, device=eng.device)
+            gathered = None
+            for step in range(3):
+                eng.search_dense_step(step, qc, k, world, gathered, keys, st, score_round=rnd, id_offset=self.row_offset)
+                gathered = gather_keys(keys, self.group)
+            status |= st
+            chunks.append(gathered)
+        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
+        if int(status.item()) != 0:
+            return None
+        return chunks[0] if len(chunks) == 1 else torch.cat(chunks, dim=1)
+
     def search(self, q_embs: torch.Tensor, k: int) -> SearchResults:
         if k > self.n_rows_total:
             raise RuntimeError(f"selected index k out of range (k={k} > N={self.n_rows_total})")
@@ -81,6 +121,12 @@ class ShardedIndex:
         eng = self.local._require_engine()
         n_local = eng.n_rows
         k_local = min(k, n_local)
+        if self._dense_steps_apply(eng, q, k):
+            keys = self._dense_stepwise(eng, q, k)
+            if keys is not None:
+                ids, scores = self._merge(keys, k)
+                scores = scores.to(self.local._value_dtype())
+                return SearchResults(ids[0], scores[0]) if one_d else SearchResults(ids, scores)
         if k_local == 0:   # a rank without rows (more ranks than rows): it contributes empty keys only
             keys = torch.zeros((q.shape[0], k), dtype=torch.int64, device=eng.device)
         else:
