@@ -79,7 +79,7 @@ class ShardedIndex:
     def _dense_steps_apply(self, eng, q: torch.Tensor, k: int) -> bool:
         """The same answer on every rank (it decides which collectives follow): a 16-bit dense index, more than one
         rank, and even the shortest shard holds the k rows and the sample share the stepwise search starts from."""
-        if not (self.dense_steps and eng.kind == 0 and dist.is_initialized() and q.layout == torch.strided):
+        if not (self.dense_steps and getattr(eng, "kind", None) == 0 and dist.is_initialized() and q.layout == torch.strided):
             return False
         world = dist.get_world_size(self.group)
         if world < 2 or self.local._value_dtype() == torch.float32:
