@@ -470,8 +470,13 @@ __device__ __forceinline__ void accumulate_slice(float *acc, const uint16_t *__r
 // The same for a binary index whose query weights went to fixed point (see `fx` in inv_search_kernel): every posting of
 // the list adds the token's integer weight, and 32-bit integer adds ARE native on shared memory (ATOMS.ADD, no CAS loop:
 // three times the CAS ceiling in scripts/micro/smem_atomics.cu).
+constexpr uint32_t kCrossCap = kInvWarps * kInvQueue;   // rows the crossing queue holds (it lives in the hit queues' memory)
+
+// CROSS: the adds return the old sums, and a row whose sum climbs over the pre-filter `tau_u` with this posting (weights
+// are positive: that happens once per row) is noted in the CTA's crossing queue -- the select then has nothing to scan.
+template <bool CROSS>
 __device__ __forceinline__ void accumulate_slice_fixed(uint32_t *acc, const uint16_t *__restrict__ rows, uint32_t begin, uint32_t end,
-                                                       uint32_t stride, uint32_t wq) {
+                                                       uint32_t stride, uint32_t wq, uint32_t tau_u, uint16_t *cross_q, uint32_t *cross_n) {
     for (uint32_t off = begin; off < end; off += stride * kInvUnroll) {
         uint32_t row[kInvUnroll];
 #pragma unroll
@@ -479,9 +484,21 @@ __device__ __forceinline__ void accumulate_slice_fixed(uint32_t *acc, const uint
             const uint32_t o = off + (uint32_t)u * stride;
             row[u] = o < end ? (uint32_t)rows[o] : 0xffffffffu;
         }
+        if constexpr (CROSS) {
+            uint32_t old[kInvUnroll];
 #pragma unroll
-        for (int u = 0; u < kInvUnroll; ++u)
-            if (row[u] != 0xffffffffu) atomicAdd(&acc[row[u]], wq);
+            for (int u = 0; u < kInvUnroll; ++u) old[u] = row[u] != 0xffffffffu ? atomicAdd(&acc[row[u]], wq) : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < kInvUnroll; ++u)
+                if (old[u] < tau_u && old[u] + wq >= tau_u) {   // (sums stay below 2^32: no wrap; idle slots hold ~0)
+                    const uint32_t slot = atomicAdd(cross_n, 1u);
+                    if (slot < kCrossCap) cross_q[slot] = (uint16_t)row[u];
+                }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kInvUnroll; ++u)
+                if (row[u] != 0xffffffffu) atomicAdd(&acc[row[u]], wq);
+        }
     }
 }
 
@@ -534,7 +551,7 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     const int blk0 = blockIdx.x * p.blocks_per_cta, blk1 = min(p.n_blocks, blk0 + p.blocks_per_cta);
     const bool cached = cnt <= kTokTile;   // the whole token list stays in shared memory across blocks
     const size_t nb = (size_t)p.n_blocks;
-    __shared__ uint32_t s_ob, s_qn[kInvWarps];
+    __shared__ uint32_t s_ob, s_qn[kInvWarps], s_cross_n;
     InvProf prof;
     prof.start(p.prof != nullptr && tid == 0);
     if (tid == 0) cta_state_reset(&st);
@@ -676,6 +693,23 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
         const uint32_t first = __shfl_sync(0xffffffffu, incl, lo) - __shfl_sync(0xffffffffu, c, lo);
         take_rows((uint32_t)warp * 32u + (uint32_t)lane < total, s_queue[lo * kInvQueue + (int)(g - first)], rows_b, row0, tau, count_from);
     };
+    // A row of the crossing queue (fixed-point blocks): its final sum -> key -> histogram and append region.  All 32 lanes.
+    auto take_crossed = [&](const bool have, const uint32_t r, const int rows_b, const int64_t row0, const uint64_t tau) {
+        uint64_t key = 0ull;
+        if (have && (int)r < rows_b) {
+            const float se = rnd(__uint2float_rn(accu[r]) * fx_inv);
+            if (se >= tau_s) {
+                const uint64_t ke = make_key(se, (uint32_t)(row0 + r));
+                if (ke > tau) { key = ke; hist_count_plain(coarse, fine, (uint32_t)(ke >> 32)); }
+            }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, key != 0ull);
+        if (m == 0u) return;
+        uint32_t base_slot = 0;
+        if (lane == 0) base_slot = atom_shared_add(&st.n_app, (uint32_t)__popc(m));
+        const uint32_t slot = __shfl_sync(0xffffffffu, base_slot, 0) + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        if (key != 0ull && slot < (uint32_t)kInvAppend) app[slot] = key;
+    };
     // raise the pre-filter to the histogram's k-th bucket: one warp asks the histogram, everybody reads the answer.
     // Called by all threads; a barrier before the call makes the counts of the rows processed so far visible.
     uint32_t n_app_seen = 0;   // the append count at the last refresh (the same value in every thread)
@@ -696,6 +730,12 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
         const int rows_b = (int)min((int64_t)R, p.n_rows - row0);
         const uint64_t base = p.blk_base[b];
         prof.lap(0);
+        // Fixed-point blocks after the CTA's first one: the pre-filter is known before the postings are added, so the rows
+        // that end up above it are caught while they cross it (accumulate_slice_fixed<true>) and the block's select
+        // only visits those instead of scanning 37 K sums for the ~150 that matter.
+        const uint32_t cross_tau = fx_floor(tau_s);
+        const bool cross = fixed && booted && !exact && cached && cross_tau > 0u;
+        if (tid == 0) s_cross_n = 0u;   // (ordered before the first add by the barrier below)
         for (int i = tid; i < (R >> 2); i += NT) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         // ---- accumulate: tiles of <= kTokTile query tokens
         for (int t0 = 0; t0 < cnt; t0 += kTokTile) {
@@ -739,7 +779,8 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                 if (len - 1u < kLongList) {
                     const uint32_t lo = (len * pc) >> psh, hi = (len * (pc + 1u)) >> psh;
                     const uint64_t at = base + s_beg[ti];
-                    if (fixed) accumulate_slice_fixed(accu, p.post_row + at, lo + lane, hi, 32u, __float2uint_rn(s_w[ti] * fx_scale));
+                    if (cross) accumulate_slice_fixed<true>(accu, p.post_row + at, lo + lane, hi, 32u, __float2uint_rn(s_w[ti] * fx_scale), cross_tau, s_queue, &s_cross_n);
+                    else if (fixed) accumulate_slice_fixed<false>(accu, p.post_row + at, lo + lane, hi, 32u, __float2uint_rn(s_w[ti] * fx_scale), 0u, nullptr, nullptr);
                     else accumulate_slice<VK>(acc, p.post_row + at, (const uint8_t *)p.post_val + at * vbytes, lo + lane, hi, 32u, s_w[ti]);
                 }
             }
@@ -750,7 +791,8 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                 for (; longm; longm &= longm - 1) {
                     const int ti = tb + __ffs(longm) - 1;
                     const uint64_t at = base + s_beg[ti];
-                    if (fixed) accumulate_slice_fixed(accu, p.post_row + at, (uint32_t)tid, s_len[ti], (uint32_t)NT, __float2uint_rn(s_w[ti] * fx_scale));
+                    if (cross) accumulate_slice_fixed<true>(accu, p.post_row + at, (uint32_t)tid, s_len[ti], (uint32_t)NT, __float2uint_rn(s_w[ti] * fx_scale), cross_tau, s_queue, &s_cross_n);
+                    else if (fixed) accumulate_slice_fixed<false>(accu, p.post_row + at, (uint32_t)tid, s_len[ti], (uint32_t)NT, __float2uint_rn(s_w[ti] * fx_scale), 0u, nullptr, nullptr);
                     else accumulate_slice<VK>(acc, p.post_row + at, (const uint8_t *)p.post_val + at * vbytes, (uint32_t)tid, s_len[ti],
                                               (uint32_t)NT, s_w[ti]);
                 }
@@ -802,17 +844,21 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
         const int n4 = (rows_b + 3) >> 2;   // float4s of the block's accumulator (the tail beyond rows_b is masked in take_rows)
         if (!exact) {
             const uint64_t tau = *(volatile uint64_t *)&st.tau;
-            if (!booted) {   // the pre-filter of the first block tightens as its rows are counted: after NT*4, 3x and 7x that many
-                // (small k: the first refresh already leaves few enough survivors for the append region, and every
-                // refresh costs two barriers; large k needs the tighter bounds, and drops what fell below them whenever
-                // the region is half full, to stay out of the exact fallback)
+            if (cross && *(volatile uint32_t *)&s_cross_n <= kCrossCap) {
+                const uint32_t n_cross = *(volatile uint32_t *)&s_cross_n;   // (stable: read after the accumulate barrier)
+                for (uint32_t e0 = (uint32_t)warp * 32u; e0 < n_cross; e0 += NT) take_crossed(e0 + lane < n_cross, s_queue[min(e0 + lane, n_cross - 1u)], rows_b, row0, tau);
+            } else {
+                // One pass over the block's sums.  The CTA's first block has no pre-filter worth the name yet: it is cut into
+                // ranges (NT float4s, then up to 3 NT, 7 NT, ...) and the pre-filter is raised from the histogram between them
+                // (small k: once, after the first range -- it already leaves few enough survivors for the append region and
+                // every refresh costs two barriers; large k: before every range, dropping what fell below the new bound
+                // whenever the region is half full, to stay out of the exact fallback).
                 const bool more = p.k > 128;
-                int i_done = min(n4, NT);
-                select_range(0, i_done, rows_b, row0, tau, count_from);
-                prof.lap(8);
+                int i_done = 0, i_next = booted ? n4 : NT;
 #pragma unroll 1
-                for (int i_next = 3 * NT; i_done < n4; i_next = 2 * i_next + NT) {
-                    if (more || i_done == NT) {
+                while (i_done < n4) {
+                    const int i_hi = min(n4, i_next);
+                    if (!booted && i_done > 0 && (more || i_done == NT)) {
                         __syncthreads();
                         const uint32_t ob = refresh();
                         // (a count beyond the region is an overflow: left alone, the check after the block sees it)
@@ -820,13 +866,11 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                             compact_appended(app, &st, n_app_seen, ob);
                         prof.lap(9);
                     }
-                    const int i_hi = (more || i_next < 7 * NT) ? min(n4, i_next) : n4;
                     select_range(i_done, i_hi, rows_b, row0, tau, count_from);
-                    prof.lap(10);
+                    if (!booted) prof.lap(10);
                     i_done = i_hi;
+                    i_next = (!booted && (more || i_next < 3 * NT)) ? 2 * i_next + NT : n4;
                 }
-            } else {
-                select_range(0, n4, rows_b, row0, tau, count_from);
             }
             flush_cta(rows_b, row0, tau, count_from);
             __syncthreads();
