@@ -159,11 +159,12 @@ def profiled_traffic(mode="scan"):
         return None, None
 
 
-def smem_atomic_ceiling():
-    """Measured shared-memory fp32 atomic-add rate of one B200 (all SMs), from the committed micro-benchmark run."""
+def smem_atomic_ceiling(op="atomicAdd(uint32)"):
+    """Measured shared-memory atomic-add rate of one B200 (all SMs), from the committed micro-benchmark run: the native
+    32-bit integer add K3 issues on a binary index (fixed-point weights), or the fp32 CAS loop of a valued index."""
     try:
         with open(os.path.join(ROOT, "profiles", "r2e_smem_atomics.json")) as f:
-            return float(json.load(f)["atomicAdd(float) CAS loop"]["ops_per_s"]), "profiles/r2e_smem_atomics.json (scripts/micro/smem_atomics.cu)"
+            return float(json.load(f)[op]["ops_per_s"]), f"profiles/r2e_smem_atomics.json (scripts/micro/smem_atomics.cu), {op}"
     except Exception:  # noqa: BLE001
         return None, None
 
@@ -419,8 +420,10 @@ def run_cfg2(ctx):
                     "kernel_share_of_step": m["kernel_share_of_step"],
                     "frac_of_8TBps": (achieved / 8000.0) if achieved else None, "q_tile": 1}
         if used != "scan":
-            # K3 is bound by shared-memory read-modify-write throughput, not HBM: postings/s against the measured ceiling of
-            # the operation it issues (atomicAdd(float) in shared memory = an ATOMS.CAST.SPIN loop; scripts/micro/smem_atomics.cu)
+            # K3's work is shared-memory read-modify-writes, not HBM bytes: postings/s against the measured ceiling of the
+            # operation it issues on this binary index (ATOMS.ADD on fixed-point weights; the fp32 CAS loop of valued
+            # indices peaks at a third of that; scripts/micro/smem_atomics.cu).  The kernel is latency- and
+            # barrier-bound well below either (profiles/README.md)
             postings = args.qnnz * (n_loc * TOKENS / V)
             ceil_ops, ceil_src = smem_atomic_ceiling()
             pps = B * postings / (kern_ms * 1e-3) if kern_ms > 0 else None
