@@ -113,11 +113,14 @@ static int64_t query_chunk(const vs_index *idx, int64_t B, int k) {
     c = c < 16 ? 16 : (c > kQueryChunk ? kQueryChunk : c);
     return B < c ? B : c;
 }
-// auto-mode cost model; refined from measurements (profiles/)
+// auto-mode cost model, fitted to profiles/r2n_sweep_*.jsonl (21M rows, 32..768 tokens per query, 1 GPU): a query through
+// the inverted lists costs postings / rate + rows * kInvSecPerRow + kInvFixedSec (36 us at 64 tokens on the binary
+// config-2 index, 69 us on the fp32 config-5 index), through the scan one pass over the stream
 constexpr double kScanBytesPerSecPair = 5.6e12;   // binary / 16-bit values
 constexpr double kScanBytesPerSecF32 = 6.2e12;    // fp32 values (HBM bound)
-constexpr double kInvPostingsPerSec = 3.5e11;     // shared-memory atomics, all SMs
-constexpr double kInvSecPerRow = 1.8e-12;         // zero + select of the block accumulators
+constexpr double kInvPostingsPerSecBinary = 3.7e11;   // fixed-point integer adds
+constexpr double kInvPostingsPerSecValued = 2.5e11;   // fp32 CAS loops + the value loads
+constexpr double kInvSecPerRow = 0.8e-12;         // zero + select of the block accumulators
 constexpr double kInvFixedSec = 5.0e-6;
 
 
@@ -411,7 +414,7 @@ static int search_impl(const vs_index *cidx, const QueryInput &in, int64_t B, in
         if (try_inv) {
             rc = inverted_prepare(idx, w.qprep, vpad, sparse_q ? sq.ptr : nullptr, sq.ptr_dtype, sparse_q ? sq.tok : nullptr,
                                   sparse_q ? sq.w : nullptr, sparse_q ? sq.b0 : 0, Bc, mode, score_round, t_scan,
-                                  kInvPostingsPerSec, t_rows_fixed, w.inv, w.flag, st);
+                                  idx->kind == 1 ? kInvPostingsPerSecValued : kInvPostingsPerSecBinary, t_rows_fixed, w.inv, w.flag, st);
             if (rc) return rc;
             idx->last_mode_on_device = true;
         } else {
