@@ -27,6 +27,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--prof", action="store_true")
 ap.add_argument("--mode", default="scan")
 ap.add_argument("--check", action="store_true", help="compare the scan's ids with the inverted lists'")
+ap.add_argument("--sparse-queries", action="store_true", help="queries as (token, weight) lists (torch sparse CSR), as bench.py sends them")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -44,6 +45,8 @@ del cols, crow
 index.search_mode = args.mode
 eng = index._require_engine()
 q = bench.gen_queries(b=args.batch, nnz=args.qnnz).to(dev)
+if args.sparse_queries:
+    q = q.to_sparse_csr()
 n_ctas = torch.cuda.get_device_properties(0).multi_processor_count
 for _ in range(2):
     index.search(q, args.k)
@@ -67,7 +70,7 @@ out = {"rows": args.rows, "batch": args.batch, "k": args.k, "mode": index.last_m
        "GBps_algorithmic": args.batch * bytes_pass / (kms * 1e-3) / 1e9, "qps": args.batch / (call_ms * 1e-3),
        "stream_bytes": eng.stream_bytes}
 if args.prof and index.last_mode() == "scan":
-    buf = torch.zeros(n_ctas * args.batch * 16, dtype=torch.int64, device=dev)
+    buf = torch.zeros(n_ctas * args.batch * 8, dtype=torch.int64, device=dev)
     nat.check(nat.LIB.vs_debug_scan_profile(eng.handle, ctypes.c_void_p(buf.data_ptr())))
     index.search(q, args.k)
     torch.cuda.synchronize()

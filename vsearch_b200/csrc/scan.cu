@@ -576,15 +576,19 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_bin_kernel(const ScanPar
 
     if (p.use_inv != nullptr && *p.use_inv != 0) return;   // auto mode chose the inverted lists for this chunk
     uint32_t phase = 0;
+    const uint4 *cp = p.cols + (uint64_t)w_begin * 32ull + lane;
+    uint4 r[kBinC];   // the step being processed; refilled chunk by chunk with the next step's (process_step8)
     for (int b = 0; b < p.B; ++b) {
         prof_mark(p, b, 0);
         // the first step's loads go out before anybody waits for the query vector
-        const uint4 *cp = p.cols + (uint64_t)w_begin * 32ull + lane;
-        uint4 r[kBinC];
         const BinSmem L = bin_smem(smem, p);
         stage_query<kScanThreads>(smem, &st, p, b, phase, [&] {
+            // (passes after the first find step 0 already in r[]: the last step of the previous pass wrapped around,
+            // so the loads were in flight under that pass's final write and this query's staging)
+            if (b == 0 || nstep == 0) {
 #pragma unroll
-            for (int i = 0; i < kBinC; ++i) r[i] = ldg_stream(cp + i * 32);
+                for (int i = 0; i < kBinC; ++i) r[i] = ldg_stream(cp + i * 32);
+            }
             for (int i = tid; i < kHistFine + kHistCoarse; i += kScanThreads) L.fine[i] = 0u;   // coarse follows fine
         });
         prof_mark(p, b, 1);
@@ -605,12 +609,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_bin_kernel(const ScanPar
                 join_if_needed<kScanThreads, kScanWarps>(gate, epoch, f.total, L.cbuf, n_keys, p.k, L.hist, &st);
             }
             const float tau_s = gate_tau_score(gate_load(&st));
+            const uint4 *nx = s + 1 < nstep ? cp + (size_t)(s + 1) * SC : cp;   // the last step wraps around: step 0, for the next query
             if (f.multi)
-                process_step8<ROUND, DIAG, true>(r, cp + (size_t)(s + 1) * SC, f, qs, lane, lt, carry, row, n_keys, tau_s, smem,
-                                                 &st, p, b);
+                process_step8<ROUND, DIAG, true>(r, nx, f, qs, lane, lt, carry, row, n_keys, tau_s, smem, &st, p, b);
             else
-                process_step8<ROUND, DIAG, false>(r, cp + (size_t)(s + 1) * SC, f, qs, lane, lt, carry, row, n_keys, tau_s, smem,
-                                                  &st, p, b);
+                process_step8<ROUND, DIAG, false>(r, nx, f, qs, lane, lt, carry, row, n_keys, tau_s, smem, &st, p, b);
         }
         if (warp == 0) prof_mark(p, b, 4);
         finish_streaming<kScanThreads, kScanWarps>(epoch, L.cbuf, n_keys, p.k, L.hist, &st);
