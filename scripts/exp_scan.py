@@ -28,23 +28,31 @@ ap.add_argument("--prof", action="store_true")
 ap.add_argument("--mode", default="scan")
 ap.add_argument("--check", action="store_true", help="compare the scan's ids with the inverted lists'")
 ap.add_argument("--sparse-queries", action="store_true", help="queries as (token, weight) lists (torch sparse CSR), as bench.py sends them")
+ap.add_argument("--zipf", action="store_true", help="Zipf(1) token popularity in rows (160 draws, duplicates dropped) and queries (scripts/sweep_crossover.py cfg2_zipf)")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
 bench.N_TOTAL = args.rows
-cols = bench.gen_rows(0, args.rows, dev, tokens=args.tokens)
-crow = torch.arange(args.rows + 1, device=dev, dtype=torch.int64) * args.tokens
+if args.zipf:
+    sys.argv = sys.argv[:1]
+    import sweep_crossover as sw   # noqa: E402  (same directory)
+
+    crow, cols = sw.zipf_rows(args.rows, 160, 1234)
+else:
+    cols = bench.gen_rows(0, args.rows, dev, tokens=args.tokens)
+    crow = torch.arange(args.rows + 1, device=dev, dtype=torch.int64) * args.tokens
 torch.cuda.synchronize()
 import time  # noqa: E402
 
 t0 = time.perf_counter()
+nnz_total = int(cols.numel())
 index = vs.BoTIndex.from_token_csr(crow, cols.reshape(-1), (args.rows, bench.V), device=dev)
 torch.cuda.synchronize()
 build_s = time.perf_counter() - t0
 del cols, crow
 index.search_mode = args.mode
 eng = index._require_engine()
-q = bench.gen_queries(b=args.batch, nnz=args.qnnz).to(dev)
+q = sw.queries(args.batch, args.qnnz, zipf=True) if args.zipf else bench.gen_queries(b=args.batch, nnz=args.qnnz).to(dev)
 if args.sparse_queries:
     q = q.to_sparse_csr()
 n_ctas = torch.cuda.get_device_properties(0).multi_processor_count
@@ -64,7 +72,7 @@ for _ in range(args.reps):
     if best is None or kms < best[0]:
         best = (kms, call_ms)
 kms, call_ms = best
-bytes_pass = args.rows * args.tokens * 2 + (args.rows + 1) * 4
+bytes_pass = nnz_total * 2 + (args.rows + 1) * 4
 out = {"rows": args.rows, "batch": args.batch, "k": args.k, "mode": index.last_mode(), "build_s": round(build_s, 2),
        "kernel_ms": kms, "call_ms": call_ms, "us_per_pass": kms * 1e3 / args.batch,
        "GBps_algorithmic": args.batch * bytes_pass / (kms * 1e-3) / 1e9, "qps": args.batch / (call_ms * 1e-3),

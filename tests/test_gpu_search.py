@@ -332,6 +332,43 @@ def test_inverted_binary_index_fixed_point_and_fp32_queries(cuda_device):
     assert msg is None, msg
 
 
+def test_inverted_binary_index_many_blocks_per_cta_and_popular_tokens(cuda_device, monkeypatch):
+    """K3 with several row blocks per CTA on a binary index (block size forced down to 2,048 rows: 196 blocks on 148
+    SMs): blocks after a CTA's first one catch the rows that cross the pre-filter while the postings are added instead
+    of scanning the sums, and three tokens that sit in (almost) every row have lists longer than 1,024 postings per
+    block -- the vectorised all-threads path.  Grid weights: bit-exact against the oracle, for fixed-point queries and
+    for one with a negative weight (fp32 path, scanned blocks)."""
+    monkeypatch.setenv("VSEARCH_B200_K3_BLOCK_ROWS", "2048")
+    n, m = 400_000, 24
+    crow, col, val = stratified_csr(n, V, m, seed=51, binary=True, jitter=5)
+    # popular tokens: column 7 in every row, 11 in two rows of three, 13 in every row but the first 1,000 (odd list starts)
+    rows = torch.arange(n)
+    extra_r = torch.cat([rows, rows[rows % 3 != 0], rows[1000:]])
+    extra_c = torch.cat([torch.full((n,), 7), torch.full((int((rows % 3 != 0).sum()),), 11), torch.full((n - 1000,), 13)])
+    crow_t = torch.as_tensor(crow).to(torch.int64)
+    r_all = torch.cat([torch.repeat_interleave(rows, crow_t[1:] - crow_t[:-1]), extra_r])
+    c_all = torch.cat([torch.as_tensor(col).to(torch.int64), extra_c])
+    X = torch.sparse_coo_tensor(torch.stack([r_all, c_all]), torch.ones(r_all.numel()), (n, V)).coalesce()
+    X = (X.to_sparse_csr())
+    crow2, col2 = X.crow_indices(), X.col_indices()
+    val2 = torch.ones(col2.numel())
+    Xb = ref_search.torch_csr(crow2, col2, val2, (n, V))
+    idx = _mk("BoTIndex", crow2, col2, val2, (n, V))
+    idx.search_mode = "inverted"
+    q = sparse_queries(5, V, 48, seed=17)
+    q[:, 7] = torch.tensor([1.0, 0.5, 2.0, 0.25, 1.5])
+    q[:, 11] = torch.tensor([0.75, 1.0, 0.0, 3.0, 0.5])
+    q[:, 13] = torch.tensor([2.0, 0.0, 1.0, 1.0, 0.25])
+    q[4, 11] = -0.5                                   # one query off the fixed-point path
+    ref = ref_search.ref_scores(q, Xb)
+    for k in (10, 200):
+        msg = ref_search.compare_results(idx.search(q, k), ref, k, exact=True)
+        assert msg is None, f"k={k}: {msg}"
+    assert idx.last_mode() == "inverted"
+    idx.search_mode = "scan"
+    assert ref_search.compare_results(idx.search(q, 200), ref, 200, exact=True) is None
+
+
 def test_inverted_ascending_scores_replay_path(cuda_device):
     """K3 worst case: scores increase with the row id, so after the sampling phase EVERY row beats the threshold;
     the optimistic whole-block pass overflows the append region and each block is replayed stepwise with joins.

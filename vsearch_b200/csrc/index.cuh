@@ -58,6 +58,7 @@ struct vs_index {
 
     // ---- K3 block-partitioned token-major inverted lists (built lazily from the WS stream on first use)
     bool inv_built = false;
+    bool inv_has_long = false;   // some (block, token) list is longer than kLongList: K3 runs its long-list variant
     // rows are cut into n_blocks blocks of blk_rows rows; each block has its own token-major lists (inverted.cu)
     int blk_rows = 0, n_blocks = 0, blocks_per_cta = 0;
     uint64_t *post_ptr = nullptr;   // n_cols + 1: global postings per token (exclusive prefix; cost model)

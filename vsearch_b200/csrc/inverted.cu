@@ -41,6 +41,15 @@ constexpr int kInvAppend = 4096;      // keys in the CTA-wide append region (>= 
 constexpr int kInvQueue = 64;         // per-warp queue of accumulator float4s that passed the pre-filter (drained 32 at a time)
 static_assert(kInvAppend >= kInvThreads * 4, "a replay step must fit the append region");
 constexpr int kTokTile = 512;         // query tokens staged per pass over a block
+constexpr uint32_t kLongList = 1024;  // postings; longer (block, token) lists are shared by all warps of the CTA
+// Long lists (popular tokens: the rows of consecutive postings are consecutive or nearly so) start on a 16-byte
+// boundary and are stored TRANSPOSED inside every full chunk of 256 postings: posting l + 32 j of the chunk sits at
+// position 8 l + j.  One 16-byte load then hands lane l the postings l, l + 32, ..., l + 224, and the j-th atomics of a
+// warp go to 32 consecutive rows = 32 different banks; read in list order, eight consecutive rows per lane, they would
+// hit 4 banks 8 ways.  The tail (< 256 postings) stays in list order.
+__host__ __device__ __forceinline__ uint32_t long_list_pos(uint32_t rel, uint32_t len) {
+    return rel < (len & ~255u) ? ((rel & ~255u) | ((rel & 31u) << 3) | ((rel >> 5) & 7u)) : rel;
+}
 
 struct BlockLists {
     uint2 *blk_rng;        // [V, n_blocks]: (start, end) of the token's list inside the block's posting region
@@ -83,7 +92,20 @@ __global__ void __launch_bounds__(kInvBuildThreads, 1) inv_build_kernel(const Ws
     const int V = bl.V, tid = threadIdx.x, b = blockIdx.x;
     if (tid == 0) s_total = 0;
     const size_t nb = (size_t)bl.n_blocks;
-    for (int i = tid; i < V; i += kInvBuildThreads) s_cnt[i] = FILL ? bl.blk_rng[(size_t)i * nb + b].x : 0u;
+    uint32_t *s_long = s_cnt + V;   // FILL: one bit per token, set for long lists
+    if constexpr (FILL) {
+        for (int i = tid; i < (V + 31) / 32; i += kInvBuildThreads) s_long[i] = 0u;
+        __syncthreads();
+    }
+    for (int i = tid; i < V; i += kInvBuildThreads) {
+        if constexpr (FILL) {
+            const uint2 rg = bl.blk_rng[(size_t)i * nb + b];
+            s_cnt[i] = rg.x;
+            if (rg.y - rg.x > kLongList) atomicOr(&s_long[i >> 5], 1u << (i & 31));
+        } else {
+            s_cnt[i] = 0u;
+        }
+    }
     __syncthreads();
     const int64_t r0 = (int64_t)b * bl.rows_per_block;
     const int64_t r1 = min(idx.n_rows, r0 + bl.rows_per_block);
@@ -100,7 +122,11 @@ __global__ void __launch_bounds__(kInvBuildThreads, 1) inv_build_kernel(const Ws
                 if (c >= (uint32_t)V) continue;  // padding
                 const uint32_t slot = atomicAdd(&s_cnt[c], 1u);
                 if constexpr (FILL) {
-                    const uint64_t pos = base + slot;
+                    uint64_t pos = base + slot;
+                    if (s_long[c >> 5] & (1u << (c & 31))) {   // a long list: transposed chunks (long_list_pos)
+                        const uint2 rg = __ldg(&bl.blk_rng[(size_t)c * nb + b]);
+                        pos = base + rg.x + long_list_pos(slot - rg.x, rg.y - rg.x);
+                    }
                     bl.post_row[pos] = (uint16_t)(r - r0);
                     if (idx.kind == 1) {
                         const uint64_t src = ch * 8ull + e;
@@ -115,20 +141,24 @@ __global__ void __launch_bounds__(kInvBuildThreads, 1) inv_build_kernel(const Ws
         __syncthreads();
         const int per = (V + kInvBuildThreads - 1) / kInvBuildThreads;
         const int lo = min(V, tid * per), hi = min(V, lo + per);
-        uint64_t sum = 0;
-        for (int i = lo; i < hi; ++i) sum += s_cnt[i];
+        uint64_t sum = 0;   // slots: a long list gets 7 spare ones so that it can start on a 16-byte boundary
+        for (int i = lo; i < hi; ++i) sum += s_cnt[i] + (s_cnt[i] > kLongList ? 7u : 0u);
         atomicAdd(&s_total, (unsigned long long)sum);
         uint32_t total;
         uint32_t run = block_exclusive_scan<kInvBuildThreads>((uint32_t)sum, s_warp, total);
         for (int i = lo; i < hi; ++i) {
             const uint32_t c = s_cnt[i];
-            bl.blk_rng[(size_t)i * nb + b] = make_uint2(run, run + c);
-            run += c;
+            const bool lng = c > kLongList;
+            if (lng) atomicOr(err, 2);   // the index has long lists (vs_index::inv_has_long)
+            const uint32_t start = lng ? (run + 7u) & ~7u : run;
+            bl.blk_rng[(size_t)i * nb + b] = make_uint2(start, start + c);
+            run += c + (lng ? 7u : 0u);
             if (c) atomicAdd((unsigned long long *)&bl.tok_total[i], (unsigned long long)c);
         }
+        __syncthreads();
         if (tid == 0) {
-            if (s_total >= (1ull << 32)) atomicExch(err, 1);
-            bl.blk_base[b] = s_total;  // sizes now, exclusive prefix after the host-side scan
+            if (s_total >= (1ull << 32) - 8ull) atomicOr(err, 1);
+            bl.blk_base[b] = (s_total + 7ull) & ~7ull;  // sizes now (multiples of 8: every block starts aligned), exclusive prefix after the host-side scan
         }
     }
 }
@@ -138,7 +168,12 @@ __global__ void __launch_bounds__(kInvBuildThreads, 1) inv_build_kernel(const Ws
 // occupies ceil(N / R) CTAs and the grid's query dimension fills the remaining SMs.
 static void block_geometry(const vs_index *idx, int *rows_per_block, int *n_blocks, int *blocks_per_cta) {
     const int64_t N = idx->n_rows > 0 ? idx->n_rows : 1;
-    int64_t R = N < kBlockRowsMax ? N : kBlockRowsMax;
+    int64_t r_max = kBlockRowsMax;
+    if (const char *e = getenv("VSEARCH_B200_K3_BLOCK_ROWS")) {   // tests: several blocks per CTA on a small index
+        const long v = atol(e);
+        if (v >= 64 && v < kBlockRowsMax) r_max = v / 4 * 4;
+    }
+    int64_t R = N < r_max ? N : r_max;
     int64_t nb = (N + R - 1) / R;
     int64_t bpc = (nb + idx->n_ctas - 1) / idx->n_ctas;
     if (nb > idx->n_ctas) {   // a large index: equal blocks, the same number for every CTA
@@ -154,7 +189,7 @@ static void block_geometry(const vs_index *idx, int *rows_per_block, int *n_bloc
 int build_inverted(vs_index *idx, cudaStream_t st) {
     if (idx->inv_built) return VS_OK;
     const int V = (int)idx->n_cols;
-    const size_t smem = (size_t)V * 4;
+    const size_t smem = (size_t)V * 4 + (size_t)((V + 31) / 32) * 4;
     VS_REQUIRE(smem <= 200 * 1024, VS_ERR_UNSUPPORTED, "vocabulary too large for the inverted-list builder");
     block_geometry(idx, &idx->blk_rows, &idx->n_blocks, &idx->blocks_per_cta);
     const int nb = idx->n_blocks;
@@ -169,9 +204,11 @@ int build_inverted(vs_index *idx, cudaStream_t st) {
     VS_CUDA(cudaMalloc(&idx->blk_ptr, (size_t)nb * V * sizeof(uint2)));
     VS_CUDA(cudaMalloc(&idx->blk_base, (size_t)(nb + 1) * 8));
     VS_CUDA(cudaMemsetAsync(idx->blk_base, 0, (size_t)(nb + 1) * 8, st));
-    VS_CUDA(cudaMalloc(&idx->post_row, idx->nnz ? (size_t)idx->nnz * 2 : 4));
+    // postings + the alignment slack of long lists (< 7 per 1,025 postings) and of the blocks (< 8 each)
+    const size_t n_slots = (size_t)idx->nnz + (size_t)idx->nnz / 128 + (size_t)nb * 8 + 64;
+    VS_CUDA(cudaMalloc(&idx->post_row, n_slots * 2));
     const size_t vbytes = idx->kind == 1 ? (idx->store_dtype == VS_F32 ? 4 : 2) : 0;
-    if (vbytes) VS_CUDA(cudaMalloc(&idx->post_val, idx->nnz ? (size_t)idx->nnz * vbytes : 4));
+    if (vbytes) VS_CUDA(cudaMalloc(&idx->post_val, n_slots * vbytes));
     BlockLists bl;
     bl.blk_rng = (uint2 *)idx->blk_ptr; bl.blk_base = idx->blk_base; bl.post_row = idx->post_row; bl.post_val = idx->post_val;
     bl.tok_total = idx->post_ptr; bl.rows_per_block = idx->blk_rows; bl.n_blocks = nb; bl.V = V;
@@ -192,8 +229,9 @@ int build_inverted(vs_index *idx, cudaStream_t st) {
     if (e == cudaSuccess) e = cudaGetLastError();
     cleanup();
     VS_CUDA(e);
-    VS_REQUIRE(h_err == 0, VS_ERR_UNSUPPORTED, "a row block holds 2^32 or more postings");
-    idx->inv_bytes = (int64_t)((size_t)idx->nnz * (2 + vbytes) + (size_t)nb * V * 8 + (size_t)(V + 1) * 8);
+    VS_REQUIRE((h_err & 1) == 0, VS_ERR_UNSUPPORTED, "a row block holds 2^32 or more postings");
+    idx->inv_has_long = (h_err & 2) != 0;
+    idx->inv_bytes = (int64_t)(n_slots * (2 + vbytes) + (size_t)nb * V * 8 + (size_t)(V + 1) * 8);
     idx->device_bytes += idx->inv_bytes;
     idx->inv_built = true;
     return VS_OK;
@@ -438,7 +476,6 @@ __device__ __forceinline__ void hist_count_plain(uint32_t *coarse, uint32_t *fin
     atomicAdd(&coarse[ob >> 25], n);
 }
 
-constexpr uint32_t kLongList = 1024;   // postings; longer (block, token) lists are shared by all warps of the CTA
 
 // Add w * value at every posting of one list slice: offsets begin, begin + stride, ... < end of the list at `rows`
 // (`vals`: its values, in the index dtype); kInvUnroll loads in flight per lane.  All lanes of a warp work on the SAME
@@ -502,6 +539,87 @@ __device__ __forceinline__ void accumulate_slice_fixed(uint32_t *acc, const uint
     }
 }
 
+// A LONG list (more postings than kLongList: a popular token), worked on by all warps of the CTA.  Its full 256-posting
+// chunks are stored transposed (long_list_pos): a warp takes a chunk with ONE 16-byte load per lane (the scalar loop has 8
+// two-byte loads in flight per lane), lane l gets postings l, l + 32, ..., and the warp's j-th atomics go to consecutive
+// rows.  MODE 0: fp32 sums (CAS loop; values of kind VK), 1: fixed point, 2: fixed point + crossing detection.
+template <int VK, int MODE>
+__device__ __noinline__ void accumulate_long(float *acc, const uint16_t *__restrict__ rows, const void *__restrict__ vals,
+                                                const uint32_t len, const float w, const uint32_t wq, const int tid, const uint32_t tau_u,
+                                                uint16_t *cross_q, uint32_t *cross_n) {
+    uint32_t *accu = reinterpret_cast<uint32_t *>(acc);
+    const int lane = tid & 31, warp = tid >> 5;
+    auto add = [&](const uint32_t r, const float v) {
+        if constexpr (MODE == 0) {
+            atomicAdd(&acc[r], v);
+        } else if constexpr (MODE == 1) {
+            atomicAdd(&accu[r], wq);
+        } else {
+            const uint32_t old = atomicAdd(&accu[r], wq);
+            if (old < tau_u && old + wq >= tau_u) {
+                const uint32_t slot = atomicAdd(cross_n, 1u);
+                if (slot < kCrossCap) cross_q[slot] = (uint16_t)r;
+            }
+        }
+    };
+    auto value = [&](const uint32_t pos) -> float {
+        if constexpr (MODE != 0 || VK == 0) return w;
+        else if constexpr (VK == 1) return w * ((const float *)vals)[pos];
+        else if constexpr (VK == 2) return w * __half2float(((const __half *)vals)[pos]);
+        else return w * __bfloat162float(((const __nv_bfloat16 *)vals)[pos]);
+    };
+    const uint32_t n_chunks = len >> 8, full = n_chunks << 8;
+    for (uint32_t i = full + (uint32_t)tid; i < len; i += kInvThreads) add(rows[i], value(i));   // tail, in list order
+    constexpr int U = (MODE == 0 && VK == 1) ? 1 : 2;   // chunks in flight per warp (register budget: 80 per thread)
+    for (uint32_t c0 = (uint32_t)warp; c0 < n_chunks; c0 += kInvWarps * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t c = c0 + (uint32_t)u * kInvWarps;
+            if (c < n_chunks) v[u] = __ldg(reinterpret_cast<const uint4 *>(rows + ((size_t)c << 8)) + lane);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t c = c0 + (uint32_t)u * kInvWarps;
+            if (c < n_chunks) {
+                const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                const uint32_t p0 = (c << 8) + ((uint32_t)lane << 3);   // this lane's 8 positions
+                if constexpr (MODE == 0 && VK == 1) {
+                    const float4 a = __ldg(reinterpret_cast<const float4 *>((const float *)vals + p0));
+                    const float4 b2 = __ldg(reinterpret_cast<const float4 *>((const float *)vals + p0) + 1);
+                    const float f[8] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) add((e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xffffu), w * f[e]);
+                } else if constexpr (MODE == 0 && (VK == 2 || VK == 3)) {
+                    const uint4 hv = __ldg(reinterpret_cast<const uint4 *>((const uint16_t *)vals + p0));
+                    const uint32_t h4[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const uint16_t bits = (uint16_t)((e & 1) ? (h4[e >> 1] >> 16) : (h4[e >> 1] & 0xffffu));
+                        float fv;
+                        if constexpr (VK == 2) fv = __half2float(__ushort_as_half(bits));
+                        else fv = __uint_as_float((uint32_t)bits << 16);
+                        add((e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xffffu), w * fv);
+                    }
+                } else if constexpr (MODE == 2) {   // all eight adds go out before the first old sum is looked at
+                    uint32_t old[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) old[e] = atomicAdd(&accu[(e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xffffu)], wq);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (old[e] < tau_u && old[e] + wq >= tau_u) {
+                            const uint32_t slot = atomicAdd(cross_n, 1u);
+                            if (slot < kCrossCap) cross_q[slot] = (uint16_t)((e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xffffu));
+                        }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) add((e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xffffu), w);
+                }
+            }
+        }
+    }
+}
+
 // Drop the keys of the append region that fell below the histogram bound `ob` (ordered score bits): called by all
 // threads of the CTA with the same (n_app, ob), nobody appending meanwhile.  Ends with a barrier.
 static __device__ __noinline__ void compact_appended(uint64_t *app, CtaState *st, const uint32_t n_app, const uint32_t ob) {
@@ -520,7 +638,9 @@ static __device__ __noinline__ void compact_appended(uint64_t *app, CtaState *st
     __syncthreads();
 }
 
-template <int VK, bool ROUND>
+// LONG: the index has lists longer than kLongList (popular tokens) -- their vectorised all-warps path is compiled in.  It
+// costs the rest of the kernel registers and ~8 % of its speed, so an index without such lists runs the variant without.
+template <int VK, bool ROUND, bool LONG>
 __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSearchParams p) {
     constexpr int NT = kInvThreads, NW = kInvWarps;
     constexpr int vbytes = VK == 0 ? 0 : (VK == 1 ? 4 : 2);
@@ -785,16 +905,18 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                 }
             }
             // long lists (heavy-tailed token popularity): every warp takes a share
+            if constexpr (LONG)
             for (int tb = 0; tb < tn; tb += 32) {
                 const int ti_l = tb + lane;
                 uint32_t longm = __ballot_sync(0xffffffffu, ti_l < tn && s_len[ti_l] > kLongList);
                 for (; longm; longm &= longm - 1) {
                     const int ti = tb + __ffs(longm) - 1;
                     const uint64_t at = base + s_beg[ti];
-                    if (cross) accumulate_slice_fixed<true>(accu, p.post_row + at, (uint32_t)tid, s_len[ti], (uint32_t)NT, __float2uint_rn(s_w[ti] * fx_scale), cross_tau, s_queue, &s_cross_n);
-                    else if (fixed) accumulate_slice_fixed<false>(accu, p.post_row + at, (uint32_t)tid, s_len[ti], (uint32_t)NT, __float2uint_rn(s_w[ti] * fx_scale), 0u, nullptr, nullptr);
-                    else accumulate_slice<VK>(acc, p.post_row + at, (const uint8_t *)p.post_val + at * vbytes, (uint32_t)tid, s_len[ti],
-                                              (uint32_t)NT, s_w[ti]);
+                    const uint16_t *lr = p.post_row + at;
+                    const void *lv = (const uint8_t *)p.post_val + at * vbytes;
+                    if (cross) accumulate_long<VK, 2>(acc, lr, lv, s_len[ti], s_w[ti], __float2uint_rn(s_w[ti] * fx_scale), tid, cross_tau, s_queue, &s_cross_n);
+                    else if (fixed) accumulate_long<VK, 1>(acc, lr, lv, s_len[ti], s_w[ti], __float2uint_rn(s_w[ti] * fx_scale), tid, 0u, nullptr, nullptr);
+                    else accumulate_long<VK, 0>(acc, lr, lv, s_len[ti], s_w[ti], 0u, tid, 0u, nullptr, nullptr);
                 }
             }
         }
@@ -1044,11 +1166,18 @@ int launch_inverted(vs_index *idx, int64_t Bc, int k, int cand_stride, int score
         return VS_OK;
     };
     const bool rnd = score_round != VS_F32;
+    if (idx->inv_has_long)
+        switch (p.val_kind) {
+            case 0: return rnd ? launch(inv_search_kernel<0, true, true>) : launch(inv_search_kernel<0, false, true>);
+            case 1: return rnd ? launch(inv_search_kernel<1, true, true>) : launch(inv_search_kernel<1, false, true>);
+            case 2: return rnd ? launch(inv_search_kernel<2, true, true>) : launch(inv_search_kernel<2, false, true>);
+            default: return rnd ? launch(inv_search_kernel<3, true, true>) : launch(inv_search_kernel<3, false, true>);
+        }
     switch (p.val_kind) {
-        case 0: return rnd ? launch(inv_search_kernel<0, true>) : launch(inv_search_kernel<0, false>);
-        case 1: return rnd ? launch(inv_search_kernel<1, true>) : launch(inv_search_kernel<1, false>);
-        case 2: return rnd ? launch(inv_search_kernel<2, true>) : launch(inv_search_kernel<2, false>);
-        default: return rnd ? launch(inv_search_kernel<3, true>) : launch(inv_search_kernel<3, false>);
+        case 0: return rnd ? launch(inv_search_kernel<0, true, false>) : launch(inv_search_kernel<0, false, false>);
+        case 1: return rnd ? launch(inv_search_kernel<1, true, false>) : launch(inv_search_kernel<1, false, false>);
+        case 2: return rnd ? launch(inv_search_kernel<2, true, false>) : launch(inv_search_kernel<2, false, false>);
+        default: return rnd ? launch(inv_search_kernel<3, true, false>) : launch(inv_search_kernel<3, false, false>);
     }
 }
 
