@@ -640,7 +640,8 @@ static __device__ __noinline__ void compact_appended(uint64_t *app, CtaState *st
 
 // LONG: the index has lists longer than kLongList (popular tokens) -- their vectorised all-warps path is compiled in.  It
 // costs the rest of the kernel registers and ~8 % of its speed, so an index without such lists runs the variant without.
-template <int VK, bool ROUND, bool LONG>
+// PROF: the phase timers of vs_debug_scan_profile (compiled for the binary, unrounded variants only).
+template <int VK, bool ROUND, bool LONG, bool PROF = false>
 __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSearchParams p) {
     constexpr int NT = kInvThreads, NW = kInvWarps;
     constexpr int vbytes = VK == 0 ? 0 : (VK == 1 ? 4 : 2);
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
     const size_t nb = (size_t)p.n_blocks;
     __shared__ uint32_t s_ob, s_qn[kInvWarps], s_cross_n;
     InvProf prof;
-    prof.start(p.prof != nullptr && tid == 0);
+    prof.start(PROF && p.prof != nullptr && tid == 0);
     if (tid == 0) cta_state_reset(&st);
     for (int i = tid; i < kHistFine + kHistCoarse; i += NT) fine[i] = 0u;   // coarse follows fine
     if (cached && tid < cnt) { s_tok[tid] = tok[tid]; s_w[tid] = w[tid]; }
@@ -1077,7 +1078,7 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
             for (int i = p.k + tid; i < p.kout; i += NT) out[i] = 0ull;
         }
     }
-    if (prof.on) {
+    if (PROF && prof.on) {
         prof.lap(6);
         prof.acc[7] = prof.t - prof.acc[7];
         for (int i = 0; i < 16; ++i) p.prof[((size_t)q * p.n_lists + blockIdx.x) * 16 + i] = prof.acc[i];
@@ -1166,6 +1167,8 @@ int launch_inverted(vs_index *idx, int64_t Bc, int k, int cand_stride, int score
         return VS_OK;
     };
     const bool rnd = score_round != VS_F32;
+    if (p.prof != nullptr && p.val_kind == 0 && !rnd)
+        return idx->inv_has_long ? launch(inv_search_kernel<0, false, true, true>) : launch(inv_search_kernel<0, false, false, true>);
     if (idx->inv_has_long)
         switch (p.val_kind) {
             case 0: return rnd ? launch(inv_search_kernel<0, true, true>) : launch(inv_search_kernel<0, false, true>);
