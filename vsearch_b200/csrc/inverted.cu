@@ -508,6 +508,7 @@ __device__ __forceinline__ void accumulate_slice(float *acc, const uint16_t *__r
 // the list adds the token's integer weight, and 32-bit integer adds ARE native on shared memory (ATOMS.ADD, no CAS loop:
 // three times the CAS ceiling in scripts/micro/smem_atomics.cu).
 constexpr uint32_t kCrossCap = kInvWarps * kInvQueue;   // rows the crossing queue holds (it lives in the hit queues' memory)
+constexpr uint32_t kCrossMaxPostings = 24576;           // per (query, block): beyond, scanning the sums is cheaper than returning adds
 
 // CROSS: the adds return the old sums, and a row whose sum climbs over the pre-filter `tau_u` with this posting (weights
 // are positive: that happens once per row) is noted in the CTA's crossing queue -- the select then has nothing to scan.
@@ -855,7 +856,9 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
         // that end up above it are caught while they cross it (accumulate_slice_fixed<true>) and the block's select
         // only visits those instead of scanning 37 K sums for the ~150 that matter.
         const uint32_t cross_tau = fx_floor(tau_s);
-        const bool cross = fixed && booted && !exact && cached && cross_tau > 0u;
+        // ... when the block has few enough postings for this query: the adds that return the old sum cost ~70 ps more per
+        // posting than the fire-and-forget ones, the scan they save ~2.3 us per block (heavy-tailed lists: 600 K postings)
+        bool cross = fixed && booted && !exact && cached && cross_tau > 0u;
         if (tid == 0) s_cross_n = 0u;   // (ordered before the first add by the barrier below)
         for (int i = tid; i < (R >> 2); i += NT) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         // ---- accumulate: tiles of <= kTokTile query tokens
@@ -875,6 +878,14 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
             }
             if (tid < tn) { s_beg[tid] = rng.x; s_len[tid] = rng.y - rng.x; }
             __syncthreads();  // also orders the zeroing above before the first atomic
+            if constexpr (LONG) {   // (an index without long lists has at most 1,024 postings per token and block)
+                if (cross) {   // (cached: this is the only tile) every warp adds up the block's postings for itself
+                    uint32_t n_post = 0;
+                    for (int i = lane; i < tn; i += 32) n_post += s_len[i];
+                    n_post = __reduce_add_sync(0xffffffffu, n_post);
+                    cross = n_post <= kCrossMaxPostings;
+                }
+            }
             prof.lap(1);
             if (p.flags & 1) {   // the heads of this tile's lists -> L1 (a warp walks its lists one after the other)
                 for (int i = tid; i < tn * 8; i += NT) {
