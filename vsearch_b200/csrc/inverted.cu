@@ -458,7 +458,8 @@ __device__ __forceinline__ float posting_value(const void *vals, int kind, uint6
     return __bfloat162float(((const __nv_bfloat16 *)vals)[pos]);
 }
 
-constexpr int kInvUnroll = 8;          // posting loads in flight per lane
+constexpr int kInvUnroll = 6;          // posting loads in flight per lane (6 x 32 covers the ~150-posting lists of the 21M-row configs in one go;
+                                       // measured: 8 -> 6 = 33.8 -> 32.0 us per query on config 2, fewer dead slots and registers)
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
