@@ -20,8 +20,11 @@
 //
 // Host side (search_dense): threshold from an exact top-k of a sample prefix -> filtered sweeps over the rest of the
 // index (the threshold is tightened once after the first ~1M rows) -> exact top-k of the survivors with the K6 merge
-// kernel.  If a candidate list overflows (adversarial ordering) the threshold is tightened from the stored candidates
-// and the sweep repeated.
+// kernel.  The whole call is enqueued without reading anything back; a candidate list that overflows (adversarial
+// ordering) raises a status word that is polled once at the end, and such a call is redone through the checked path
+// (counts read after every sweep, an overflowed sweep repeated with the k-th best of what it stored).  Row-sharded
+// (search_dense_step): the same sweeps in three steps, the ranks' [B, k] keys pooled after each, so every rank sweeps
+// 1/W of the sample and filters with the thresholds of the whole index.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 

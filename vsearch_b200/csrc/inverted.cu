@@ -11,14 +11,20 @@
 //             that the bounds a CTA needs for its consecutive blocks share a 32-byte sector), blk_base[n_blocks] (uint64),
 //             post_row[nnz] (uint16) (+ post_val[nnz]), post_ptr[V+1] = global list lengths (cost model) -- lazy
 //   extract : prepared query [vpad] -> compact (token, weight) list + total postings (or the caller's lists as they are)
-//   search  : grid (n_ctas, queries); CTA x owns blocks [x*bpc, (x+1)*bpc) -> one candidate list per CTA -> merge.cu
-// Accumulate: the block's postings of ALL query tokens form one sequence (prefix sums of the list lengths); every warp
-// takes an equal share of it, 32 consecutive postings per load, 8 loads in flight per lane -- balanced whatever the list
-// lengths (heavy-tailed token popularity included), no per-list ramp-up.
-// Thresholds: the score histogram of topk.cuh.  The CTA's first block is counted whole (one pass over its accumulator),
-// the k-th bucket's lower bound becomes the float pre-filter; later blocks count and append only what passes it, and the
-// bound only rises.  At the end everything >= the final bound (k .. ~2k keys) goes to the merge kernel.  The exact
-// 64-bit machinery (CTA-wide radix selects) remains as the fallback for masses of equal scores / adversarial order.
+//   search  : grid (CTAs that own blocks, query lanes); CTA x owns blocks [x*bpc, (x+1)*bpc) and walks the queries
+//             y, y + gridDim.y, ... -> one candidate list per (query, CTA) -> merge.cu
+// Accumulate: one warp per list piece (a list, or half / a quarter of one when the query has few tokens), 32 consecutive
+// postings per load, kInvUnroll loads in flight per lane; lists longer than kLongList postings (popular tokens) are
+// stored transposed in 256-posting chunks and worked on by all warps, a chunk per 16-byte load.  Binary index, positive
+// query weights: the weights go to fixed point (inv_fixed_point_kernel) and the adds are native integer shared-memory
+// atomics instead of fp32 CAS loops; blocks after a CTA's first one then catch the rows whose sums cross the pre-filter
+// while adding (the adds return the old sums) and the select visits only those.
+// Thresholds: the score histogram of topk.cuh.  The first 3,072 rows of a CTA's first block are counted whole, the k-th
+// bucket's lower bound becomes the float pre-filter; everything after counts and appends only what passes it, the bound
+// is refreshed inside the first block and between blocks, and only rises.  Hits of the scan go to per-warp queues that
+// are drained 32 at a time; the leftovers of a block are dealt to a few warps.  At the end everything >= the final bound
+// (k .. ~2k keys) goes to the merge kernel.  The exact 64-bit machinery (CTA-wide radix selects) remains as the fallback
+// for masses of equal scores / adversarial order.
 // Rows never touched keep score 0 and compete like any other row.
 // Algorithmic bytes per query: sum_t len(post_t) * (2 + b_val)  (+ 8 B of list bounds per (block, token)).
 #include <cub/device/device_scan.cuh>
