@@ -2,24 +2,27 @@
 // fused in (K5), for sm_100a.  Replaces `torch.matmul(q, vector.t())` + `scores.topk(k)`
 // (upstream src/ir/retriever/index.py:91-92) for SparseIndex / BoTIndex.
 //
-// One persistent CTA per SM, kScanWarps (24) warps.  Per query ("pass"):
-//   1. the dense fp32 query vector (V+1 slots, slot V = 0 for padding) is pulled into shared
-//      memory with 1-D bulk TMA copies (cp.async.bulk + mbarrier);
+// One persistent CTA per SM, kScanWarps (20) warps.  Per query ("pass"):
+//   1. the dense fp32 query vector (V+1 slots, slot V = 0 for padding) is staged in shared memory: 1-D bulk TMA copies of
+//      the prepared row (cp.async.bulk + mbarrier), or zero + scatter of the caller's (token, weight) list;
 //   2. every warp streams ITS part of the WS index (index.cuh) in steps of 32*C chunks, C consecutive (logical)
 //      chunks per lane stored transposed so every load is a coalesced 512-byte window -- C = 8 for the binary index
-//      (scan_bin_kernel: a whole step in flight per warp), 2 for 16-bit values, 1 for fp32 values (register ring of D
-//      steps); loads never depend on row pointers, the row-end ("tail") flag of a chunk rides in bit 15 of its first
-//      entry; each lane gathers q[col] for its entries from shared memory;
+//      (scan_bin_kernel: a whole step in flight per warp; the last step of a pass wraps around and loads step 0 for the
+//      next query), 2 for 16-bit values, 1 for fp32 values (register ring of D steps); loads never depend on row
+//      pointers, the row-end ("tail") flag of a chunk rides in bit 15 of its first entry; each lane gathers q[col] for
+//      its entries from shared memory;
 //   3. ONE segmented warp scan per step turns lane partials into row scores -- with 8 chunks per lane a row of ~15
 //      chunks spans 2-3 lanes, so the scan needs 1-2 shuffle levels per 256 chunks (the levels nobody needs are
 //      skipped) instead of 5 per 64;
-//   4. the first rows of a pass are sampled into shared memory and ONE CTA-wide radix select sets the threshold;
-//      afterwards a float pre-filter rejects almost every row, rows whose rank key beats the threshold are appended
-//      to the warp's PRIVATE region with plain stores, and a warp whose region runs low raises a join epoch that all
-//      warps poll: one CTA-wide re-selection, no locks, no per-row atomics (topk.cuh);
-//   5. at the end of the pass the CTA selects its exact top-k and writes k keys to HBM.
-// The [B, N] score matrix is never written.  A second tiny kernel (merge.cu) merges the
-// per-CTA lists.
+//   4. thresholds.  Binary kernel: every candidate row is counted in a two-level score histogram (topk.cuh); a warp whose
+//      private region fills asks the histogram for the k-th bucket's bound (no barrier), drops its keys below it and
+//      goes on.  Valued kernels (K1): the first rows of a pass are sampled and ONE CTA-wide radix select sets the
+//      threshold.  Behind both: a float pre-filter rejects almost every row, keys go to the warp's PRIVATE region with
+//      plain stores, and the exact join protocol (one CTA-wide re-selection per epoch, no locks, no per-row atomics)
+//      covers what a score bucket cannot separate;
+//   5. end of pass: the binary kernel hands every key at or above its final bound (k .. 2k + 64) to the merge kernel;
+//      the valued kernels select their exact top-k and write k keys.
+// The [B, N] score matrix is never written.  A second tiny kernel (merge.cu) merges the per-CTA lists.
 #include "index.cuh"
 #include "topk.cuh"
 

@@ -7,6 +7,10 @@ global id = local id + row offset.  Queries are replicated.  Each rank runs the 
 rows and contributes ``k`` packed rank keys per query; ONE all-gather (NCCL over NVLink) moves
 ``W x B x k x 8`` bytes, then every rank merges with the K6 kernel.  Contiguous ranges keep "lower id wins"
 consistent across ranks because the key carries the global id.
+
+A 16-bit dense index goes through three such gathers (``vs_search_dense_step``): the ranks pool their top-k keys
+after the sample sweep and after the second sweep, so every rank sweeps 1/W of the sample and filters with the
+thresholds of the whole index; the last gather is the one above.
 """
 from __future__ import annotations
 
