@@ -28,6 +28,7 @@ ap.add_argument("--prof", action="store_true")
 ap.add_argument("--mode", default="scan")
 ap.add_argument("--check", action="store_true", help="compare the scan's ids with the inverted lists'")
 ap.add_argument("--sparse-queries", action="store_true", help="queries as (token, weight) lists (torch sparse CSR), as bench.py sends them")
+ap.add_argument("--values", action="store_true", help="a valued fp32 SparseIndex (values U(0.01, 2)) instead of the binary one: config 3 / 5 shapes")
 ap.add_argument("--zipf", action="store_true", help="Zipf(1) token popularity in rows (160 draws, duplicates dropped) and queries (scripts/sweep_crossover.py cfg2_zipf)")
 args = ap.parse_args()
 
@@ -46,7 +47,16 @@ import time  # noqa: E402
 
 t0 = time.perf_counter()
 nnz_total = int(cols.numel())
-index = vs.BoTIndex.from_token_csr(crow, cols.reshape(-1), (args.rows, bench.V), device=dev)
+if args.values:
+    from vsearch_b200.index import _Engine   # noqa: E402
+
+    vals = torch.rand(nnz_total, generator=torch.Generator(device=dev).manual_seed(99), device=dev) * 1.99 + 0.01
+    index = vs.SparseIndex()
+    index._engine = _Engine.from_csr(crow, cols.reshape(-1), vals, (args.rows, bench.V), dev)
+    index.device = dev
+    del vals
+else:
+    index = vs.BoTIndex.from_token_csr(crow, cols.reshape(-1), (args.rows, bench.V), device=dev)
 torch.cuda.synchronize()
 build_s = time.perf_counter() - t0
 del cols, crow
@@ -72,7 +82,7 @@ for _ in range(args.reps):
     if best is None or kms < best[0]:
         best = (kms, call_ms)
 kms, call_ms = best
-bytes_pass = nnz_total * 2 + (args.rows + 1) * 4
+bytes_pass = nnz_total * (6 if args.values else 2) + (args.rows + 1) * 4
 out = {"rows": args.rows, "batch": args.batch, "k": args.k, "mode": index.last_mode(), "build_s": round(build_s, 2),
        "kernel_ms": kms, "call_ms": call_ms, "us_per_pass": kms * 1e3 / args.batch,
        "GBps_algorithmic": args.batch * bytes_pass / (kms * 1e-3) / 1e9, "qps": args.batch / (call_ms * 1e-3),

@@ -648,7 +648,7 @@ static __device__ __noinline__ void compact_appended(uint64_t *app, CtaState *st
 
 // LONG: the index has lists longer than kLongList (popular tokens) -- their vectorised all-warps path is compiled in.  It
 // costs the rest of the kernel registers and ~8 % of its speed, so an index without such lists runs the variant without.
-// PROF: the phase timers of vs_debug_scan_profile (compiled for the binary, unrounded variants only).
+// PROF: the phase timers of vs_debug_scan_profile (compiled for the binary and the fp32-valued unrounded variants only).
 template <int VK, bool ROUND, bool LONG, bool PROF = false>
 __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSearchParams p) {
     constexpr int NT = kInvThreads, NW = kInvWarps;
@@ -1187,6 +1187,7 @@ int launch_inverted(vs_index *idx, int64_t Bc, int k, int cand_stride, int score
     const bool rnd = score_round != VS_F32;
     if (p.prof != nullptr && p.val_kind == 0 && !rnd)
         return idx->inv_has_long ? launch(inv_search_kernel<0, false, true, true>) : launch(inv_search_kernel<0, false, false, true>);
+    if (p.prof != nullptr && p.val_kind == 1 && !rnd && !idx->inv_has_long) return launch(inv_search_kernel<1, false, false, true>);
     if (idx->inv_has_long)
         switch (p.val_kind) {
             case 0: return rnd ? launch(inv_search_kernel<0, true, true>) : launch(inv_search_kernel<0, false, true>);
