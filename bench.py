@@ -405,9 +405,9 @@ def run_cfg2(ctx):
             bytes_pass = int(args.qnnz * (n_loc * TOKENS / V)) * 2
             kernel = "vs::inv_search_kernel"
         # our kernels per step: [prep_query (dense rows only)] + scan + merge; auto / inverted add the list kernel (extract
-        # or lists-from-CSR), the decision kernel and the inverted-list kernel (the loser of the two scoring kernels exits
-        # at once); N > 1 adds the merge of the gathered keys
-        launches = steps * ((2 if mode == "scan" else 5) + (1 if args.dense_queries else 0) + (1 if world > 1 else 0))
+        # or lists-from-CSR), the fixed-point kernel (binary index), the decision kernel and the inverted-list kernel (the
+        # loser of the two scoring kernels exits at once); N > 1 adds the merge of the gathered keys
+        launches = steps * ((2 if mode == "scan" else 6) + (1 if args.dense_queries else 0) + (1 if world > 1 else 0))
         achieved = B * bytes_pass / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
         traffic, traffic_src = profiled_traffic(used) if world == 1 else (None, None)
         peak = ctx.peaks["hbm"]
