@@ -547,6 +547,64 @@ __device__ __forceinline__ void accumulate_slice_fixed(uint32_t *acc, const uint
     }
 }
 
+// The short lists of one token tile, fixed point, G pieces of a warp at a time: the postings of all G pieces are asked for
+// before the first add of the group, so a warp waits for one load round trip per G pieces instead of one per piece.
+#ifndef VS_K3_GROUP
+#define VS_K3_GROUP 3
+#endif
+template <bool CROSS, int G>
+__device__ __forceinline__ void accumulate_pieces_fixed(uint32_t *accu, const uint16_t *__restrict__ post_row, const uint64_t base,
+                                                        const uint32_t *s_beg, const uint32_t *s_len, const float *s_w, const float fx_scale,
+                                                        const int tn, const int psh, const int warp, const int lane,
+                                                        const uint32_t tau_u, uint16_t *cross_q, uint32_t *cross_n) {
+    const int n_it = tn << psh;
+    for (int it0 = warp; it0 < n_it; it0 += G * kInvWarps) {
+        uint32_t row[G][kInvUnroll], wq[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int it = it0 + g * kInvWarps;
+            const int ti = min(it >> psh, tn - 1);
+            const uint32_t pc = (uint32_t)(it & ((1 << psh) - 1)), len = s_len[ti];
+            const bool ok = it < n_it && len - 1u < kLongList;
+            const uint32_t lo = ok ? (len * pc) >> psh : 0u, hi = ok ? (len * (pc + 1u)) >> psh : 0u;
+            const uint16_t *rows = post_row + base + s_beg[ti];
+            wq[g] = __float2uint_rn(s_w[ti] * fx_scale);
+#pragma unroll
+            for (int u = 0; u < kInvUnroll; ++u) {
+                const uint32_t o = lo + (uint32_t)lane + 32u * (uint32_t)u;
+                row[g][u] = o < hi ? (uint32_t)rows[o] : 0xffffffffu;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if constexpr (CROSS) {
+                uint32_t old[kInvUnroll];
+#pragma unroll
+                for (int u = 0; u < kInvUnroll; ++u) old[u] = row[g][u] != 0xffffffffu ? atomicAdd(&accu[row[g][u]], wq[g]) : 0xffffffffu;
+#pragma unroll
+                for (int u = 0; u < kInvUnroll; ++u)
+                    if (old[u] < tau_u && old[u] + wq[g] >= tau_u) {
+                        const uint32_t slot = atomicAdd(cross_n, 1u);
+                        if (slot < kCrossCap) cross_q[slot] = (uint16_t)row[g][u];
+                    }
+            } else {
+#pragma unroll
+                for (int u = 0; u < kInvUnroll; ++u)
+                    if (row[g][u] != 0xffffffffu) atomicAdd(&accu[row[g][u]], wq[g]);
+            }
+            // what a piece has beyond 32 * kInvUnroll postings goes the plain way
+            const int it = it0 + g * kInvWarps;
+            if (it < n_it) {
+                const int ti = it >> psh;
+                const uint32_t pc = (uint32_t)(it & ((1 << psh) - 1)), len = s_len[ti];
+                const uint32_t lo = (len * pc) >> psh, hi = (len * (pc + 1u)) >> psh;
+                if (len - 1u < kLongList && hi - lo > 32u * kInvUnroll)
+                    accumulate_slice_fixed<CROSS>(accu, post_row + base + s_beg[ti], lo + 32u * kInvUnroll + (uint32_t)lane, hi, 32u, wq[g], tau_u, cross_q, cross_n);
+            }
+        }
+    }
+}
+
 // A LONG list (more postings than kLongList: a popular token), worked on by all warps of the CTA.  Its full 256-posting
 // chunks are stored transposed (long_list_pos): a warp takes a chunk with ONE 16-byte load per lane (the scalar loop has 8
 // two-byte loads in flight per lane), lane l gets postings l, l + 32, ..., and the warp's j-th atomics go to consecutive
@@ -911,6 +969,11 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
             // short lists: one warp per list piece, round robin; few tokens -> lists are cut in 2 or 4 pieces so that
             // every warp gets about the same number of postings
             const int psh = tn >= 2 * NW ? 0 : (tn >= NW ? 1 : 2);   // 1, 2 or 4 pieces per list
+            // (fixed point, index without long lists: three pieces of a warp per load round trip; with the heavy-tailed lists
+            // of the LONG variant the grouping measured 7 % slower -- most of a piece is its tail there)
+            if (!LONG && cross) accumulate_pieces_fixed<true, VS_K3_GROUP>(accu, p.post_row, base, s_beg, s_len, s_w, fx_scale, tn, psh, warp, lane, cross_tau, s_queue, &s_cross_n);
+            else if (!LONG && fixed) accumulate_pieces_fixed<false, VS_K3_GROUP>(accu, p.post_row, base, s_beg, s_len, s_w, fx_scale, tn, psh, warp, lane, 0u, nullptr, nullptr);
+            else
             for (int it = warp; it < (tn << psh); it += NW) {
                 const int ti = it >> psh;
                 const uint32_t pc = (uint32_t)(it & ((1 << psh) - 1));
@@ -918,8 +981,8 @@ __global__ void __launch_bounds__(kInvThreads, 1) inv_search_kernel(const InvSea
                 if (len - 1u < kLongList) {
                     const uint32_t lo = (len * pc) >> psh, hi = (len * (pc + 1u)) >> psh;
                     const uint64_t at = base + s_beg[ti];
-                    if (cross) accumulate_slice_fixed<true>(accu, p.post_row + at, lo + lane, hi, 32u, __float2uint_rn(s_w[ti] * fx_scale), cross_tau, s_queue, &s_cross_n);
-                    else if (fixed) accumulate_slice_fixed<false>(accu, p.post_row + at, lo + lane, hi, 32u, __float2uint_rn(s_w[ti] * fx_scale), 0u, nullptr, nullptr);
+                    if (LONG && cross) accumulate_slice_fixed<true>(accu, p.post_row + at, lo + lane, hi, 32u, __float2uint_rn(s_w[ti] * fx_scale), cross_tau, s_queue, &s_cross_n);
+                    else if (LONG && fixed) accumulate_slice_fixed<false>(accu, p.post_row + at, lo + lane, hi, 32u, __float2uint_rn(s_w[ti] * fx_scale), 0u, nullptr, nullptr);
                     else accumulate_slice<VK>(acc, p.post_row + at, (const uint8_t *)p.post_val + at * vbytes, lo + lane, hi, 32u, s_w[ti]);
                 }
             }
